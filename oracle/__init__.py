@@ -1,0 +1,35 @@
+"""CPU oracle for the ParaDiag block-circulant preconditioner hot path.
+
+THIS PACKAGE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` may import it.  The product path
+(``optimal_control_paradiag_b200``) never imports it and has no CPU fallback.
+
+What it restates (all citations are into the read-only upstream checkout,
+``Code/Control_Wave_PC.py`` unless another file is named):
+
+* ``fem1d``        1-D uniform P1 mass / stiffness matrices (what Firedrake
+                   assembles for ``UnitIntervalMesh`` + ``CG1``, :17, :33, :42).
+* ``eigs``         circulant eigenvalues :387-388, the 2x2 blocks :418-419,
+                   ``np.linalg.eig`` / ``inv`` :421-425 and the closed forms.
+* ``pc_ref_route`` line-by-line restatement of ``DiagFFTPC.initialize`` /
+                   ``apply`` :380-553 (eig per k, S^-1, shifted solves, S,
+                   1/lambda_2, fft).
+* ``pc_explicit``  the explicit sparse block-circulant matrix P, factorised by
+                   SuperLU -- semantic ground truth at small sizes.
+* ``pc_fast``      the division-free decoupled form (same operator), used as
+                   the timed CPU baseline and the large-size checker.
+* ``pc_longdouble`` the same in 80-bit extended precision (conditioning).
+* ``operator``     the all-at-once matrix of ``Build_L`` :86-179 and the
+                   manufactured right-hand side of ``Build_f/g/IC`` :48-83.
+* ``gmres``        PETSc-KSPGMRES semantics selected by the options :347-359.
+
+PARITY UNPINNED.  The upstream repository holds no golden vectors, fixtures or
+recorded logs for PC-apply outputs or GMRES iteration counts, and none of
+Firedrake / petsc4py / MUMPS is installable in this image, so the upstream
+code itself cannot be run.  The only known-answer checks upstream are the
+numpy identities of ``Code/mat_test.ipynb`` (FFT convention, circulant
+eigenvalues, 2x2 diagonalisation); the oracle is pinned against those
+(``tests/test_oracle_notebook.py``) and, beyond them, only against itself
+(three independent routes agreeing to ~1e-13 at small sizes).
+"""
