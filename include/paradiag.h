@@ -1,0 +1,134 @@
+/*
+ * paradiag.h -- C ABI of libparadiag.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of Molin-Han/Optimal_Control_ParaDiag: the
+ * ParaDiag block-circulant preconditioner `DiagFFTPC` that
+ * Code/Control_Wave_PC.py applies inside the all-at-once GMRES solve of the 1-D
+ * wave-equation optimal-control system, plus the matvec / right-hand side /
+ * Krylov loop either side of it.  Every entry point names the upstream
+ * interface it replaces (file:line into the upstream checkout).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles; no torch / PETSc types.
+ *   - every function returns 0 on success, a negative pd_status otherwise;
+ *     pd_last_error() returns a thread-local message.  The library never
+ *     exits or aborts the process.
+ *   - vectors are complex128 (interleaved re, im) in the PETSc layout of the
+ *     reference: index(field f, node j, time i) = (f*n + j)*N_t + i with
+ *     f in {0 = state u, 1 = adjoint p}, n = N_x + 1 nodes, time fastest
+ *     (Control_Wave_PC.py:496-501: dat.data has shape (n, N_t), FFT on axis=1).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); work is
+ *     enqueued on it, the *_host variants synchronise before returning.
+ *   - the caller owns all vectors (torch tensors, PETSc Vecs); the library owns
+ *     only its workspace (pd_workspace_bytes).
+ */
+#ifndef PARADIAG_H
+#define PARADIAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_ABI_VERSION 1
+
+typedef enum pd_status {
+  PD_OK = 0,
+  PD_ERR_INVALID = -1,      /* bad argument / unsupported size              */
+  PD_ERR_CUDA = -2,         /* CUDA runtime error (message has the detail)  */
+  PD_ERR_NOMEM = -3,        /* workspace allocation failed                  */
+  PD_ERR_UNSUPPORTED = -4,  /* e.g. applyTranspose                          */
+  PD_ERR_NOT_CONVERGED = -5 /* pd_gmres hit max_it (x still holds iterate)  */
+} pd_status;
+
+/* Problem description.  Replaces the module globals the upstream PC reads
+ * (Control_Wave_PC.py:335-339 T, N_t, N_x, gamma; :362-368 dt, W, bcs).       */
+typedef struct pd_config {
+  int32_t abi_version; /* = PD_ABI_VERSION                                       */
+  int32_t N_x;         /* cells of UnitIntervalMesh (:17, :337); n = N_x+1 nodes */
+  int32_t N_t;         /* time levels (:336)                                     */
+  int32_t bug138;      /* 1: keep the sqrt(gamma) factor on the last state row's
+                          stiffness term exactly as upstream :138 (default);
+                          0: drop it.  Only affects pd_matvec.                   */
+  double T;            /* final time (:335)                                      */
+  double gamma;        /* regulariser (:339); the sqrt(gamma) scaling of the
+                          pc=True formulation is built in (:56-57, :78-80, :87)  */
+  double alpha;        /* alpha-circulant weight; 1.0 = the upstream operator.
+                          Other values are an extension with no upstream pin.   */
+  int32_t device;      /* CUDA device ordinal                                    */
+  /* Frequency shard solved by this handle in pd_stage_solve (multi-GPU):
+   * global frequencies [k_begin, k_begin + k_count).  k_count = 0 means all.   */
+  int32_t k_begin;
+  int32_t k_count;
+  /* Node slab transformed by this handle in pd_stage_fft (multi-GPU):
+   * n_local lines per field.  0 means all n = N_x + 1 nodes.                    */
+  int32_t n_local;
+  int32_t reserved[5];
+} pd_config;
+
+typedef struct pd_handle pd_handle;
+
+/* Lifetime.  pd_create replaces DiagFFTPC.initialize (:380-484): instead of the
+ * per-k numpy eig/inv loop (:415-436) and the MUMPS factorisation (:481-484) it
+ * allocates the workspace and the time-twiddle table; all per-frequency
+ * coefficients are regenerated inside the kernels.                              */
+int pd_create(const pd_config* cfg, pd_handle** out);
+int pd_destroy(pd_handle* h);
+const char* pd_last_error(void);
+int pd_abi_version(void);
+size_t pd_workspace_bytes(const pd_handle* h);
+/* number of kernels launched through this handle since creation                */
+int64_t pd_launch_count(const pd_handle* h);
+
+/* DiagFFTPC.apply (:491-553): y = P^-1 x, device pointers.  x and y may alias.  */
+int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+/* Same with host buffers (PETSc Vec arrays): H2D, apply, D2H, synchronises.     */
+int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host);
+/* DiagFFTPC.applyTranspose (:557-558): upstream raises NotImplementedError;
+ * this returns PD_ERR_UNSUPPORTED.                                              */
+int pd_pc_apply_transpose(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+
+/* The three stages of the apply, exposed for the multi-GPU path (spatial slabs
+ * for the FFTs, frequency slabs for the solves, an all-to-all in between).
+ *   pd_stage_fft   : batched time-axis DFT of `nlines` contiguous lines of
+ *                    length N_t.  inverse != 0: scipy ifft (:500-501, 1/N_t,
+ *                    e^{+i..}); inverse == 0: scipy fft (:547-548).  in == out ok.
+ *   pd_stage_solve : in place on w = [u-hat ; p-hat], shape (2, n, k_count),
+ *                    frequency fastest: S^-1 rotation (:445-457), the 2*k_count
+ *                    shifted tridiagonal solves with Dirichlet rows (:460-484,
+ *                    :512), S rotation (:516-529) and 1/lambda_2 (:532-540).     */
+int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines,
+                 int inverse, void* stream);
+int pd_stage_solve(pd_handle* h, void* w_dev, void* stream);
+
+/* Matrix-free action of the Jacobian of Build_L (:86-179, pc=True branches):
+ * y = A x with Dirichlet rows as identity.  x and y must not alias.             */
+int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+
+/* Right-hand side of the manufactured problem, Build_f / Build_g /
+ * Build_Initial_Condition (:48-83) folded through the residual (:118, :139,
+ * :144, :93-95): b such that the ksponly solve is A U = b.                      */
+int pd_build_rhs(pd_handle* h, void* b_dev, void* stream);
+
+/* KSP GMRES as configured at :347-359 (left PC, classical Gram-Schmidt, zero
+ * initial guess, preconditioned-residual test against rtol*||P^-1 b||).
+ *   hist      : optional, length max_it+1, receives the residual-norm history
+ *               (what -ksp_monitor prints); hist[0] = ||P^-1 b||.
+ *   its       : Krylov iterations taken.
+ *   reason    : PETSc-style converged reason (2 = RTOL, 3 = ATOL, -3 = ITS).
+ * Returns PD_OK when converged, PD_ERR_NOT_CONVERGED at max_it.                 */
+int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol,
+             int restart, int max_it, int* its, double* hist, int* reason,
+             void* stream);
+
+/* Batched reductions used by the multi-GPU Krylov loop (device results):
+ * out[i] = sum_j conj(V[i*ld + j]) * w[j], i < nv  (PETSc VecMDot order).       */
+int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* w_dev,
+            int64_t len, void* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARADIAG_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of ``libparadiag.so`` (the C ABI of ``include/paradiag.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or ``make`` in ``csrc/``).
+Loading fails loudly when it is missing: the product path has no fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libparadiag.so"
+PD_ABI_VERSION = 1
+
+PD_OK, PD_ERR_INVALID, PD_ERR_CUDA, PD_ERR_NOMEM, PD_ERR_UNSUPPORTED, PD_ERR_NOT_CONVERGED = 0, -1, -2, -3, -4, -5
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+class ParaDiagError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libparadiag error {status}: {message}")
+        self.status = status
+
+
+class pd_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("N_x", C.c_int32), ("N_t", C.c_int32), ("bug138", C.c_int32),
+        ("T", C.c_double), ("gamma", C.c_double), ("alpha", C.c_double),
+        ("device", C.c_int32), ("k_begin", C.c_int32), ("k_count", C.c_int32), ("n_local", C.c_int32),
+        ("reserved", C.c_int32 * 5),
+    ]
+
+
+# every symbol include/paradiag.h declares: name -> (restype, argtypes)
+_VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SYMBOLS = {
+    "pd_create": (_I, [C.POINTER(pd_config), C.POINTER(_VP)]),
+    "pd_destroy": (_I, [_VP]),
+    "pd_last_error": (C.c_char_p, []),
+    "pd_abi_version": (_I, []),
+    "pd_workspace_bytes": (C.c_size_t, [_VP]),
+    "pd_launch_count": (_I64, [_VP]),
+    "pd_pc_apply": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_pc_apply_host": (_I, [_VP, _VP, _VP]),
+    "pd_pc_apply_transpose": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_stage_fft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
+    "pd_stage_solve": (_I, [_VP, _VP, _VP]),
+    "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_build_rhs": (_I, [_VP, _VP, _VP]),
+    "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
+    "pd_mdot": (_I, [_VP, _VP, _I64, _I, _VP, _I64, _VP, _VP]),
+}
+
+_lib = None
+
+
+def library_path():
+    return os.environ.get("PARADIAG_LIB", os.path.join(_HERE, _LIBNAME))
+
+
+def load_library():
+    """Load libparadiag.so and type every entry point.  Raises LibraryNotBuilt if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryNotBuilt(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C optimal_control_paradiag_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pd_abi_version() != PD_ABI_VERSION:
+        raise LibraryNotBuilt(f"{path}: ABI version {lib.pd_abi_version()} != {PD_ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status, allow=()):
+    if status != PD_OK and status not in allow:
+        raise ParaDiagError(status, load_library().pd_last_error().decode())
+    return status

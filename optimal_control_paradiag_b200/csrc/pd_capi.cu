@@ -1,0 +1,197 @@
+// C ABI of libparadiag.so: handle lifetime and the DiagFFTPC entry points.
+// See include/paradiag.h for the contract and the upstream lines each call replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include "pd_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pd_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void pd_krylov_free(pd_handle* h);
+
+extern "C" const char* pd_last_error(void) { return g_err; }
+extern "C" int pd_abi_version(void) { return PD_ABI_VERSION; }
+extern "C" size_t pd_workspace_bytes(const pd_handle* h) { return h ? h->ws_bytes : 0; }
+extern "C" int64_t pd_launch_count(const pd_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int pd_destroy(pd_handle* h) {
+  if (!h) return PD_OK;
+  cudaSetDevice(h->cfg.device);
+  pd_krylov_free(h);
+  if (h->twiddle) cudaFree(h->twiddle);
+  if (h->red) cudaFree(h->red);
+  if (h->zsep) cudaFree(h->zsep);
+  if (h->work) cudaFree(h->work);
+  if (h->stage_x) cudaFree(h->stage_x);
+  if (h->stage_y) cudaFree(h->stage_y);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return PD_OK;
+}
+
+extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
+  if (!cfg || !out) {
+    pd_set_error("pd_create: null argument");
+    return PD_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != PD_ABI_VERSION) {
+    pd_set_error("pd_create: ABI version mismatch (caller %d, library %d)", cfg->abi_version, PD_ABI_VERSION);
+    return PD_ERR_INVALID;
+  }
+  if (cfg->N_x < 2 || cfg->N_t < 3) {
+    pd_set_error("pd_create: need N_x >= 2 and N_t >= 3 (got %d, %d)", cfg->N_x, cfg->N_t);
+    return PD_ERR_INVALID;
+  }
+  if (!(cfg->T > 0.0) || !(cfg->gamma > 0.0)) {
+    pd_set_error("pd_create: T and gamma must be positive");
+    return PD_ERR_INVALID;
+  }
+  if (cfg->alpha != 1.0) {
+    pd_set_error("pd_create: alpha = %g is not supported; the upstream preconditioner is the alpha = 1 "
+                 "block circulant and has no alpha", cfg->alpha);
+    return PD_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    pd_set_error("pd_create: no CUDA device available (%s); libparadiag has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return PD_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    pd_set_error("pd_create: device %d out of range (%d devices)", cfg->device, ndev);
+    return PD_ERR_INVALID;
+  }
+  PD_CUDA(cudaSetDevice(cfg->device));
+  pd_handle* h = new pd_handle();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->n = cfg->N_x + 1;
+  h->m = cfg->N_x - 1;
+  h->kbegin = cfg->k_count > 0 ? cfg->k_begin : 0;
+  h->kcount = cfg->k_count > 0 ? cfg->k_count : cfg->N_t;
+  h->nloc = cfg->n_local > 0 ? cfg->n_local : h->n;
+  if (h->kbegin < 0 || h->kbegin + h->kcount > cfg->N_t) {
+    pd_set_error("pd_create: frequency shard [%d, %d) outside [0, %d)", h->kbegin, h->kbegin + h->kcount,
+                 cfg->N_t);
+    delete h;
+    return PD_ERR_INVALID;
+  }
+  h->dt = cfg->T / cfg->N_t;
+  h->h = 1.0 / cfg->N_x;
+  h->c = h->dt * h->dt / sqrt(cfg->gamma);
+  cudaDeviceProp prop;
+  PD_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  h->num_sms = prop.multiProcessorCount;
+  int rc = pd_fft_plan(h);
+  if (rc == PD_OK) rc = pd_solve_plan(h);
+  if (rc != PD_OK) {
+    pd_destroy(h);
+    return rc;
+  }
+  PD_CUDA(cudaDeviceSynchronize());
+  *out = h;
+  return PD_OK;
+}
+
+static int ensure_work(pd_handle* h) {
+  if (!h->work) {
+    size_t bytes = sizeof(cplx) * 2 * (size_t)h->n * h->cfg.N_t;
+    cudaError_t e = cudaMalloc(&h->work, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      pd_set_error("workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+      return PD_ERR_NOMEM;
+    }
+    h->ws_bytes += bytes;
+  }
+  return PD_OK;
+}
+
+extern "C" int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int inverse,
+                            void* stream) {
+  if (!h || !in_dev || !out_dev || nlines < 0) {
+    pd_set_error("pd_stage_fft: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_fft_launch(h, (const cplx*)in_dev, (cplx*)out_dev, nlines, inverse, (cudaStream_t)stream);
+}
+
+extern "C" int pd_stage_solve(pd_handle* h, void* w_dev, void* stream) {
+  if (!h || !w_dev) {
+    pd_set_error("pd_stage_solve: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev) {
+    pd_set_error("pd_pc_apply: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
+    pd_set_error("pd_pc_apply: handle is sharded (k_count/n_local set); use the stage API");
+    return PD_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_work(h);
+  if (rc) return rc;
+  const int64_t nlines = 2 * (int64_t)h->n;
+  // :500-501 ifft along time, :445-540 per-frequency stage, :547-548 fft along time
+  if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st))) return rc;
+  if ((rc = pd_solve_launch(h, h->work, st))) return rc;
+  if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
+  return PD_OK;
+}
+
+extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {
+  pd_set_error("applyTranspose is not implemented (the upstream PC raises NotImplementedError)");
+  return PD_ERR_UNSUPPORTED;
+}
+
+extern "C" int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host) {
+  if (!h || !x_host || !y_host) {
+    pd_set_error("pd_pc_apply_host: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  PD_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t bytes = sizeof(cplx) * 2 * (size_t)h->n * h->cfg.N_t;
+  if (!h->stage_x) {
+    PD_CUDA(cudaMalloc(&h->stage_x, bytes));
+    h->ws_bytes += bytes;
+  }
+  if (!h->own_stream) PD_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = h->own_stream;
+  PD_CUDA(cudaMemcpyAsync(h->stage_x, x_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = pd_pc_apply(h, h->stage_x, h->stage_x, st);
+  if (rc) return rc;
+  PD_CUDA(cudaMemcpyAsync(y_host, h->stage_x, bytes, cudaMemcpyDeviceToHost, st));
+  PD_CUDA(cudaStreamSynchronize(st));
+  return PD_OK;
+}
+
+extern "C" int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev || x_dev == y_dev) {
+    pd_set_error("pd_matvec: invalid argument (x and y must be distinct device vectors)");
+    return PD_ERR_INVALID;
+  }
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pd_build_rhs(pd_handle* h, void* b_dev, void* stream) {
+  if (!h || !b_dev) {
+    pd_set_error("pd_build_rhs: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_rhs_launch(h, (cplx*)b_dev, (cudaStream_t)stream);
+}

@@ -1,0 +1,120 @@
+// Shared device/host helpers for libparadiag (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "paradiag.h"
+
+typedef double2 cplx;  // x = re, y = im; 16-byte aligned -> 128-bit loads/stores
+
+// ---------------------------------------------------------------- complex math
+__host__ __device__ __forceinline__ cplx cmake(double re, double im) { return make_double2(re, im); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cneg(cplx a) { return cmake(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return cmake(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
+  return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// acc + a*b
+__host__ __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx acc) {
+  return cmake(acc.x + a.x * b.x - a.y * b.y, acc.y + a.x * b.y + a.y * b.x);
+}
+// acc - a*b
+__host__ __device__ __forceinline__ cplx cfms(cplx a, cplx b, cplx acc) {
+  return cmake(acc.x - a.x * b.x + a.y * b.y, acc.y - a.x * b.y - a.y * b.x);
+}
+// multiply by +i / -i
+__host__ __device__ __forceinline__ cplx cmuli(cplx a) { return cmake(-a.y, a.x); }
+__host__ __device__ __forceinline__ cplx cmulni(cplx a) { return cmake(a.y, -a.x); }
+__host__ __device__ __forceinline__ cplx crcp(cplx a) {
+  double d = 1.0 / (a.x * a.x + a.y * a.y);
+  return cmake(a.x * d, -a.y * d);
+}
+
+// ------------------------------------------------------------- error handling
+void pd_set_error(const char* fmt, ...);
+
+#define PD_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      pd_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                   cudaGetErrorString(_e));                                        \
+      return PD_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+#define PD_CHECK_LAUNCH()                                                          \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      pd_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,        \
+                   cudaGetErrorString(_e));                                        \
+      return PD_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------ the handle
+static const int PD_MAX_FFT_PASSES = 16;
+
+struct pd_handle {
+  pd_config cfg;
+  int n;         // nodes = N_x + 1
+  int m;         // interior nodes = N_x - 1
+  int kcount;    // frequencies solved by this handle
+  int kbegin;
+  int nloc;      // node lines per field transformed by this handle
+  double dt, h, c;
+  int num_sms;
+  size_t ws_bytes;
+  int64_t launches;
+
+  // FFT plan
+  cplx* twiddle;  // e^{-2 pi i j / N_t}, j < N_t
+  int fft_kind;   // 0 generic smem Stockham, 1 power-of-two register kernel
+  int npass;
+  int radix[PD_MAX_FFT_PASSES];
+
+  // solve-stage partition
+  int L;       // chunk length
+  int P;       // separators (interface unknowns per system)
+  int Llast;   // rows in the last chunk
+  cplx* red;   // [P+1][4][kcount]  chunk functionals (f+, l+, f-, l-)
+  cplx* zsep;  // [P][2][kcount]    interface solutions (zeta+, conj-form zeta-)
+
+  // work vector (2, n, N_t) for the single-GPU apply
+  cplx* work;
+
+  // host staging for the *_host entry points
+  cplx* stage_x;
+  cplx* stage_y;
+  void* pinned;
+  size_t pinned_bytes;
+
+  // Krylov workspace (lazily allocated)
+  cplx* kry_V;      // basis vectors, allocated in blocks
+  int kry_cap;
+  cplx* kry_w;
+  cplx* kry_t;
+  cplx* kry_partial;
+  cplx* kry_h;
+  double* kry_host;
+  cudaStream_t own_stream;
+};
+
+// stage launchers implemented in the .cu files
+int pd_fft_plan(pd_handle* h);
+int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
+                  cudaStream_t st);
+int pd_solve_plan(pd_handle* h);
+int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st);
+int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st);
+int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st);

@@ -1,0 +1,351 @@
+// Batched time-axis DFT kernels (complex128) for sm_100a.
+//
+// Replaces scipy.fft.ifft / fft along axis=1 in DiagFFTPC.apply
+// (Control_Wave_PC.py:500-501 and :547-548).  Convention (mat_test.ipynb cells
+// 5-9): forward = sum_j x_j e^{-2 pi i jk/N}, inverse = (1/N) sum_j x_j e^{+2 pi i jk/N}.
+//
+// Two implementations behind pd_fft_launch:
+//   kind 1  power-of-two N_t: register-resident radix-16/8/4/2 Stockham passes,
+//           one shared-memory exchange between passes (padded against bank
+//           conflicts), coalesced 128-bit global loads in the first pass and
+//           stores in the last.
+//   kind 0  any other N_t (the upstream default is 81 = 3^4): mixed-radix
+//           Stockham with direct (O(R) per output) passes ping-ponging between
+//           two shared-memory buffers; prime factors of any size are accepted.
+#include "pd_common.cuh"
+
+// ------------------------------------------------------------ twiddle table
+__global__ void pd_twiddle_kernel(cplx* tw, int N) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) {
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)N, &s, &c);
+    tw[j] = cmake(c, s);
+  }
+}
+
+struct PassList {
+  int n;
+  int r[PD_MAX_FFT_PASSES];
+};
+
+// ------------------------------------------------------------ generic kernel
+template <bool INV>
+__global__ void __launch_bounds__(256)
+pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N,
+                      int64_t nlines, const cplx* __restrict__ tw, PassList pl, double scale) {
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  cplx* buf0 = reinterpret_cast<cplx*>(pd_smem_raw);
+  cplx* buf1 = buf0 + N;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int64_t line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const cplx* src_g = in + line * (int64_t)N;
+    cplx* dst_g = out + line * (int64_t)N;
+    for (int i = tid; i < N; i += nth) buf0[i] = src_g[i];
+    __syncthreads();
+    cplx* s = buf0;
+    cplx* d = buf1;
+    int Ns = 1;
+    for (int p = 0; p < pl.n; ++p) {
+      const int R = pl.r[p];
+      const int NR = N / R;
+      const int tws = N / (Ns * R);
+      const bool last = (p == pl.n - 1);
+      for (int o = tid; o < N; o += nth) {
+        int jl = o % Ns, t = o / Ns;
+        int r = t % R, jh = t / R;
+        int j = jh * Ns + jl;
+        int step = (int)(((int64_t)jl * tws + (int64_t)r * NR) % N);
+        int e = 0;
+        cplx acc = cmake(0.0, 0.0);
+        for (int q = 0; q < R; ++q) {
+          cplx w = tw[e];
+          if (INV) w.y = -w.y;
+          acc = cfma(s[j + q * NR], w, acc);
+          e += step;
+          if (e >= N) e -= N;
+        }
+        if (last)
+          dst_g[o] = cscale(acc, scale);
+        else
+          d[o] = acc;
+      }
+      __syncthreads();
+      cplx* tmp = s; s = d; d = tmp;
+      Ns *= R;
+    }
+  }
+}
+
+// ------------------------------------------------- power-of-two register kernel
+// Small DFTs on registers (forward sign; the inverse transform conjugates on
+// load and store).
+__device__ __forceinline__ void bf2(cplx& a, cplx& b) {
+  cplx t = csub(a, b);
+  a = cadd(a, b);
+  b = t;
+}
+template <int R>
+__device__ __forceinline__ void dft_pow2(cplx* v);
+template <>
+__device__ __forceinline__ void dft_pow2<2>(cplx* v) { bf2(v[0], v[1]); }
+template <>
+__device__ __forceinline__ void dft_pow2<4>(cplx* v) {
+  bf2(v[0], v[2]);
+  bf2(v[1], v[3]);
+  v[3] = cmulni(v[3]);  // * -i
+  bf2(v[0], v[1]);
+  bf2(v[2], v[3]);
+  // outputs in bit-reversed order: v0, v2, v1, v3 -> fix
+  cplx t = v[1]; v[1] = v[2]; v[2] = t;
+}
+template <>
+__device__ __forceinline__ void dft_pow2<8>(cplx* v) {
+  const double r = 0.70710678118654752440;
+  bf2(v[0], v[4]); bf2(v[1], v[5]); bf2(v[2], v[6]); bf2(v[3], v[7]);
+  v[5] = cmake((v[5].x + v[5].y) * r, (v[5].y - v[5].x) * r);    // * e^{-i pi/4}
+  v[6] = cmulni(v[6]);                                           // * -i
+  v[7] = cmake((v[7].y - v[7].x) * r, (-v[7].x - v[7].y) * r);   // * e^{-3i pi/4}
+  bf2(v[0], v[2]); bf2(v[1], v[3]); bf2(v[4], v[6]); bf2(v[5], v[7]);
+  v[3] = cmulni(v[3]); v[7] = cmulni(v[7]);
+  bf2(v[0], v[1]); bf2(v[2], v[3]); bf2(v[4], v[5]); bf2(v[6], v[7]);
+  // bit reversal of 3 bits: 1<->4, 3<->6
+  cplx t = v[1]; v[1] = v[4]; v[4] = t;
+  t = v[3]; v[3] = v[6]; v[6] = t;
+}
+template <>
+__device__ __forceinline__ void dft_pow2<16>(cplx* v) {
+  // 4 x 4 decomposition: columns, twiddle W16^{ab}, rows.
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+  const double r = 0.70710678118654752440;
+  cplx a[4][4];
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) {
+    cplx t[4] = {v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]};
+    dft_pow2<4>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) a[k1][n2] = t[k1];
+  }
+  // twiddles W16^{k1*n2}
+  a[1][1] = cmul(a[1][1], cmake(c1, -s1));
+  a[1][2] = cmake((a[1][2].x + a[1][2].y) * r, (a[1][2].y - a[1][2].x) * r);
+  a[1][3] = cmul(a[1][3], cmake(s1, -c1));
+  a[2][1] = cmake((a[2][1].x + a[2][1].y) * r, (a[2][1].y - a[2][1].x) * r);
+  a[2][2] = cmulni(a[2][2]);
+  a[2][3] = cmake((a[2][3].y - a[2][3].x) * r, (-a[2][3].x - a[2][3].y) * r);
+  a[3][1] = cmul(a[3][1], cmake(s1, -c1));
+  a[3][2] = cmake((a[3][2].y - a[3][2].x) * r, (-a[3][2].x - a[3][2].y) * r);
+  a[3][3] = cmul(a[3][3], cmake(-c1, s1));  // W16^9 = e^{-9 i pi/8} = (-c1, +s1)
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    cplx t[4] = {a[k1][0], a[k1][1], a[k1][2], a[k1][3]};
+    dft_pow2<4>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = t[k2];
+  }
+}
+
+// padded shared-memory index: one 16-byte pad every 16 elements
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+// One Stockham pass of radix R over the 16 elements this thread owns.
+// src/dst: either shared (padded) or global (first load / last store).
+template <int R, bool INV, bool FIRST, bool LAST>
+__device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
+                                          cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
+                                          int t, int T, double scale, bool live) {
+  constexpr int NB = 16 / R;  // butterflies per thread
+  const int NR = N / R;
+  const int tws = N / (Ns * R);
+  cplx v[NB][R];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const int j = t + u * T;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      cplx x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
+      if (FIRST && INV) x.y = -x.y;
+      v[u][q] = x;
+    }
+  }
+  if (!FIRST) {
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int j = t + u * T;
+      const int jl = j & (Ns - 1);
+      if (R == 2) {
+        v[u][1] = cmul(v[u][1], tw[jl * tws]);
+      } else {
+        // powers of w = W_{Ns R}^{jl}: table look-up for w, w^2, w^3 ..., depth-limited products
+        const cplx w1 = tw[jl * tws];
+        cplx w[R];
+        w[1] = w1;
+#pragma unroll
+        for (int q = 2; q < R; ++q) w[q] = (q & 1) ? cmul(w[q - 1], w1) : cmul(w[q / 2], w[q / 2]);
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[u][q] = cmul(v[u][q], w[q]);
+      }
+    }
+    __syncthreads();  // all reads of sm done before anyone overwrites it
+  }
+#pragma unroll
+  for (int u = 0; u < NB; ++u) dft_pow2<R>(v[u]);
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const int j = t + u * T;
+    const int base = (j / Ns) * Ns * R + (j & (Ns - 1));
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cplx x = v[u][r];
+      if (LAST) {
+        if (INV) x.y = -x.y;
+        if (live) gdst[base + r * Ns] = cscale(x, scale);
+      } else {
+        sm[pad16(base + r * Ns)] = x;
+      }
+    }
+  }
+  if (!LAST) __syncthreads();
+}
+
+// N = R0 * R1 * R2 * R3 (unused radices = 1); T = N/16 threads per line,
+// LPB lines per block.
+template <int R0, int R1, int R2, int R3, bool INV>
+__global__ void __launch_bounds__(512)
+pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
+                   const cplx* __restrict__ tw, double scale) {
+  constexpr int N = R0 * R1 * R2 * R3;
+  constexpr int T = N / 16;
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  const int lpb = blockDim.x / T;
+  const int lane_line = threadIdx.x / T;
+  const int t = threadIdx.x - lane_line * T;
+  cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw) + (size_t)lane_line * (N + N / 16);
+  for (int64_t line0 = (int64_t)blockIdx.x * lpb; line0 < nlines; line0 += (int64_t)gridDim.x * lpb) {
+    const int64_t line = line0 + lane_line;
+    // whole block must take the same path through __syncthreads: clamp the line
+    const int64_t ln = line < nlines ? line : nlines - 1;
+    const cplx* gsrc = in + ln * N;
+    cplx* gdst = out + ln * N;
+    // a partially filled last block still runs every pass (block-wide barriers)
+    // on the clamped line and only skips the final store
+    const bool live = line < nlines;
+    constexpr bool L0 = (R1 == 1);
+    pow2_pass<R0, INV, true, L0>(gsrc, gdst, sm, tw, N, 1, t, T, scale, live);
+    if (R1 > 1) {
+      constexpr bool L1 = (R2 == 1);
+      pow2_pass<(R1 > 1 ? R1 : 2), INV, false, L1>(gsrc, gdst, sm, tw, N, R0, t, T, scale, live);
+    }
+    if (R2 > 1) {
+      constexpr bool L2 = (R3 == 1);
+      pow2_pass<(R2 > 1 ? R2 : 2), INV, false, L2>(gsrc, gdst, sm, tw, N, R0 * R1, t, T, scale, live);
+    }
+    if (R3 > 1) {
+      pow2_pass<(R3 > 1 ? R3 : 2), INV, false, true>(gsrc, gdst, sm, tw, N, R0 * R1 * R2, t, T, scale, live);
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------- host side
+static void factorize(int N, PassList& pl) {
+  pl.n = 0;
+  int rem = N;
+  const int pref[] = {16, 8, 4, 2, 3, 5, 7};
+  for (int f : pref)
+    while (rem % f == 0 && rem > 1 && pl.n < PD_MAX_FFT_PASSES - 1) {
+      pl.r[pl.n++] = f;
+      rem /= f;
+    }
+  for (int f = 11; rem > 1 && pl.n < PD_MAX_FFT_PASSES - 1; f += 2)
+    while (rem % f == 0 && pl.n < PD_MAX_FFT_PASSES - 1) {
+      pl.r[pl.n++] = f;
+      rem /= f;
+    }
+  if (rem > 1) pl.r[pl.n++] = rem;
+  if (pl.n == 0) pl.r[pl.n++] = 1;
+}
+
+static bool is_pow2(int N) { return N > 0 && (N & (N - 1)) == 0; }
+
+int pd_fft_plan(pd_handle* h) {
+  const int N = h->cfg.N_t;
+  PD_CUDA(cudaMalloc(&h->twiddle, sizeof(cplx) * (size_t)N));
+  h->ws_bytes += sizeof(cplx) * (size_t)N;
+  pd_twiddle_kernel<<<(N + 255) / 256, 256>>>(h->twiddle, N);
+  PD_CHECK_LAUNCH();
+  PassList pl;
+  factorize(N, pl);
+  h->npass = pl.n;
+  for (int i = 0; i < pl.n; ++i) h->radix[i] = pl.r[i];
+  h->fft_kind = (is_pow2(N) && N >= 64 && N <= 8192) ? 1 : 0;
+  if (h->fft_kind == 0) {
+    size_t smem = 2 * sizeof(cplx) * (size_t)N;
+    if (smem > 227 * 1024) {
+      pd_set_error("N_t = %d is not supported by the time-axis FFT (needs %zu bytes of shared memory)", N,
+                   smem);
+      return PD_ERR_INVALID;
+    }
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  }
+  return PD_OK;
+}
+
+template <int R0, int R1, int R2, int R3>
+static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
+                       cudaStream_t st) {
+  constexpr int N = R0 * R1 * R2 * R3;
+  constexpr int T = N / 16;
+  int threads = T < 256 ? 256 : T;
+  int lpb = threads / T;
+  size_t smem = (size_t)lpb * (N + N / 16) * sizeof(cplx);
+  int64_t nblk = (nlines + lpb - 1) / lpb;
+  double scale = inverse ? 1.0 / (double)N : 1.0;
+  if (inverse) {
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
+  } else {
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
+  }
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
+                  cudaStream_t st) {
+  const int N = h->cfg.N_t;
+  if (nlines <= 0) return PD_OK;
+  if (h->fft_kind == 1) {
+    switch (N) {
+      case 64:   return launch_pow2<16, 4, 1, 1>(h, in, out, nlines, inverse, st);
+      case 128:  return launch_pow2<16, 8, 1, 1>(h, in, out, nlines, inverse, st);
+      case 256:  return launch_pow2<16, 16, 1, 1>(h, in, out, nlines, inverse, st);
+      case 512:  return launch_pow2<16, 8, 4, 1>(h, in, out, nlines, inverse, st);
+      case 1024: return launch_pow2<16, 16, 4, 1>(h, in, out, nlines, inverse, st);
+      case 2048: return launch_pow2<16, 16, 8, 1>(h, in, out, nlines, inverse, st);
+      case 4096: return launch_pow2<16, 16, 16, 1>(h, in, out, nlines, inverse, st);
+      case 8192: return launch_pow2<16, 16, 8, 4>(h, in, out, nlines, inverse, st);
+      default: break;
+    }
+  }
+  PassList pl;
+  pl.n = h->npass;
+  for (int i = 0; i < pl.n; ++i) pl.r[i] = h->radix[i];
+  size_t smem = 2 * sizeof(cplx) * (size_t)N;
+  int64_t nblk = nlines < (int64_t)h->num_sms * 8 ? nlines : (int64_t)h->num_sms * 8;
+  double scale = inverse ? 1.0 / (double)N : 1.0;
+  if (inverse)
+    pd_fft_generic_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale);
+  else
+    pd_fft_generic_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}

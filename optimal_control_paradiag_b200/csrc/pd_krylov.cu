@@ -1,0 +1,573 @@
+// All-at-once matvec, manufactured right-hand side and the device-resident
+// GMRES loop (complex128, sm_100a).
+//
+//   pd_matvec_launch : Jacobian action of Build_L, Control_Wave_PC.py:86-179
+//                      (pc=True branches), Dirichlet rows as identity.
+//   pd_rhs_launch    : Build_f / Build_g / Build_Initial_Condition (:48-83)
+//                      folded through the residual (:118, :139, :144, :93-95).
+//   pd_gmres         : KSPGMRES as configured at :347-359 (left PC, classical
+//                      Gram-Schmidt without refinement, zero initial guess,
+//                      preconditioned-residual test relative to ||P^-1 b||).
+#include <math.h>
+
+#include <vector>
+
+#include "pd_common.cuh"
+
+// --------------------------------------------------------------------- matvec
+struct OpParams {
+  int n, N_t;
+  double h, dt2h;  // dt^2 / 2
+  double c;        // dt^2 / sqrt(gamma)
+  double qlast;    // sqrt(gamma) if bug138 else 1
+  int64_t plane;
+};
+
+__device__ __forceinline__ cplx ld_or_zero(const cplx* __restrict__ v, int j, int i, const OpParams& op) {
+  // Dirichlet columns are dropped: boundary-node values never enter interior rows
+  if (j < 1 || j > op.n - 2 || i < 0 || i >= op.N_t) return cmake(0, 0);
+  return v[(int64_t)j * op.N_t + i];
+}
+
+__global__ void __launch_bounds__(256)
+pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= op.N_t) return;
+  const cplx* u = x;
+  const cplx* p = x + op.plane;
+  const int64_t o = (int64_t)j * op.N_t + i;
+  if (j == 0 || j == op.n - 1) {
+    y[o] = u[o];
+    y[op.plane + o] = p[o];
+    return;
+  }
+  const double m_off = op.h / 6.0, m_dia = 2.0 * op.h / 3.0;
+  const double k_off = -1.0 / op.h, k_dia = 2.0 / op.h;
+  const double d_i = (i == 0) ? 0.5 : 1.0;               // :117
+  const double e_i = (i == op.N_t - 1) ? 0.5 : 1.0;      // :143
+  const double q_i = (i == op.N_t - 1) ? op.qlast : 1.0; // :138
+  cplx yu = cmake(0, 0), yp = cmake(0, 0);
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj) {
+    const double mw = dj == 0 ? m_dia : m_off;
+    const double kw = dj == 0 ? k_dia : k_off;
+    const int jj = j + dj;
+    const cplx u0 = ld_or_zero(u, jj, i, op), u1 = ld_or_zero(u, jj, i - 1, op),
+               u2 = ld_or_zero(u, jj, i - 2, op);
+    const cplx p0 = ld_or_zero(p, jj, i, op), p1 = ld_or_zero(p, jj, i + 1, op),
+               p2 = ld_or_zero(p, jj, i + 2, op);
+    // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
+    const double cu_m = mw, cu_k = q_i * op.dt2h * kw;
+    yu.x += cu_m * (u0.x - 2.0 * u1.x + u2.x) + cu_k * (u0.x + u2.x) - d_i * op.c * mw * p0.x;
+    yu.y += cu_m * (u0.y - 2.0 * u1.y + u2.y) + cu_k * (u0.y + u2.y) - d_i * op.c * mw * p0.y;
+    // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
+    const double cp_k = op.dt2h * kw;
+    yp.x += e_i * op.c * mw * u0.x + mw * (p0.x - 2.0 * p1.x + p2.x) + cp_k * (p0.x + p2.x);
+    yp.y += e_i * op.c * mw * u0.y + mw * (p0.y - 2.0 * p1.y + p2.y) + cp_k * (p0.y + p2.y);
+  }
+  y[o] = yu;
+  y[op.plane + o] = yp;
+}
+
+int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st) {
+  OpParams op;
+  op.n = h->n; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
+  op.qlast = h->cfg.bug138 ? sqrt(h->cfg.gamma) : 1.0;
+  op.plane = (int64_t)h->n * h->cfg.N_t;
+  dim3 grid((op.N_t + 255) / 256, h->n);
+  pd_matvec_kernel<<<grid, 256, 0, st>>>(x, y, op);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// ------------------------------------------------------------------------ rhs
+struct RhsParams {
+  int n, N_t, N_x;
+  double h, dt, T, gamma;
+  int64_t plane;
+};
+
+__global__ void __launch_bounds__(256)
+pd_rhs_kernel(cplx* __restrict__ b, RhsParams rp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= rp.N_t) return;
+  const int64_t o = (int64_t)j * rp.N_t + i;
+  if (j == 0 || j == rp.n - 1) {
+    b[o] = cmake(0, 0);
+    b[rp.plane + o] = cmake(0, 0);
+    return;
+  }
+  // nodal sin(pi x) at j-1, j, j+1 (full vectors: boundary nodal values enter M f)
+  const double sl = sinpi((double)(j - 1) / rp.N_x), sc = sinpi((double)j / rp.N_x),
+               sr = sinpi((double)(j + 1) / rp.N_x);
+  const double Ms = rp.h / 6.0 * (sl + 4.0 * sc + sr);
+  const double Ks = (-sl + 2.0 * sc - sr) / rp.h;
+  const double sg = sqrt(rp.gamma), dt2 = rp.dt * rp.dt, eT = exp(rp.T);
+  // f_i at t = i dt, scaled by sqrt(gamma) (:55-57); g_i at t = (i+1) dt (:69-72)
+  const double tf = i * rp.dt, tg = (i + 1) * rp.dt;
+  const double ef = exp(tf) - eT;
+  const double F = -(1.0 / rp.gamma) * ef * ef * sg;
+  const double eg = exp(tg) - eT;
+  const double G = 2.0 * (2.0 * exp(2.0 * tg) - exp(rp.T + tg)) + M_PI * M_PI * eg * eg + cospi(tg);
+  double bu;
+  if (i == 0) {
+    bu = dt2 * Ms * (0.5 * F + sg / dt2);                 // :118 (u_1 = 0, :80)
+  } else {
+    bu = dt2 * Ms * F;                                    // :139, :159
+    if (i == 1) bu += -Ms * sg - 0.5 * dt2 * Ks * sg;     // :93-95 with :157-158
+  }
+  double bp = dt2 * Ms * G;                               // :123, :164
+  if (i == rp.N_t - 1) bp *= 0.5;                         // :144
+  b[o] = cmake(bu, 0.0);
+  b[rp.plane + o] = cmake(bp, 0.0);
+}
+
+int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st) {
+  RhsParams rp;
+  rp.n = h->n; rp.N_t = h->cfg.N_t; rp.N_x = h->cfg.N_x; rp.h = h->h; rp.dt = h->dt;
+  rp.T = h->cfg.T; rp.gamma = h->cfg.gamma; rp.plane = (int64_t)h->n * h->cfg.N_t;
+  dim3 grid((rp.N_t + 255) / 256, h->n);
+  pd_rhs_kernel<<<grid, 256, 0, st>>>(b, rp);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// ------------------------------------------------------------- BLAS-1 kernels
+#define PD_RED_THREADS 256
+#define PD_MAXB 8  // basis vectors handled per launch
+
+struct VecBatch {
+  const cplx* v[PD_MAXB];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// partial[blk * NV + i] = sum over this block's elements of conj(V_i[e]) * w[e]
+template <int NV>
+__global__ void __launch_bounds__(PD_RED_THREADS)
+pd_mdot_kernel(VecBatch vb, const cplx* __restrict__ w, int64_t len, cplx* __restrict__ partial) {
+  double ar[NV], ai[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ar[i] = ai[i] = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const cplx we = w[e];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const cplx ve = vb.v[i][e];
+      ar[i] += ve.x * we.x + ve.y * we.y;
+      ai[i] += ve.x * we.y - ve.y * we.x;
+    }
+  }
+  __shared__ double sr[NV][PD_RED_THREADS / 32], si[NV][PD_RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double r = warp_sum(ar[i]), im = warp_sum(ai[i]);
+    if (lane == 0) { sr[i][wid] = r; si[i][wid] = im; }
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0, im = 0;
+    for (int k = 0; k < PD_RED_THREADS / 32; ++k) { r += sr[threadIdx.x][k]; im += si[threadIdx.x][k]; }
+    partial[(int64_t)blockIdx.x * NV + threadIdx.x] = cmake(r, im);
+  }
+}
+
+// out[i] = sum_blk partial[blk * nv + i]   (fixed order: deterministic)
+__global__ void pd_reduce_partials_kernel(const cplx* __restrict__ partial, int nblk, int nv,
+                                          cplx* __restrict__ out) {
+  const int i = blockIdx.x;
+  double r = 0, im = 0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    cplx p = partial[(int64_t)b * nv + i];
+    r += p.x; im += p.y;
+  }
+  __shared__ double sr[32], si[32];
+  r = warp_sum(r); im = warp_sum(im);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sr[wid] = r; si[wid] = im; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0, ti = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { tr += sr[k]; ti += si[k]; }
+    out[i] = cmake(tr, ti);
+  }
+}
+
+// w += sign * sum_i coef[i] * V_i ; optionally partial[blk] = sum |w_new|^2
+template <int NV, bool NORM>
+__global__ void __launch_bounds__(PD_RED_THREADS)
+pd_maxpy_kernel(VecBatch vb, const cplx* __restrict__ coef, double sign, cplx* __restrict__ w,
+                int64_t len, cplx* __restrict__ partial) {
+  cplx cf[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) cf[i] = cscale(coef[i], sign);
+  double acc = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    cplx we = w[e];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) we = cfma(cf[i], vb.v[i][e], we);
+    w[e] = we;
+    if (NORM) acc += we.x * we.x + we.y * we.y;
+  }
+  if (NORM) {
+    __shared__ double sr[PD_RED_THREADS / 32];
+    double r = warp_sum(acc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sr[wid] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int k = 0; k < PD_RED_THREADS / 32; ++k) t += sr[k];
+      partial[blockIdx.x] = cmake(t, 0.0);
+    }
+  }
+}
+
+// y = a*x + b*y elementwise with real scalars (b = 0: y = a*x)
+__global__ void __launch_bounds__(256)
+pd_axpby_kernel(double a, const cplx* __restrict__ x, double b, cplx* __restrict__ y, int64_t len) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    cplx xe = x[e];
+    if (b == 0.0) {
+      y[e] = cscale(xe, a);
+    } else {
+      cplx ye = y[e];
+      y[e] = cmake(a * xe.x + b * ye.x, a * xe.y + b * ye.y);
+    }
+  }
+}
+
+// v *= 1/sqrt(norm2[0].x)
+__global__ void __launch_bounds__(256)
+pd_normalize_kernel(cplx* __restrict__ v, const cplx* __restrict__ norm2, int64_t len) {
+  const double s = rsqrt(norm2[0].x);
+  const double inv = s;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len;
+       e += (int64_t)gridDim.x * blockDim.x)
+    v[e] = cscale(v[e], inv);
+}
+
+static int red_blocks(const pd_handle* h, int64_t len) {
+  int64_t nb = (len + PD_RED_THREADS - 1) / PD_RED_THREADS;
+  int64_t cap = (int64_t)h->num_sms * 8;
+  return (int)(nb < cap ? nb : cap);
+}
+
+template <int NV>
+static int mdot_batch(pd_handle* h, const cplx* const* vs, const cplx* w, int64_t len, cplx* out,
+                      cudaStream_t st) {
+  VecBatch vb;
+  for (int i = 0; i < PD_MAXB; ++i) vb.v[i] = vs[i < NV ? i : 0];
+  const int nb = red_blocks(h, len);
+  pd_mdot_kernel<NV><<<nb, PD_RED_THREADS, 0, st>>>(vb, w, len, h->kry_partial);
+  PD_CHECK_LAUNCH();
+  pd_reduce_partials_kernel<<<NV, 256, 0, st>>>(h->kry_partial, nb, NV, out);
+  PD_CHECK_LAUNCH();
+  h->launches += 2;
+  return PD_OK;
+}
+
+static int ensure_partial(pd_handle* h) {
+  if (!h->kry_partial) {
+    size_t bytes = sizeof(cplx) * (size_t)h->num_sms * 8 * PD_MAXB;
+    PD_CUDA(cudaMalloc(&h->kry_partial, bytes));
+    h->ws_bytes += bytes;
+  }
+  return PD_OK;
+}
+
+// out[i] = V_i^H w for i < nv, vectors given by pointer list
+static int mdot_list(pd_handle* h, const cplx* const* vs, int nv, const cplx* w, int64_t len, cplx* out,
+                     cudaStream_t st) {
+  int rc = ensure_partial(h);
+  if (rc) return rc;
+  for (int base = 0; base < nv; base += PD_MAXB) {
+    const int cnt = nv - base < PD_MAXB ? nv - base : PD_MAXB;
+    const cplx* const* v = vs + base;
+    switch (cnt) {
+      case 1: rc = mdot_batch<1>(h, v, w, len, out + base, st); break;
+      case 2: rc = mdot_batch<2>(h, v, w, len, out + base, st); break;
+      case 3: rc = mdot_batch<3>(h, v, w, len, out + base, st); break;
+      case 4: rc = mdot_batch<4>(h, v, w, len, out + base, st); break;
+      case 5: rc = mdot_batch<5>(h, v, w, len, out + base, st); break;
+      case 6: rc = mdot_batch<6>(h, v, w, len, out + base, st); break;
+      case 7: rc = mdot_batch<7>(h, v, w, len, out + base, st); break;
+      default: rc = mdot_batch<8>(h, v, w, len, out + base, st); break;
+    }
+    if (rc) return rc;
+  }
+  return PD_OK;
+}
+
+template <int NV>
+static int maxpy_batch(pd_handle* h, const cplx* const* vs, const cplx* coef, double sign, cplx* w,
+                       int64_t len, bool norm, cplx* norm_out, cudaStream_t st) {
+  VecBatch vb;
+  for (int i = 0; i < PD_MAXB; ++i) vb.v[i] = vs[i < NV ? i : 0];
+  const int nb = red_blocks(h, len);
+  if (norm) {
+    pd_maxpy_kernel<NV, true><<<nb, PD_RED_THREADS, 0, st>>>(vb, coef, sign, w, len, h->kry_partial);
+    PD_CHECK_LAUNCH();
+    pd_reduce_partials_kernel<<<1, 256, 0, st>>>(h->kry_partial, nb, 1, norm_out);
+    PD_CHECK_LAUNCH();
+    h->launches += 2;
+  } else {
+    pd_maxpy_kernel<NV, false><<<nb, PD_RED_THREADS, 0, st>>>(vb, coef, sign, w, len, h->kry_partial);
+    PD_CHECK_LAUNCH();
+    h->launches += 1;
+  }
+  return PD_OK;
+}
+
+// w += sign * sum_i coef[i] V_i ; if norm_out: norm_out[0] = ||w_new||^2
+static int maxpy_list(pd_handle* h, const cplx* const* vs, int nv, const cplx* coef, double sign, cplx* w,
+                      int64_t len, cplx* norm_out, cudaStream_t st) {
+  int rc = ensure_partial(h);
+  if (rc) return rc;
+  for (int base = 0; base < nv; base += PD_MAXB) {
+    const int cnt = nv - base < PD_MAXB ? nv - base : PD_MAXB;
+    const bool lastb = base + cnt >= nv;
+    const bool norm = lastb && norm_out != nullptr;
+    const cplx* const* v = vs + base;
+    const cplx* cf = coef + base;
+    switch (cnt) {
+      case 1: rc = maxpy_batch<1>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 2: rc = maxpy_batch<2>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 3: rc = maxpy_batch<3>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 4: rc = maxpy_batch<4>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 5: rc = maxpy_batch<5>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 6: rc = maxpy_batch<6>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 7: rc = maxpy_batch<7>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      default: rc = maxpy_batch<8>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+    }
+    if (rc) return rc;
+  }
+  return PD_OK;
+}
+
+extern "C" int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* w_dev, int64_t len,
+                       void* out_dev, void* stream) {
+  if (!h || !V_dev || !w_dev || !out_dev || nv < 0) {
+    pd_set_error("pd_mdot: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  std::vector<const cplx*> vs(nv);
+  for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
+  return mdot_list(h, vs.data(), nv, (const cplx*)w_dev, len, (cplx*)out_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------- GMRES
+struct hcplx {
+  double re, im;
+};
+static inline hcplx hmul(hcplx a, hcplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline hcplx hconj(hcplx a) { return {a.re, -a.im}; }
+static inline hcplx hadd(hcplx a, hcplx b) { return {a.re + b.re, a.im + b.im}; }
+static inline hcplx hsub(hcplx a, hcplx b) { return {a.re - b.re, a.im - b.im}; }
+static inline double habs(hcplx a) { return hypot(a.re, a.im); }
+static inline hcplx hdiv(hcplx a, hcplx b) {
+  double d = b.re * b.re + b.im * b.im;
+  return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+
+static int ensure_basis(pd_handle* h, std::vector<cplx*>& V, int need, int64_t len) {
+  // basis vectors are cached on the handle as one allocation each
+  while ((int)V.size() < need) {
+    cplx* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(cplx) * (size_t)len);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return PD_ERR_NOMEM;
+    }
+    h->ws_bytes += sizeof(cplx) * (size_t)len;
+    V.push_back(p);
+  }
+  return PD_OK;
+}
+
+struct KrylovCache {
+  std::vector<cplx*> V;
+};
+
+static KrylovCache* cache_of(pd_handle* h) {
+  if (!h->kry_V) h->kry_V = reinterpret_cast<cplx*>(new KrylovCache());
+  return reinterpret_cast<KrylovCache*>(h->kry_V);
+}
+
+void pd_krylov_free(pd_handle* h) {
+  if (h->kry_V) {
+    KrylovCache* kc = reinterpret_cast<KrylovCache*>(h->kry_V);
+    for (cplx* p : kc->V) cudaFree(p);
+    delete kc;
+    h->kry_V = nullptr;
+  }
+  if (h->kry_partial) cudaFree(h->kry_partial);
+  if (h->kry_h) cudaFree(h->kry_h);
+  if (h->kry_t) cudaFree(h->kry_t);
+  if (h->kry_host) cudaFreeHost(h->kry_host);
+  h->kry_partial = h->kry_h = h->kry_t = nullptr;
+  h->kry_host = nullptr;
+}
+
+extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
+                        int max_it, int* its_out, double* hist, int* reason_out, void* stream) {
+  if (!h || !b_dev || !x_dev || restart < 1 || max_it < 0) {
+    pd_set_error("pd_gmres: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
+    pd_set_error("pd_gmres: handle is sharded (k_count/n_local set); use the stage API");
+    return PD_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t len = 2 * (int64_t)h->n * h->cfg.N_t;
+  const cplx* b = (const cplx*)b_dev;
+  cplx* x = (cplx*)x_dev;
+  KrylovCache* kc = cache_of(h);
+  int rc;
+  if ((rc = ensure_partial(h))) return rc;
+  const int hcap = restart + 2;
+  if (!h->kry_h || h->kry_cap < hcap) {
+    if (h->kry_h) cudaFree(h->kry_h);
+    if (h->kry_host) cudaFreeHost(h->kry_host);
+    PD_CUDA(cudaMalloc(&h->kry_h, sizeof(cplx) * (size_t)hcap));
+    PD_CUDA(cudaMallocHost(&h->kry_host, sizeof(cplx) * (size_t)hcap));
+    h->kry_cap = hcap;
+  }
+  if (!h->kry_t) {
+    PD_CUDA(cudaMalloc(&h->kry_t, sizeof(cplx) * (size_t)len));
+    h->ws_bytes += sizeof(cplx) * (size_t)len;
+  }
+  cplx* t = h->kry_t;
+  cplx* hdev = h->kry_h;
+  hcplx* hhost = reinterpret_cast<hcplx*>(h->kry_host);
+  const int nb1 = (int)((len + 255) / 256 < (int64_t)h->num_sms * 16 ? (len + 255) / 256
+                                                                      : (int64_t)h->num_sms * 16);
+
+  int its = 0, reason = -3;
+  double beta0 = 0.0, target = 0.0;
+  bool converged = false, first = true;
+  PD_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * (size_t)len, st));
+
+  std::vector<hcplx> H((size_t)(restart + 1) * restart), g(restart + 1), cs(restart), sn(restart), yk(restart);
+  auto Hat = [&](int i, int j) -> hcplx& { return H[(size_t)j * (restart + 1) + i]; };
+
+  while (!converged && (its < max_it || first)) {
+    if ((rc = ensure_basis(h, kc->V, 1, len))) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
+    cplx* v0 = kc->V[0];
+    // r = P^-1 (b - A x)   (x = 0 on the first cycle)
+    if (first) {
+      if ((rc = pd_pc_apply(h, b, v0, st))) return rc;
+    } else {
+      if ((rc = pd_matvec_launch(h, x, t, st))) return rc;
+      pd_axpby_kernel<<<nb1, 256, 0, st>>>(1.0, b, -1.0, t, len);
+      PD_CHECK_LAUNCH();
+      h->launches++;
+      if ((rc = pd_pc_apply(h, t, v0, st))) return rc;
+    }
+    const cplx* vs0[1] = {v0};
+    if ((rc = mdot_list(h, vs0, 1, v0, len, hdev, st))) return rc;
+    PD_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    PD_CUDA(cudaStreamSynchronize(st));
+    const double beta = sqrt(hhost[0].re);
+    if (first) {
+      beta0 = beta;
+      target = fmax(rtol * beta0, atol);
+      if (hist) hist[0] = beta0;
+      first = false;
+      if (beta0 <= target || beta0 == 0.0) {
+        converged = true;
+        reason = beta0 <= atol ? 3 : 2;
+        break;
+      }
+      if (max_it == 0) break;
+    }
+    pd_normalize_kernel<<<nb1, 256, 0, st>>>(v0, hdev, len);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+    for (auto& e : g) e = {0, 0};
+    g[0] = {beta, 0};
+    int jdone = 0;
+    for (int j = 0; j < restart; ++j) {
+      // a basis slot for w; if memory runs out, restart early with what we have
+      rc = ensure_basis(h, kc->V, j + 2, len);
+      if (rc == PD_ERR_NOMEM) {
+        if (j == 0) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
+        break;
+      }
+      cplx* w = kc->V[j + 1];
+      if ((rc = pd_matvec_launch(h, kc->V[j], t, st))) return rc;
+      if ((rc = pd_pc_apply(h, t, w, st))) return rc;
+      // classical Gram-Schmidt: all inner products against the unmodified w first
+      if ((rc = mdot_list(h, kc->V.data(), j + 1, w, len, hdev, st))) return rc;
+      if ((rc = maxpy_list(h, kc->V.data(), j + 1, hdev, -1.0, w, len, hdev + (j + 1), st))) return rc;
+      PD_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(cplx) * (size_t)(j + 2), cudaMemcpyDeviceToHost, st));
+      PD_CUDA(cudaStreamSynchronize(st));
+      for (int i = 0; i <= j; ++i) Hat(i, j) = hhost[i];
+      const double hn = sqrt(fmax(hhost[j + 1].re, 0.0));
+      Hat(j + 1, j) = {hn, 0};
+      for (int i = 0; i < j; ++i) {
+        hcplx a_ = Hat(i, j), b_ = Hat(i + 1, j);
+        Hat(i, j) = hadd(hmul(hconj(cs[i]), a_), hmul(hconj(sn[i]), b_));
+        Hat(i + 1, j) = hsub(hmul(cs[i], b_), hmul(sn[i], a_));
+      }
+      {
+        hcplx a_ = Hat(j, j), b_ = Hat(j + 1, j);
+        double den = sqrt(a_.re * a_.re + a_.im * a_.im + b_.re * b_.re + b_.im * b_.im);
+        if (den == 0.0) { cs[j] = {1, 0}; sn[j] = {0, 0}; }
+        else { cs[j] = {a_.re / den, a_.im / den}; sn[j] = {b_.re / den, b_.im / den}; }
+        Hat(j, j) = hadd(hmul(hconj(cs[j]), a_), hmul(hconj(sn[j]), b_));
+        Hat(j + 1, j) = {0, 0};
+        hcplx gj = g[j];
+        g[j + 1] = hmul({-sn[j].re, -sn[j].im}, gj);
+        g[j] = hmul(hconj(cs[j]), gj);
+      }
+      ++its;
+      jdone = j + 1;
+      const double rn = habs(g[j + 1]);
+      if (hist) hist[its] = rn;
+      if (rn <= target) {
+        converged = true;
+        reason = rn > atol ? 2 : 3;
+        break;
+      }
+      if (its >= max_it || hn == 0.0) break;
+      pd_normalize_kernel<<<nb1, 256, 0, st>>>(w, hdev + (j + 1), len);
+      PD_CHECK_LAUNCH();
+      h->launches++;
+    }
+    // y = H^-1 g (upper triangular), x += V y
+    for (int i = jdone - 1; i >= 0; --i) {
+      hcplx s = g[i];
+      for (int k = i + 1; k < jdone; ++k) s = hsub(s, hmul(Hat(i, k), yk[k]));
+      yk[i] = hdiv(s, Hat(i, i));
+    }
+    if (jdone > 0) {
+      for (int i = 0; i < jdone; ++i) hhost[i] = yk[i];
+      PD_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(cplx) * (size_t)jdone, cudaMemcpyHostToDevice, st));
+      if ((rc = maxpy_list(h, kc->V.data(), jdone, hdev, 1.0, x, len, nullptr, st))) return rc;
+      PD_CUDA(cudaStreamSynchronize(st));
+    }
+    if (its >= max_it) break;
+  }
+  PD_CUDA(cudaStreamSynchronize(st));
+  if (its_out) *its_out = its;
+  if (reason_out) *reason_out = reason;
+  if (!converged) {
+    pd_set_error("pd_gmres: not converged after %d iterations", its);
+    return PD_ERR_NOT_CONVERGED;
+  }
+  return PD_OK;
+}

@@ -1,0 +1,157 @@
+"""Python wrapper of one ``pd_handle`` (a problem size bound to one CUDA device).
+
+Device vectors are torch tensors (complex128, contiguous, on the handle's device); the
+wrapper only extracts ``data_ptr()`` and the current CUDA stream -- torch is plumbing
+for memory and streams, all arithmetic happens inside libparadiag.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, pd_config
+
+CONVERGED_REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS"}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class ParaDiagHandle:
+    def __init__(self, N_x, N_t, T=2.0, gamma=1.0, alpha=1.0, bug138=True, device=0,
+                 k_begin=0, k_count=0, n_local=0):
+        self._h = C.c_void_p()
+        self.lib = _lib.load_library()
+        self.N_x, self.N_t, self.T, self.gamma = int(N_x), int(N_t), float(T), float(gamma)
+        self.n = self.N_x + 1
+        self.device = int(device)
+        self.size = 2 * self.n * self.N_t
+        self.k_count = int(k_count) if k_count else self.N_t
+        self.k_begin = int(k_begin) if k_count else 0
+        self.n_local = int(n_local) if n_local else self.n
+        cfg = pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=self.N_x, N_t=self.N_t, bug138=int(bool(bug138)),
+                        T=self.T, gamma=self.gamma, alpha=float(alpha), device=self.device,
+                        k_begin=int(k_begin), k_count=int(k_count), n_local=int(n_local))
+        check(self.lib.pd_create(C.byref(cfg), C.byref(self._h)))
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.pd_workspace_bytes(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pd_launch_count(self._h))
+
+    # ------------------------------------------------------------------- helpers
+    def _ptr(self, t, numel=None, name="vector"):
+        torch = _torch()
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected a torch tensor, got {type(t)}")
+        if t.dtype != torch.complex128 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{name}: need a contiguous complex128 CUDA tensor")
+        if t.device.index != self.device:
+            raise ValueError(f"{name}: tensor on cuda:{t.device.index}, handle on cuda:{self.device}")
+        if numel is not None and t.numel() != numel:
+            raise ValueError(f"{name}: expected {numel} entries, got {t.numel()}")
+        return C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self):
+        torch = _torch()
+        return torch.empty(self.size, dtype=torch.complex128, device=f"cuda:{self.device}")
+
+    # -------------------------------------------------------------- entry points
+    def pc_apply(self, x, y=None):
+        """y = P^-1 x on device tensors (DiagFFTPC.apply, Control_Wave_PC.py:491-553)."""
+        if y is None:
+            y = self.empty()
+        check(self.lib.pd_pc_apply(self._h, self._ptr(x, self.size, "x"), self._ptr(y, self.size, "y"),
+                                   self._stream()))
+        return y
+
+    def pc_apply_host(self, x, y=None):
+        """Same through host buffers (numpy complex128): H2D, apply, D2H."""
+        x = np.ascontiguousarray(x, dtype=np.complex128).reshape(-1)
+        if x.size != self.size:
+            raise ValueError(f"x: expected {self.size} entries, got {x.size}")
+        if y is None:
+            y = np.empty(self.size, dtype=np.complex128)
+        if y.dtype != np.complex128 or not y.flags.c_contiguous or y.size != self.size:
+            raise ValueError("y: need a contiguous complex128 array of the vector size")
+        check(self.lib.pd_pc_apply_host(self._h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+        return y
+
+    def pc_apply_transpose(self, x, y):
+        st = self.lib.pd_pc_apply_transpose(self._h, None, None, None)
+        if st == _lib.PD_ERR_UNSUPPORTED:
+            raise NotImplementedError
+        check(st)
+
+    def stage_fft(self, src, dst, nlines, inverse):
+        check(self.lib.pd_stage_fft(self._h, self._ptr(src, nlines * self.N_t, "src"),
+                                    self._ptr(dst, nlines * self.N_t, "dst"), int(nlines), int(bool(inverse)),
+                                    self._stream()))
+        return dst
+
+    def stage_solve(self, w):
+        check(self.lib.pd_stage_solve(self._h, self._ptr(w, 2 * self.n * self.k_count, "w"), self._stream()))
+        return w
+
+    def matvec(self, x, y=None):
+        """y = A x, the Jacobian action of Build_L (Control_Wave_PC.py:86-179)."""
+        if y is None:
+            y = self.empty()
+        check(self.lib.pd_matvec(self._h, self._ptr(x, self.size, "x"), self._ptr(y, self.size, "y"),
+                                 self._stream()))
+        return y
+
+    def build_rhs(self, b=None):
+        if b is None:
+            b = self.empty()
+        check(self.lib.pd_build_rhs(self._h, self._ptr(b, self.size, "b"), self._stream()))
+        return b
+
+    def gmres(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
+        """Left-preconditioned GMRES (options of Control_Wave_PC.py:347-359).
+
+        Returns (x, iterations, residual_history, reason)."""
+        if x is None:
+            x = self.empty()
+        its, reason = C.c_int(0), C.c_int(0)
+        hist = (C.c_double * (max_it + 1))()
+        st = self.lib.pd_gmres(self._h, self._ptr(b, self.size, "b"), self._ptr(x, self.size, "x"),
+                               float(rtol), float(atol), int(restart), int(max_it), C.byref(its), hist,
+                               C.byref(reason), self._stream())
+        check(st, allow=(_lib.PD_ERR_NOT_CONVERGED,))
+        return x, its.value, list(hist[: its.value + 1]), CONVERGED_REASONS.get(reason.value, str(reason.value))
+
+    def mdot(self, V, w):
+        """V^H w for a (nv, len) basis tensor: PETSc VecMDot order."""
+        torch = _torch()
+        nv, ln = V.shape
+        out = torch.empty(nv, dtype=torch.complex128, device=V.device)
+        check(self.lib.pd_mdot(self._h, self._ptr(V, None, "V"), int(V.stride(0)), int(nv),
+                               self._ptr(w, ln, "w"), int(ln), self._ptr(out, nv, "out"), self._stream()))
+        return out

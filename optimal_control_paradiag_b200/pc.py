@@ -1,0 +1,211 @@
+"""``DiagFFTPC``: the reference's python-PC surface on top of libparadiag.
+
+Mirrors ``class DiagFFTPC(fd.PCBase)`` of Code/Control_Wave_PC.py:376-558 -- same class
+name, ``initialize(pc)`` / ``update(pc)`` / ``apply(pc, x, y)`` / ``applyTranspose`` with the
+same argument meaning and error behaviour -- so it is selected exactly like upstream
+(:357-358)::
+
+    'pc_type': 'python', 'pc_python_type': 'optimal_control_paradiag_b200.DiagFFTPC'
+
+Configuration.  Upstream reads module globals (``N_t, dt, gamma, W, bcs`` :362-368).  Here the
+problem description (N_x, N_t, T, gamma) is looked up, in this order:
+
+1. a Firedrake ``appctx`` (``get_appctx(pc)``) with key ``"paradiag"`` (a dict) or the keys
+   ``N_x, N_t, T, gamma`` directly, when Firedrake's ``PCBase`` is the base class;
+2. PC-local options under the prefix PETSc hands the PC (``pc.getOptionsPrefix()``):
+   ``<prefix>diagfft_nx``, ``..._nt``, ``..._T``, ``..._gamma``, ``..._device``;
+3. ``DiagFFTPC.configure(...)`` class-level defaults;
+4. the globals ``N_x, N_t, T, gamma`` of ``__main__`` (how the upstream script itself is laid out).
+
+Vectors.  ``x`` / ``y`` may be petsc4py ``Vec`` objects (host arrays via ``getArray``), the
+fake ``Vec`` of ``petsc_shim``, numpy arrays, or torch CUDA tensors (device path, no copies).
+Layout is the PETSc layout of the reference: ``[u-block ; p-block]``, node-major, time fastest
+(:496-501).  ``node_order`` (optional) maps Vec node position -> geometric node index for
+meshes whose dof numbering is not monotone in x.
+"""
+import sys
+
+import numpy as np
+
+from .handle import ParaDiagHandle
+
+try:  # the genuine base class when Firedrake exists (not in this image)
+    from firedrake import PCBase as _FiredrakePCBase  # type: ignore
+except Exception:  # pragma: no cover - firedrake absent
+    _FiredrakePCBase = None
+
+
+class _ShimPCBase:
+    """Minimal stand-in for ``firedrake.PCBase`` (the draft pre_cond.py:14-23 shows the shape):
+    ``setUp`` calls ``initialize`` once and ``update`` afterwards."""
+
+    needs_python_amat = False
+    needs_python_pmat = False
+
+    def __init__(self):
+        self.initialized = False
+
+    def setUp(self, pc):
+        if not getattr(self, "initialized", False):
+            self.initialize(pc)
+            self.initialized = True
+        else:
+            self.update(pc)
+
+    def view(self, pc, viewer=None):
+        pass
+
+    def destroy(self, pc):
+        pass
+
+    @staticmethod
+    def get_appctx(pc):
+        return {}
+
+
+PCBase = _FiredrakePCBase if _FiredrakePCBase is not None else _ShimPCBase
+
+_KEYS = ("N_x", "N_t", "T", "gamma")
+_OPT_NAMES = {"N_x": "diagfft_nx", "N_t": "diagfft_nt", "T": "diagfft_T", "gamma": "diagfft_gamma"}
+
+
+def _options_lookup(pc, name, conv):
+    """Read ``<prefix><name>`` from the PETSc options database (or the shim's)."""
+    prefix = ""
+    try:
+        prefix = pc.getOptionsPrefix() or ""
+    except Exception:
+        pass
+    db = getattr(pc, "options", None)
+    if db is None:
+        try:
+            from petsc4py import PETSc  # type: ignore
+            db = PETSc.Options()
+        except Exception:
+            return None
+    key = prefix + name
+    try:
+        if hasattr(db, "hasName") and not db.hasName(key):
+            return None
+        val = db.getString(key) if hasattr(db, "getString") else db[key]
+    except Exception:
+        return None
+    return conv(val)
+
+
+class DiagFFTPC(PCBase):
+    _defaults = {}
+
+    # -- configuration -------------------------------------------------------------
+    @classmethod
+    def configure(cls, **kw):
+        """Class-level problem description (replaces the module globals :362-368)."""
+        for k in kw:
+            if k not in _KEYS + ("device", "node_order", "bug138"):
+                raise TypeError(f"unknown DiagFFTPC option {k!r}")
+        cls._defaults = dict(cls._defaults, **kw)
+
+    def _resolve(self, pc):
+        cfg = {}
+        main = sys.modules.get("__main__")
+        for k in _KEYS:                                              # 4. __main__ globals
+            if main is not None and hasattr(main, k):
+                cfg[k] = getattr(main, k)
+        cfg.update(self._defaults)                                   # 3. configure()
+        for k in _KEYS:                                              # 2. options prefix
+            v = _options_lookup(pc, _OPT_NAMES[k], float if k in ("T", "gamma") else int)
+            if v is not None:
+                cfg[k] = v
+        dev = _options_lookup(pc, "diagfft_device", int)
+        if dev is not None:
+            cfg["device"] = dev
+        try:                                                         # 1. appctx
+            ctx = self.get_appctx(pc) or {}
+        except Exception:
+            ctx = {}
+        sub = ctx.get("paradiag", {}) if hasattr(ctx, "get") else {}
+        for k in _KEYS + ("device", "node_order", "bug138"):
+            if k in sub:
+                cfg[k] = sub[k]
+            elif hasattr(ctx, "get") and k in ctx:
+                cfg[k] = ctx[k]
+        missing = [k for k in _KEYS if k not in cfg]
+        if missing:
+            raise ValueError(f"DiagFFTPC: problem description incomplete, missing {missing}; pass an appctx, "
+                             f"options <prefix>diagfft_*, or call DiagFFTPC.configure()")
+        return cfg
+
+    # -- reference surface ---------------------------------------------------------
+    def initialize(self, pc):
+        """Control_Wave_PC.py:380-484.  Upstream: per-k ``eig``/``inv`` (:415-436), the UFL forms
+        (:445-473) and the MUMPS solver (:481-484).  Here: create the device handle; every
+        per-frequency coefficient is regenerated inside the kernels."""
+        cfg = self._resolve(pc)
+        self.N_x, self.N_t = int(cfg["N_x"]), int(cfg["N_t"])
+        self.T, self.gamma = float(cfg["T"]), float(cfg["gamma"])
+        self.n = self.N_x + 1
+        self.node_order = cfg.get("node_order")
+        if self.node_order is not None:
+            self.node_order = np.asarray(self.node_order, dtype=np.int64)
+            if sorted(self.node_order.tolist()) != list(range(self.n)):
+                raise ValueError("node_order must be a permutation of range(N_x + 1)")
+            self._inv_order = np.argsort(self.node_order)
+        self.handle = ParaDiagHandle(self.N_x, self.N_t, T=self.T, gamma=self.gamma,
+                                     bug138=cfg.get("bug138", True), device=int(cfg.get("device", 0)))
+        self.initialized = True
+
+    def update(self, pc):                                           # :487-488
+        pass
+
+    def apply(self, pc, x, y):
+        """Control_Wave_PC.py:491-553: y = P^-1 x."""
+        if not getattr(self, "initialized", False) or not hasattr(self, "handle"):
+            self.initialize(pc)
+        try:
+            import torch
+            is_dev = isinstance(x, torch.Tensor) and x.is_cuda
+        except Exception:  # pragma: no cover
+            is_dev = False
+        if is_dev:
+            if self.node_order is not None:
+                raise NotImplementedError("node_order is only supported on the host-Vec path")
+            self.handle.pc_apply(x.reshape(-1), y.reshape(-1))
+            return
+        xa = _host_array(x, readonly=True)
+        ya = _host_array(y, readonly=False)
+        if xa.size != self.handle.size or ya.size != self.handle.size:
+            raise ValueError(f"DiagFFTPC.apply: Vec size {xa.size} != 2*(N_x+1)*N_t = {self.handle.size}")
+        if self.node_order is None:
+            if ya.dtype == np.complex128 and ya.flags.c_contiguous:
+                self.handle.pc_apply_host(xa, ya)
+            else:
+                ya[...] = self.handle.pc_apply_host(xa).astype(ya.dtype, copy=False)
+        else:
+            xs = xa.reshape(2, self.n, self.N_t)[:, self._inv_order, :]
+            ys = self.handle.pc_apply_host(xs).reshape(2, self.n, self.N_t)
+            ya.reshape(2, self.n, self.N_t)[...] = ys[:, self.node_order, :]
+        _restore(y, ya)
+
+    def applyTranspose(self, pc, x, y):                             # :557-558
+        raise NotImplementedError
+
+    def destroy(self, pc):
+        if hasattr(self, "handle"):
+            self.handle.close()
+
+
+def _host_array(v, readonly):
+    if isinstance(v, np.ndarray):
+        return v.reshape(-1)
+    if hasattr(v, "getArray"):
+        try:
+            return v.getArray(readonly=readonly).reshape(-1)
+        except TypeError:
+            return v.getArray().reshape(-1)
+    raise TypeError(f"DiagFFTPC.apply: unsupported vector type {type(v)}")
+
+
+def _restore(v, arr):
+    # petsc4py's getArray() returns a view that writes through; shims may need setArray
+    if not isinstance(v, np.ndarray) and hasattr(v, "setArray") and not getattr(v, "array_is_view", True):
+        v.setArray(arr)
