@@ -107,6 +107,12 @@ int pd_stage_solve(pd_handle* h, void* w_dev, void* stream);
  * y = A x with Dirichlet rows as identity.  x and y must not alias.             */
 int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 
+/* y = P x for the block-circulant matrix P that DiagFFTPC inverts (the operator above
+ * with the time stencils of :121, :137 made periodic -- C1, C2 of mat_test.ipynb cells
+ * 8-9 -- and the half weights :117, :143 and the :138 factor replaced by 1).  Lets a
+ * caller verify an apply at any size: P (P^-1 x) = x on interior rows.               */
+int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+
 /* Right-hand side of the manufactured problem, Build_f / Build_g /
  * Build_Initial_Condition (:48-83) folded through the residual (:118, :139,
  * :144, :93-95): b such that the ksponly solve is A U = b.                      */

@@ -47,6 +47,7 @@ SYMBOLS = {
     "pd_stage_fft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "pd_stage_solve": (_I, [_VP, _VP, _VP]),
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),
     "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
     "pd_mdot": (_I, [_VP, _VP, _I64, _I, _VP, _I64, _VP, _VP]),

@@ -185,7 +185,15 @@ extern "C" int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* str
     pd_set_error("pd_matvec: invalid argument (x and y must be distinct device vectors)");
     return PD_ERR_INVALID;
   }
-  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream);
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0);
+}
+
+extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev || x_dev == y_dev) {
+    pd_set_error("pd_pc_matvec: invalid argument (x and y must be distinct device vectors)");
+    return PD_ERR_INVALID;
+  }
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 1);
 }
 
 extern "C" int pd_build_rhs(pd_handle* h, void* b_dev, void* stream) {

@@ -20,12 +20,17 @@ struct OpParams {
   double h, dt2h;  // dt^2 / 2
   double c;        // dt^2 / sqrt(gamma)
   double qlast;    // sqrt(gamma) if bug138 else 1
+  int circulant;   // 1: the block-circulant operator P the preconditioner inverts
   int64_t plane;
 };
 
 __device__ __forceinline__ cplx ld_or_zero(const cplx* __restrict__ v, int j, int i, const OpParams& op) {
   // Dirichlet columns are dropped: boundary-node values never enter interior rows
-  if (j < 1 || j > op.n - 2 || i < 0 || i >= op.N_t) return cmake(0, 0);
+  if (j < 1 || j > op.n - 2) return cmake(0, 0);
+  if (i < 0 || i >= op.N_t) {
+    if (!op.circulant) return cmake(0, 0);
+    i = i < 0 ? i + op.N_t : i - op.N_t;  // C1, C2 wrap around (mat_test.ipynb cells 8-9)
+  }
   return v[(int64_t)j * op.N_t + i];
 }
 
@@ -44,9 +49,9 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   }
   const double m_off = op.h / 6.0, m_dia = 2.0 * op.h / 3.0;
   const double k_off = -1.0 / op.h, k_dia = 2.0 / op.h;
-  const double d_i = (i == 0) ? 0.5 : 1.0;               // :117
-  const double e_i = (i == op.N_t - 1) ? 0.5 : 1.0;      // :143
-  const double q_i = (i == op.N_t - 1) ? op.qlast : 1.0; // :138
+  const double d_i = (i == 0 && !op.circulant) ? 0.5 : 1.0;               // :117
+  const double e_i = (i == op.N_t - 1 && !op.circulant) ? 0.5 : 1.0;      // :143
+  const double q_i = (i == op.N_t - 1 && !op.circulant) ? op.qlast : 1.0; // :138
   cplx yu = cmake(0, 0), yp = cmake(0, 0);
 #pragma unroll
   for (int dj = -1; dj <= 1; ++dj) {
@@ -70,8 +75,9 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   y[op.plane + o] = yp;
 }
 
-int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st) {
+int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant) {
   OpParams op;
+  op.circulant = circulant;
   op.n = h->n; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
   op.qlast = h->cfg.bug138 ? sqrt(h->cfg.gamma) : 1.0;
   op.plane = (int64_t)h->n * h->cfg.N_t;
@@ -471,7 +477,7 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     if (first) {
       if ((rc = pd_pc_apply(h, b, v0, st))) return rc;
     } else {
-      if ((rc = pd_matvec_launch(h, x, t, st))) return rc;
+      if ((rc = pd_matvec_launch(h, x, t, st, 0))) return rc;
       pd_axpby_kernel<<<nb1, 256, 0, st>>>(1.0, b, -1.0, t, len);
       PD_CHECK_LAUNCH();
       h->launches++;
@@ -508,7 +514,7 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
         break;
       }
       cplx* w = kc->V[j + 1];
-      if ((rc = pd_matvec_launch(h, kc->V[j], t, st))) return rc;
+      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0))) return rc;
       if ((rc = pd_pc_apply(h, t, w, st))) return rc;
       // classical Gram-Schmidt: all inner products against the unmodified w first
       if ((rc = mdot_list(h, kc->V.data(), j + 1, w, len, hdev, st))) return rc;

@@ -127,6 +127,14 @@ class ParaDiagHandle:
                                  self._stream()))
         return y
 
+    def pc_matvec(self, x, y=None):
+        """y = P x, the block-circulant matrix whose inverse ``pc_apply`` applies."""
+        if y is None:
+            y = self.empty()
+        check(self.lib.pd_pc_matvec(self._h, self._ptr(x, self.size, "x"), self._ptr(y, self.size, "y"),
+                                    self._stream()))
+        return y
+
     def build_rhs(self, b=None):
         if b is None:
             b = self.empty()

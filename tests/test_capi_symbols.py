@@ -1,0 +1,86 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/paradiag.h declares
+(no compute calls without a GPU).  It must also fail loudly -- not fall back -- without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import optimal_control_paradiag_b200 as pkg
+from optimal_control_paradiag_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "paradiag.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pd_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    path = pkg.library_path()
+    assert os.path.exists(path), f"{path} missing: run __graft_entry__.build()"
+    assert os.path.dirname(path) == os.path.join(ROOT, "optimal_control_paradiag_b200")
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = pkg.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"libparadiag.so does not export {s}"
+        assert s in _lib.SYMBOLS, f"{s} is declared in paradiag.h but not bound in _lib.py"
+    for s in _lib.SYMBOLS:
+        assert s in syms, f"{s} is bound in _lib.py but not declared in paradiag.h"
+
+
+def test_abi_version_and_struct_size():
+    lib = pkg.load_library()
+    assert lib.pd_abi_version() == _lib.PD_ABI_VERSION
+    # pd_config: 4 int32, 3 double, 4 int32, 5 reserved int32 -> 16 + 24 + 16 + 20 = 76 -> padded to 80
+    assert C.sizeof(_lib.pd_config) == 80
+
+
+def test_invalid_config_is_rejected_before_touching_cuda():
+    lib = pkg.load_library()
+    h = C.c_void_p()
+    cfg = _lib.pd_config(abi_version=999, N_x=8, N_t=8, T=2.0, gamma=1.0, alpha=1.0)
+    assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_INVALID
+    assert b"ABI" in lib.pd_last_error()
+    cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=1, N_t=8, T=2.0, gamma=1.0, alpha=1.0)
+    assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_INVALID
+    cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=8, N_t=8, T=2.0, gamma=1.0, alpha=0.1)
+    assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_UNSUPPORTED
+    assert lib.pd_create(None, C.byref(h)) == _lib.PD_ERR_INVALID
+    assert lib.pd_destroy(None) == 0
+    assert lib.pd_pc_apply_transpose(None, None, None, None) == _lib.PD_ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.ParaDiagError) as ei:
+        pkg.ParaDiagHandle(16, 16)
+    assert ei.value.status == _lib.PD_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("PARADIAG_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(pkg.LibraryNotBuilt):
+        pkg.load_library()
+    monkeypatch.delenv("PARADIAG_LIB")
+    monkeypatch.setattr(_lib, "_lib", None)
+    pkg.load_library()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkgdir = os.path.join(ROOT, "optimal_control_paradiag_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
