@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- PC applies/s of the ParaDiag block-circulant preconditioner on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one application of the preconditioner (DiagFFTPC.apply, Control_Wave_PC.py:491-553)
+to one synthetic complex128 vector (numpy default_rng(0) normal, layout (2, N_x+1, N_t)).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+
+Workloads (BASELINE.json configs): cfg1 80x81 (upstream default), cfg2 1024x1024,
+cfg5 4096x4096, cfg3 16384x4096 (default at N=1: the largest single-GPU configuration and the
+one the >=60 %-of-HBM-roofline target is quoted on; its 2.1 GB vectors exceed the 126 MB L2,
+so no L2 flush is needed between timed iterations).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg1": (80, 81), "cfg2": (1024, 1024), "cfg5": (4096, 4096), "cfg3": (16384, 4096),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = upper half of the samples (the sampler also sees idle gaps)
+        med = sm[len(sm) * 3 // 4] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_apply(N_x, N_t, steps, warmup, threads=None):
+    """The reference's CPU implementation of the path, restated (oracle): scipy.fft (pocketfft, what
+    upstream calls) with all host threads + pthread-parallel Thomas solves.  Returns (sec/apply, cores)."""
+    import numpy as np
+    from oracle import csolve
+    from oracle.pc_fast import DiagFFTPCFast
+    cores = threads or len(os.sched_getaffinity(0))
+    csolve.set_num_threads(cores)
+    pc = DiagFFTPCFast(N_x, N_t, 2.0, 1.0, workers=cores, solver=csolve.thomas_toeplitz_c)
+    rng = np.random.default_rng(0)
+    size = 2 * (N_x + 1) * N_t
+    x = rng.standard_normal(size) + 1j * rng.standard_normal(size)
+    for _ in range(warmup):
+        pc.apply(x)
+    best = float("inf")
+    for _ in range(steps):
+        t = time.perf_counter()
+        pc.apply(x)
+        best = min(best, time.perf_counter() - t)
+    return best, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N_x, N_t = WORKLOADS[args.workload]
+    # bounded sample: the full apply of the workload, best of `steps` (<= 3) after `warmup` (<= 1)
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    sec, cores = cpu_reference_apply(N_x, N_t, steps, warmup)
+    val = 1.0 / sec
+    sample = f"full {N_x}x{N_t} apply, best of {steps} after {warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": "pc_applies_per_sec", "value": val, "unit": "applies/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64 complex)",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: 1D wave control N_x={N_x}, N_t={N_t}, T=2, gamma=1"},
+        "cpu_baseline": {"value": val, "unit": "applies/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Firedrake/PETSc/MUMPS are not installable here; this is the oracle's CPU restatement "
+                "(scipy.fft + threaded Thomas) on the box's host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from optimal_control_paradiag_b200 import DiagFFTPC, ParaDiagHandle, petsc_shim
+
+    N_x, N_t = WORKLOADS[args.workload]
+    n = N_x + 1
+    S = 32 * n * N_t                      # one sweep: both complex128 fields once
+    B_pc = 6 * S                          # algorithmic bytes per apply
+    peak, peak_src = measured_peak()
+
+    if world > 1:
+        from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
+        dpc = DistributedDiagFFTPC(N_x, N_t, device=local)
+        x = dpc.random_local(seed=rank)
+        y = torch.empty_like(x)
+        apply_fn = lambda: dpc.apply(x, y)
+        handle = dpc
+    else:
+        handle = ParaDiagHandle(N_x, N_t, device=local)
+        rng = np.random.default_rng(0)
+        xh = torch.empty(handle.size, dtype=torch.complex128, pin_memory=True)
+        xn = xh.numpy()
+        # fill in slabs to bound host memory traffic of the generator
+        step = 1 << 24
+        for o in range(0, handle.size, step):
+            m = min(step, handle.size - o)
+            xn[o:o + m] = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+        x = xh.to(dev)
+        y = torch.empty_like(x)
+        apply_fn = lambda: handle.pc_apply(x, y)
+
+    flush = None
+    if 2 * S <= 2 * L2_BYTES:             # working set may live in L2: flush between iterations
+        flush = torch.empty(2 * L2_BYTES // 8, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        apply_fn()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = handle.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.perf_counter()
+    for s, e in ev:
+        if flush is not None:
+            flush.zero_()
+        s.record()
+        apply_fn()
+        e.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = handle.launch_count - launches0
+    ms = sum(s.elapsed_time(e) for s, e in ev) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "pc_applies_per_sec", "value": 1e3 / ms, "unit": "applies/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64 complex)", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: 1D wave control N_x={N_x}, N_t={N_t}, T=2, gamma=1, alpha=1",
+            "vector_bytes": S, "algorithmic_bytes_per_apply": B_pc,
+            "l2": "inputs larger than L2" if flush is None else "L2 flushed between timed iterations",
+            "parallelism": "1 GPU" if world == 1 else f"space slabs <-> frequency slabs over {world} GPUs (all-to-all)",
+        },
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "apply_gbs_algorithmic": B_pc / (ms * 1e-3) / 1e9,
+        "apply_frac_of_hbm_peak": B_pc / (ms * 1e-3) / 1e9 / peak,
+        "wall_s_timed_region": wall,
+    }
+
+    if world == 1:
+        # per-kernel device times (CUDA events on the launching stream), live
+        prof = None
+        reps = 5
+        for _ in range(reps):
+            p = handle.pc_apply_profile(x, y)
+            prof = p if prof is None else {k: prof[k] + p[k] for k in p}
+        prof = {k: v / reps for k, v in prof.items()}
+        tot = sum(prof.values())
+        # algorithmic bytes per launch: each FFT pass and the solve pass read S and write S;
+        # the solve pass is pass A + PCR + pass B, of which pass B carries the read+write sweep
+        dom = max(prof, key=prof.get)
+        alg = {"ifft": 2 * S, "fft": 2 * S, "passB": 2 * S, "passA": S, "pcr": 0.3 * S}[dom]
+        names = {"ifft": "pd_fft_pow2_kernel<inv>", "fft": "pd_fft_pow2_kernel<fwd>", "passA": "pd_solve_passA_kernel",
+                 "pcr": "pd_solve_pcr_kernel", "passB": "pd_solve_passB_kernel"}
+        ach = alg / (prof[dom] * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg, "ms_per_launch": prof[dom],
+                            "share_of_apply": prof[dom] / tot}
+        line["kernels_ms"] = prof
+        line["roofline_whole_apply"] = {"achieved": B_pc / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": B_pc / (ms * 1e-3) / 1e9 / peak,
+                                        "frac_of_nominal_8000": B_pc / (ms * 1e-3) / 1e9 / 8000.0}
+
+        # end to end through the reference-facing python PC with HOST vectors (pinned), every step:
+        # H2D of x, apply, D2H of y
+        DiagFFTPC.configure(N_x=N_x, N_t=N_t, T=2.0, gamma=1.0, device=local)
+        pc = petsc_shim.PC()
+        pc.setPythonContext(DiagFFTPC())
+        pc.setUp()
+        yh = torch.empty(handle.size, dtype=torch.complex128, pin_memory=True)
+        xv, yv = petsc_shim.Vec(xn), petsc_shim.Vec(yh.numpy())
+        xv._a, yv._a = xn, yh.numpy()
+        e2e_steps = max(1, min(args.steps, 5))
+        pc.apply(xv, yv)
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pc.apply(xv, yv)
+        e2e_ms = (time.perf_counter() - t1) / e2e_steps * 1e3
+        line["e2e"] = {"value": 1e3 / e2e_ms, "unit": "applies/s", "h2d_bytes_per_step": S, "d2h_bytes_per_step": S,
+                       "ms_per_step": e2e_ms, "api": "DiagFFTPC.apply(pc, x, y) with host Vec buffers"}
+        pc.destroy()
+        DiagFFTPC._defaults = {}
+
+        # GMRES time-to-solution on the reference's manufactured problem (secondary metric)
+        if not args.no_gmres:
+            try:
+                b = handle.build_rhs()
+                handle.gmres(b, rtol=1e-7)           # warm-up: allocates the Krylov basis
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                _, its, hist, reason = handle.gmres(b, rtol=1e-7)
+                torch.cuda.synchronize()
+                line["gmres"] = {"seconds": time.perf_counter() - t1, "iterations": its, "reason": reason,
+                                 "rtol": 1e-7, "rhs": "manufactured (Build_f/g/IC)"}
+                del b
+            except Exception as ex:  # pragma: no cover
+                line["gmres"] = {"error": str(ex)}
+
+        # CPU baseline: the oracle's restatement on the host cores, bounded sample
+        if not args.no_cpu:
+            try:
+                # one full apply of the same workload when it is affordable, else a smaller N_t slab
+                cN_x, cN_t = N_x, N_t
+                sec, cores = cpu_reference_apply(cN_x, cN_t, steps=2, warmup=0)
+                line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "applies/s", "cores": cores, "kind": "port",
+                                        "sample": f"full {cN_x}x{cN_t} apply (scipy.fft + threaded Thomas), best of 2"}
+            except Exception as ex:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "applies/s", "cores": 0, "kind": "port",
+                                        "sample": f"failed: {ex}"}
+    else:
+        line["e2e"] = None
+        line["dist"] = handle.describe()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES time-to-solution leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,11 @@ int64_t pd_launch_count(const pd_handle* h);
 int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 /* Same with host buffers (PETSc Vec arrays): H2D, apply, D2H, synchronises.     */
 int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host);
+/* One apply with CUDA events recorded on `stream` between its kernels; ms[0..4] receive
+ * the device durations (milliseconds) of {inverse FFT, solve pass A, interface PCR, solve
+ * pass B, forward FFT}.  Synchronises the stream.  Measurement aid for bench.py.           */
+int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev, void* stream, float* ms,
+                        int nms);
 /* DiagFFTPC.applyTranspose (:557-558): upstream raises NotImplementedError;
  * this returns PD_ERR_UNSUPPORTED.                                              */
 int pd_pc_apply_transpose(pd_handle* h, const void* x_dev, void* y_dev, void* stream);

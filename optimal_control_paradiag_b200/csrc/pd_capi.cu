@@ -15,6 +15,7 @@ void pd_set_error(const char* fmt, ...) {
 }
 
 void pd_krylov_free(pd_handle* h);
+void pd_solve_free(pd_handle* h);
 
 extern "C" const char* pd_last_error(void) { return g_err; }
 extern "C" int pd_abi_version(void) { return PD_ABI_VERSION; }
@@ -26,8 +27,8 @@ extern "C" int pd_destroy(pd_handle* h) {
   cudaSetDevice(h->cfg.device);
   pd_krylov_free(h);
   if (h->twiddle) cudaFree(h->twiddle);
-  if (h->red) cudaFree(h->red);
-  if (h->zsep) cudaFree(h->zsep);
+  pd_solve_free(h);
+
   if (h->work) cudaFree(h->work);
   if (h->stage_x) cudaFree(h->stage_x);
   if (h->stage_y) cudaFree(h->stage_y);
@@ -152,6 +153,36 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
   if ((rc = pd_solve_launch(h, h->work, st))) return rc;
   if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
   return PD_OK;
+}
+
+extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev, void* stream, float* ms,
+                                   int nms) {
+  if (!h || !x_dev || !y_dev || !ms || nms < 5) {
+    pd_set_error("pd_pc_apply_profile: invalid argument (need ms[5])");
+    return PD_ERR_INVALID;
+  }
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
+    pd_set_error("pd_pc_apply_profile: handle is sharded");
+    return PD_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_work(h);
+  if (rc) return rc;
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) PD_CUDA(cudaEventCreate(&ev[i]));
+  const int64_t nlines = 2 * (int64_t)h->n;
+  PD_CUDA(cudaEventRecord(ev[0], st));
+  rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st);
+  PD_CUDA(cudaEventRecord(ev[1], st));
+  if (!rc) rc = pd_solve_launch(h, h->work, st, &ev[2]);  // records ev[2] after pass A, ev[3] after PCR
+  PD_CUDA(cudaEventRecord(ev[4], st));
+  if (!rc) rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st);
+  PD_CUDA(cudaEventRecord(ev[5], st));
+  PD_CUDA(cudaStreamSynchronize(st));
+  if (!rc)
+    for (int i = 0; i < 5; ++i) PD_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {

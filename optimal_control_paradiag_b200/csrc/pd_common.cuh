@@ -115,6 +115,6 @@ int pd_fft_plan(pd_handle* h);
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
                   cudaStream_t st);
 int pd_solve_plan(pd_handle* h);
-int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st);
+int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st);

@@ -19,32 +19,42 @@
 // so each k is ONE complex-symmetric Toeplitz tridiagonal matrix with two
 // right-hand sides (rho_+ and conj(rho_-)).
 //
-// Algorithm (layout [field][node][k], k fastest, so a warp reads 512 contiguous
-// bytes per node row): the interior nodes are cut into chunks of L rows with
-// one separator row between chunks.
-//   pass A  (streaming, 1 read sweep): per (k, chunk) a register-resident
-//           forward recurrence yields the first and last entry of the local
-//           solve Tt_L^-1 rho_chunk.
-//   PCR     the separators of one k form a tridiagonal interface system
-//           (P = m/(L+1) unknowns); it is solved by parallel cyclic reduction
-//           held in shared memory, one CTA per 1..4 frequencies.
-//   pass B  (streaming, 1 read + 1 write sweep): per (k, chunk) Thomas with the
-//           now-known separator values, rotation back, store in place.
-// The pivots m_i of the chunk-local factorisation depend on (k, i) only; each
-// CTA regenerates them once into a per-thread shared-memory column and reuses
-// them for all the chunks it visits.
+// Algorithm.  Layout [field][node][k], k fastest, so a warp touches 512
+// contiguous bytes per node row and every access below is coalesced.  The
+// systems are solved by recursive partitioning:
+//   level 0  the m interior rows are cut into chunks of L = 16 rows with one
+//            separator row between chunks.  pass A (1 read sweep of the big
+//            array) runs a register-resident forward recurrence per (k, chunk)
+//            and emits the first/last entry of the local solve.
+//   level l  the separators of level l-1 form a tridiagonal interface system
+//            (Toeplitz except its last diagonal entry -- a structure the reduction
+//            preserves, so its coefficients too are regenerated, never stored).
+//            While it has more than PD_PCR_MAX rows it is reduced again the same way
+//            (generic kernels, 1/17 of the data per level).
+//   top      the last interface system (<= 128 rows per k) is solved by parallel
+//            cyclic reduction held in shared memory, several frequencies per CTA.
+//   back     the generic levels are back-substituted, then pass B (1 read + 1 write
+//            sweep of the big array) runs Thomas per (k, chunk) with the now-known
+//            separator values, rotates back and stores in place.
+// The level-0 pivots m_i depend on (k, i) only; each CTA regenerates them once into a
+// per-thread shared-memory column and reuses them for all the chunks it visits.
+#include <string.h>
+
 #include "pd_common.cuh"
 
-#define PD_L 16          // chunk length (rows held in registers)
-#define PD_KB 128        // frequencies per CTA in the streaming passes
+#define PD_L 16            // chunk length (rows held in registers)
+#define PD_KB 128          // frequencies per CTA in the streaming passes
+#define PD_PCR_MAX 128     // largest interface system handed to the PCR kernel
 #define PD_PCR_THREADS 256
-#define PD_PCR_MAXROWS 8  // rows per thread in the PCR kernel
+#define PD_PCR_MAXROWS 4   // rows per thread in the PCR kernel
+#define PD_MAX_LEVELS 8
 
 struct SolveParams {
   int n, m, K, kbegin, N_t;
-  int P, Llast;
   double h, dt2, c;
-  int64_t plane;  // elements per field plane = n * K
+  int64_t plane;            // elements per field plane = n * K
+  int nlev;                 // number of interface levels (0: single chunk, no interface)
+  int rows[PD_MAX_LEVELS];  // rows[l] = size of the level-l system (rows[0] = m)
 };
 
 struct KCoef {
@@ -84,7 +94,47 @@ __device__ __forceinline__ void rotate_out(const KCoef& kc, cplx zp, cplx zmc, c
   wp = cmake(t.y * kc.sigma, -t.x * kc.sigma);      // -i sigma (d z)
 }
 
-// pivots of the chunk-local LU: m_1 = 1/b, m_i = 1/(b - a^2 m_{i-1})
+// A level system: tridiag(off, d, off) with n rows, d = dmain except the last row (dlast).
+struct Sys {
+  cplx off, dmain, dlast;
+  int n;
+};
+
+// Interface system obtained by cutting `s` into chunks of PD_L rows + separators.
+__device__ __forceinline__ Sys reduce_sys(const Sys& s) {
+  const int P = s.n / (PD_L + 1), Llast = s.n - P * (PD_L + 1);
+  const cplx o2 = cmul(s.off, s.off);
+  // full Toeplitz chunk: alpha = (T^-1)_{11} = m_L, beta = (T^-1)_{1L} = pi_L m_L
+  cplx m = crcp(s.dmain), pi = cmake(1, 0);
+#pragma unroll
+  for (int i = 1; i < PD_L; ++i) {
+    pi = cneg(cmul(pi, cmul(s.off, m)));
+    m = crcp(cfms(o2, m, s.dmain));
+  }
+  const cplx alpha = m, beta = cmul(pi, m);
+  // (T^-1)_{11} of the last chunk (Llast rows, its last diagonal is dlast): upward recurrence
+  cplx afirst = cmake(0, 0);
+  if (Llast > 0) {
+    afirst = crcp(s.dlast);
+    for (int i = 1; i < Llast; ++i) afirst = crcp(cfms(o2, afirst, s.dmain));
+  }
+  Sys r;
+  r.n = P;
+  r.off = cneg(cmul(o2, beta));
+  r.dmain = cfms(o2, cadd(alpha, alpha), s.dmain);
+  // last separator: row P(L+1)-1 of s; if the last chunk is empty it IS the last row of s
+  r.dlast = Llast == 0 ? cfms(o2, alpha, s.dlast) : cfms(o2, cadd(alpha, afirst), s.dmain);
+  return r;
+}
+
+__device__ __forceinline__ Sys level_sys(const KCoef& kc, const SolveParams& sp, int level) {
+  Sys s;
+  s.off = kc.a; s.dmain = kc.b; s.dlast = kc.b; s.n = sp.m;
+  for (int l = 0; l < level; ++l) s = reduce_sys(s);
+  return s;
+}
+
+// pivots of the level-0 chunk-local LU: m_1 = 1/b, m_i = 1/(b - a^2 m_{i-1})
 __device__ __forceinline__ void fill_pivots(const KCoef& kc, cplx (*mtab)[PD_KB], int tid) {
   const cplx a2 = cmul(kc.a, kc.a);
   cplx m = crcp(kc.b);
@@ -96,9 +146,15 @@ __device__ __forceinline__ void fill_pivots(const KCoef& kc, cplx (*mtab)[PD_KB]
   }
 }
 
+// Workspace of the interface levels (device pointers, by value in kernel params).
+struct Levels {
+  cplx* R[PD_MAX_LEVELS];   // R[l], l >= 1: [rows[l]][2][K]  rhs, overwritten by the solution
+  cplx* FL[PD_MAX_LEVELS];  // FL[l], l >= 0: [rows[l+1] + 1][4][K]  (f+, l+, f-, l-) per chunk
+};
+
 // ------------------------------------------------------------------- pass A
 __global__ void __launch_bounds__(PD_KB)
-pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ red, SolveParams sp) {
+pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ fl0, SolveParams sp) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = blockIdx.x * PD_KB + tid;
@@ -108,8 +164,9 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ red, SolveP
   fill_pivots(kc, mtab, tid);
   const cplx* wu = w + kc_idx;
   const cplx* wp = w + sp.plane + kc_idx;
-  for (int c = blockIdx.y; c <= sp.P; c += gridDim.y) {
-    const int Lc = c < sp.P ? PD_L : sp.Llast;
+  const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
+  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+    const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
     cplx ru[PD_L], rp_[PD_L];
 #pragma unroll
@@ -138,7 +195,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ red, SolveP
       }
     }
     if (valid) {
-      cplx* r = red + ((int64_t)c * 4) * sp.K + kk;
+      cplx* r = fl0 + ((int64_t)c * 4) * sp.K + kk;
       r[0] = fP;
       r[sp.K] = dP;
       r[2 * (int64_t)sp.K] = fM;
@@ -147,66 +204,186 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ red, SolveP
   }
 }
 
-// ------------------------------------------------------ interface system (PCR)
-// Rows are kept normalised (unit diagonal): (lo, 1, up | rP, rM).
-template <int KPB>
+// Right-hand side of row q of the level-`lev` interface system (lev >= 1), assembled from the
+// level below: rhs_q = rhs_below(separator q) - off_below (l_q + f_{q+1}).
+__device__ __forceinline__ void assemble_row(const cplx* __restrict__ w, const Levels& lv, const SolveParams& sp,
+                                             const KCoef& kc, cplx off_below, int lev, int q, int kk, cplx& rP,
+                                             cplx& rM) {
+  const int64_t K = sp.K;
+  const int64_t srow = (int64_t)q * (PD_L + 1) + PD_L;  // separator row index in the level below
+  if (lev == 1) {
+    rotate_in(kc, w[(srow + 1) * K + kk], w[sp.plane + (srow + 1) * K + kk], rP, rM);
+  } else {
+    const cplx* rb = lv.R[lev - 1] + srow * 2 * K + kk;
+    rP = rb[0];
+    rM = rb[K];
+  }
+  const cplx* f0 = lv.FL[lev - 1] + ((int64_t)q * 4) * K + kk;  // chunk q   : (f+, l+, f-, l-)
+  const cplx* f1 = f0 + 4 * K;                                  // chunk q+1
+  rP = cfms(off_below, cadd(f0[K], f1[0]), rP);
+  rM = cfms(off_below, cadd(f0[3 * K], f1[2 * K]), rM);
+}
+
+// ------------------------------------------------ generic level: reduce (lev >= 1)
+// thread = (k, chunk c of level lev).  Assembles and stores the rhs of its PD_L rows and of its
+// trailing separator, runs the forward recurrences, emits (f, l) of the chunk.
+__global__ void __launch_bounds__(PD_KB)
+pd_solve_level_reduce_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int lev) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.K) return;
+  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const Sys below = level_sys(kc, sp, lev - 1);
+  const Sys s = reduce_sys(below);
+  const int64_t K = sp.K;
+  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_L + 1);
+  const cplx o2 = cmul(s.off, s.off);
+  cplx* R = lv.R[lev];
+  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+    const int Lc = c < P ? PD_L : Llast;
+    const int q0 = c * (PD_L + 1);
+    cplx dP = cmake(0, 0), dM = cmake(0, 0), fP = cmake(0, 0), fM = cmake(0, 0);
+    cplx pi = cmake(1, 0), m = cmake(0, 0);
+    for (int i = 0; i < Lc; ++i) {
+      const int q = q0 + i;
+      cplx rP, rM;
+      assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
+      R[((int64_t)q * 2) * K + kk] = rP;
+      R[((int64_t)q * 2 + 1) * K + kk] = rM;
+      const cplx dq = (q == s.n - 1) ? s.dlast : s.dmain;
+      if (i > 0) pi = cneg(cmul(pi, cmul(s.off, m)));
+      m = crcp(cfms(o2, m, dq));
+      dP = cmul(cfms(s.off, dP, rP), m);
+      dM = cmul(cfms(s.off, dM, rM), m);
+      fP = cfma(pi, dP, fP);
+      fM = cfma(pi, dM, fM);
+    }
+    if (c < P) {  // trailing separator row: only assembled and stored
+      const int q = q0 + PD_L;
+      cplx rP, rM;
+      assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
+      R[((int64_t)q * 2) * K + kk] = rP;
+      R[((int64_t)q * 2 + 1) * K + kk] = rM;
+    }
+    cplx* r = lv.FL[lev] + ((int64_t)c * 4) * K + kk;
+    r[0] = fP;
+    r[K] = dP;
+    r[2 * K] = fM;
+    r[3 * K] = dM;
+  }
+}
+
+// ------------------------------------------- generic level: back substitution (lev >= 1)
+// thread = (k, chunk c).  Separator solutions live in R[lev+1]; the chunk rows (and a copy of the
+// trailing separator) are overwritten by the solution in R[lev].
+__global__ void __launch_bounds__(PD_KB)
+pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.K) return;
+  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const Sys s = level_sys(kc, sp, lev);
+  const int64_t K = sp.K;
+  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_L + 1);
+  const cplx o2 = cmul(s.off, s.off);
+  cplx* R = lv.R[lev];
+  const cplx* Z = lv.R[lev + 1];
+  const cplx zero = cmake(0, 0);
+  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+    const int Lc = c < P ? PD_L : Llast;
+    const int q0 = c * (PD_L + 1);
+    cplx zlP = zero, zlM = zero, zrP = zero, zrM = zero;
+    if (c > 0) {
+      zlP = Z[((int64_t)(c - 1) * 2) * K + kk];
+      zlM = Z[((int64_t)(c - 1) * 2 + 1) * K + kk];
+    }
+    if (c < P) {
+      zrP = Z[((int64_t)c * 2) * K + kk];
+      zrM = Z[((int64_t)c * 2 + 1) * K + kk];
+      R[((int64_t)(q0 + PD_L) * 2) * K + kk] = zrP;
+      R[((int64_t)(q0 + PD_L) * 2 + 1) * K + kk] = zrM;
+    }
+    cplx dP[PD_L], dM[PD_L], mm[PD_L];
+    cplx pP = zlP, pM = zlM, m = zero;
+#pragma unroll
+    for (int i = 0; i < PD_L; ++i) {
+      if (i < Lc) {
+        const int q = q0 + i;
+        cplx rP = R[((int64_t)q * 2) * K + kk], rM = R[((int64_t)q * 2 + 1) * K + kk];
+        if (i == Lc - 1) {
+          rP = cfms(s.off, zrP, rP);
+          rM = cfms(s.off, zrM, rM);
+        }
+        const cplx dq = (q == s.n - 1) ? s.dlast : s.dmain;
+        m = crcp(cfms(o2, m, dq));
+        mm[i] = m;
+        pP = cmul(cfms(s.off, pP, rP), m);
+        pM = cmul(cfms(s.off, pM, rM), m);
+        dP[i] = pP;
+        dM[i] = pM;
+      }
+    }
+    cplx nP = zero, nM = zero;
+#pragma unroll
+    for (int i = PD_L - 1; i >= 0; --i) {
+      if (i < Lc) {
+        if (i < Lc - 1) {
+          const cplx cp = cmul(s.off, mm[i]);
+          nP = cfms(cp, nP, dP[i]);
+          nM = cfms(cp, nM, dM[i]);
+        } else {
+          nP = dP[i];
+          nM = dM[i];
+        }
+        R[((int64_t)(q0 + i) * 2) * K + kk] = nP;
+        R[((int64_t)(q0 + i) * 2 + 1) * K + kk] = nM;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------ top interface system (PCR in smem)
+// One CTA solves the top-level systems of `kpb` consecutive frequencies (n <= PD_PCR_MAX rows
+// each, two right-hand sides) by parallel cyclic reduction.  Rows are kept normalised (unit
+// diagonal): (lo, 1, up | rP, rM).  smem slot = ks * n + q.
 __global__ void __launch_bounds__(PD_PCR_THREADS)
-pd_solve_pcr_kernel(cplx* __restrict__ w, const cplx* __restrict__ red, cplx* __restrict__ zsep,
-                    SolveParams sp) {
+pd_solve_pcr_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int lev, int kpb) {
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
-  const int P = sp.P;
-  const int rows = P * KPB;
+  const int n = sp.rows[lev];
+  const int rows = n * kpb;
   cplx* s_lo = reinterpret_cast<cplx*>(pd_smem_raw);
   cplx* s_up = s_lo + rows;
   cplx* s_rp = s_up + rows;
   cplx* s_rm = s_rp + rows;
   const int tid = threadIdx.x;
-  const int kk0 = blockIdx.x * KPB;
+  const int kk0 = blockIdx.x * kpb;
+  const int64_t K = sp.K;
 
-  // build: row index idx -> (q = idx / KPB, ks = idx % KPB); smem slot = ks * P + q
+  // build: idx -> (q = idx / kpb, ks = idx % kpb) so that consecutive threads read consecutive k
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
-    const int q = idx / KPB, ks = idx - q * KPB;
+    const int q = idx / kpb, ks = idx - q * kpb;
     int kk = kk0 + ks;
     if (kk >= sp.K) kk = sp.K - 1;
     const KCoef kc = make_coef(sp.kbegin + kk, sp);
-    const cplx a2 = cmul(kc.a, kc.a);
-    // alpha_L = m_L, beta_L = pi_L m_L; alpha of the (possibly shorter) last chunk
-    cplx m = crcp(kc.b), pi = cmake(1, 0), alast = cmake(0, 0);
-    if (sp.Llast == 1) alast = m;
-#pragma unroll
-    for (int i = 1; i < PD_L; ++i) {
-      pi = cneg(cmul(pi, cmul(kc.a, m)));
-      m = crcp(cfms(a2, m, kc.b));
-      if (i + 1 == sp.Llast) alast = m;
-    }
-    const cplx alpha = m, beta = cmul(pi, m);
-    const cplx aright = (q + 1 < P) ? alpha : alast;
-    cplx di = cfms(a2, cadd(alpha, aright), kc.b);
-    const cplx dinv = crcp(di);
-    const cplx off = cneg(cmul(a2, beta));
-    const int j = q * (PD_L + 1) + PD_L + 1;  // node of separator q
+    const Sys below = level_sys(kc, sp, lev - 1);
+    const Sys s = reduce_sys(below);
     cplx rP, rM;
-    rotate_in(kc, w[(int64_t)j * sp.K + kk], w[sp.plane + (int64_t)j * sp.K + kk], rP, rM);
-    const cplx* r0 = red + ((int64_t)q * 4) * sp.K + kk;        // chunk q   : (f+, l+, f-, l-)
-    const cplx* r1 = red + ((int64_t)(q + 1) * 4) * sp.K + kk;  // chunk q+1
-    rP = cfms(kc.a, cadd(r0[sp.K], r1[0]), rP);
-    rM = cfms(kc.a, cadd(r0[3 * (int64_t)sp.K], r1[2 * (int64_t)sp.K]), rM);
-    const int slot = ks * P + q;
-    s_lo[slot] = q > 0 ? cmul(off, dinv) : cmake(0, 0);
-    s_up[slot] = q + 1 < P ? cmul(off, dinv) : cmake(0, 0);
+    assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
+    const cplx dinv = crcp(q == n - 1 ? s.dlast : s.dmain);
+    const int slot = ks * n + q;
+    s_lo[slot] = q > 0 ? cmul(s.off, dinv) : cmake(0, 0);
+    s_up[slot] = q + 1 < n ? cmul(s.off, dinv) : cmake(0, 0);
     s_rp[slot] = cmul(rP, dinv);
     s_rm[slot] = cmul(rM, dinv);
   }
   __syncthreads();
 
-  for (int delta = 1; delta < P; delta <<= 1) {
+  for (int delta = 1; delta < n; delta <<= 1) {
     cplx nlo[PD_PCR_MAXROWS], nup[PD_PCR_MAXROWS], nrp[PD_PCR_MAXROWS], nrm[PD_PCR_MAXROWS];
 #pragma unroll
     for (int it = 0; it < PD_PCR_MAXROWS; ++it) {
       const int idx = tid + it * PD_PCR_THREADS;
       if (idx < rows) {
-        const int q = idx / KPB, ks = idx - q * KPB;
-        const int slot = ks * P + q;
+        const int q = idx / kpb, ks = idx - q * kpb;
+        const int slot = ks * n + q;
         const cplx l = s_lo[slot], u = s_up[slot];
         cplx diag = cmake(1, 0), rp = s_rp[slot], rm = s_rm[slot];
         cplx l2 = cmake(0, 0), u2 = cmake(0, 0);
@@ -217,7 +394,7 @@ pd_solve_pcr_kernel(cplx* __restrict__ w, const cplx* __restrict__ red, cplx* __
           rm = cfms(l, s_rm[sl], rm);
           l2 = cneg(cmul(l, s_lo[sl]));
         }
-        if (q + delta < P) {
+        if (q + delta < n) {
           const int sl = slot + delta;
           diag = cfms(u, s_lo[sl], diag);
           rp = cfms(u, s_rp[sl], rp);
@@ -236,8 +413,8 @@ pd_solve_pcr_kernel(cplx* __restrict__ w, const cplx* __restrict__ red, cplx* __
     for (int it = 0; it < PD_PCR_MAXROWS; ++it) {
       const int idx = tid + it * PD_PCR_THREADS;
       if (idx < rows) {
-        const int q = idx / KPB, ks = idx - q * KPB;
-        const int slot = ks * P + q;
+        const int q = idx / kpb, ks = idx - q * kpb;
+        const int slot = ks * n + q;
         s_lo[slot] = nlo[it];
         s_up[slot] = nup[it];
         s_rp[slot] = nrp[it];
@@ -247,21 +424,14 @@ pd_solve_pcr_kernel(cplx* __restrict__ w, const cplx* __restrict__ red, cplx* __
     __syncthreads();
   }
 
-  // write the interface values (for pass B) and the finished separator rows
+  cplx* R = lv.R[lev];
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
-    const int q = idx / KPB, ks = idx - q * KPB;
+    const int q = idx / kpb, ks = idx - q * kpb;
     const int kk = kk0 + ks;
     if (kk >= sp.K) continue;
-    const int slot = ks * P + q;
-    const cplx zp = s_rp[slot], zmc = s_rm[slot];
-    zsep[((int64_t)q * 2) * sp.K + kk] = zp;
-    zsep[((int64_t)q * 2 + 1) * sp.K + kk] = zmc;
-    const KCoef kc = make_coef(sp.kbegin + kk, sp);
-    cplx wu, wp;
-    rotate_out(kc, zp, zmc, wu, wp);
-    const int j = q * (PD_L + 1) + PD_L + 1;
-    w[(int64_t)j * sp.K + kk] = wu;
-    w[sp.plane + (int64_t)j * sp.K + kk] = wp;
+    const int slot = ks * n + q;
+    R[((int64_t)q * 2) * K + kk] = s_rp[slot];
+    R[((int64_t)q * 2 + 1) * K + kk] = s_rm[slot];
   }
 }
 
@@ -278,8 +448,9 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
   cplx* wu = w + kc_idx;
   cplx* wp = w + sp.plane + kc_idx;
   const cplx zero = cmake(0, 0);
-  for (int c = blockIdx.y; c <= sp.P; c += gridDim.y) {
-    const int Lc = c < sp.P ? PD_L : sp.Llast;
+  const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
+  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+    const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
     cplx dP[PD_L], dM[PD_L];
 #pragma unroll
@@ -294,7 +465,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       zlP = zsep[((int64_t)(c - 1) * 2) * sp.K + kc_idx];
       zlM = zsep[((int64_t)(c - 1) * 2 + 1) * sp.K + kc_idx];
     }
-    if (c < sp.P) {
+    if (c < P) {
       zrP = zsep[((int64_t)c * 2) * sp.K + kc_idx];
       zrM = zsep[((int64_t)c * 2 + 1) * sp.K + kc_idx];
     }
@@ -337,12 +508,18 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
         }
       }
     }
+    if (valid && c < P) {  // the separator row that follows this chunk
+      cplx ou, op;
+      rotate_out(kc, zrP, zrM, ou, op);
+      wu[(int64_t)(j0 + PD_L) * sp.K] = ou;
+      wp[(int64_t)(j0 + PD_L) * sp.K] = op;
+    }
     // Dirichlet rows: output exactly 0 (:482, bcs :44-45)
     if (valid && c == 0) {
       wu[0] = zero;
       wp[0] = zero;
     }
-    if (valid && c == sp.P) {
+    if (valid && c == P) {
       wu[(int64_t)(sp.n - 1) * sp.K] = zero;
       wp[(int64_t)(sp.n - 1) * sp.K] = zero;
     }
@@ -350,75 +527,122 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
 }
 
 // --------------------------------------------------------------- host side
-static int pcr_kpb(int P) {
-  // largest KPB in {4,2,1} with rows <= threads*maxrows and <= ~96 KB of shared memory
-  for (int kpb = 4; kpb >= 1; kpb >>= 1) {
-    size_t rows = (size_t)P * kpb;
-    if (rows <= (size_t)PD_PCR_THREADS * PD_PCR_MAXROWS && rows * 64 <= 96 * 1024) return kpb;
+struct SolvePlan {
+  int nlev;
+  int rows[PD_MAX_LEVELS];
+  cplx* R[PD_MAX_LEVELS];
+  cplx* FL[PD_MAX_LEVELS];
+};
+
+static SolvePlan* plan_of(pd_handle* h) { return reinterpret_cast<SolvePlan*>(h->red); }
+
+void pd_solve_free(pd_handle* h) {
+  SolvePlan* pl = plan_of(h);
+  if (!pl) return;
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) {
+    if (pl->R[l]) cudaFree(pl->R[l]);
+    if (pl->FL[l]) cudaFree(pl->FL[l]);
   }
-  return 1;
+  delete pl;
+  h->red = nullptr;
 }
 
 int pd_solve_plan(pd_handle* h) {
+  SolvePlan* pl = new SolvePlan();
+  memset(pl, 0, sizeof(*pl));
+  h->red = reinterpret_cast<cplx*>(pl);
   h->L = PD_L;
-  h->P = h->m / (PD_L + 1);
-  h->Llast = h->m % (PD_L + 1);
   const size_t K = (size_t)h->kcount;
-  if ((size_t)h->P > (size_t)PD_PCR_THREADS * PD_PCR_MAXROWS || (size_t)h->P * 64 > 227 * 1024) {
-    pd_set_error("N_x = %d gives an interface system of %d rows per frequency; the shared-memory PCR "
-                 "kernel supports at most %d", h->cfg.N_x, h->P, PD_PCR_THREADS * PD_PCR_MAXROWS);
-    return PD_ERR_INVALID;
+  // rows[0] = m; reduce while the interface is too large for the PCR kernel
+  pl->rows[0] = h->m;
+  int l = 0;
+  while (true) {
+    const int next = pl->rows[l] / (PD_L + 1);
+    if (l + 1 >= PD_MAX_LEVELS) {
+      pd_set_error("N_x = %d needs more than %d partition levels", h->cfg.N_x, PD_MAX_LEVELS);
+      return PD_ERR_INVALID;
+    }
+    pl->rows[l + 1] = next;
+    ++l;
+    if (next <= PD_PCR_MAX) break;
   }
-  size_t red_bytes = sizeof(cplx) * (size_t)(h->P + 1) * 4 * K;
-  size_t zs_bytes = sizeof(cplx) * (size_t)(h->P > 0 ? h->P : 1) * 2 * K;
-  PD_CUDA(cudaMalloc(&h->red, red_bytes));
-  PD_CUDA(cudaMalloc(&h->zsep, zs_bytes));
-  h->ws_bytes += red_bytes + zs_bytes;
+  // l is the top level: solved by PCR when it has rows, absent when rows == 0
+  pl->nlev = pl->rows[l] > 0 ? l : l - 1;
+  h->P = pl->rows[1];
+  h->Llast = h->m - h->P * (PD_L + 1);
+  for (int lev = 0; lev <= pl->nlev; ++lev) {
+    if (lev >= 1) {
+      size_t bytes = sizeof(cplx) * (size_t)pl->rows[lev] * 2 * K;
+      PD_CUDA(cudaMalloc(&pl->R[lev], bytes));
+      h->ws_bytes += bytes;
+    }
+    if (lev < pl->nlev) {
+      size_t bytes = sizeof(cplx) * (size_t)(pl->rows[lev + 1] + 1) * 4 * K;
+      PD_CUDA(cudaMalloc(&pl->FL[lev], bytes));
+      h->ws_bytes += bytes;
+    }
+  }
   return PD_OK;
 }
 
-int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st) {
-  SolveParams sp;
-  sp.n = h->n; sp.m = h->m; sp.K = h->kcount; sp.kbegin = h->kbegin; sp.N_t = h->cfg.N_t;
-  sp.P = h->P; sp.Llast = h->Llast;
-  sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
-  sp.plane = (int64_t)h->n * h->kcount;
-  const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
-  int nchunks = sp.P + 1;
-  // enough CTAs for ~6 resident per SM; more chunks than that are looped over
-  int ny = (h->num_sms * 6 + kblocks - 1) / kblocks;
+static dim3 stream_grid(const pd_handle* h, int K, int nchunks) {
+  const int kblocks = (K + PD_KB - 1) / PD_KB;
+  // enough CTAs for ~8 resident per SM; more chunks than that are looped over
+  int ny = (h->num_sms * 8 + kblocks - 1) / kblocks;
   if (ny > nchunks) ny = nchunks;
   if (ny < 1) ny = 1;
   if (ny > 65535) ny = 65535;
-  dim3 grid(kblocks, ny);
-  if (sp.P > 0) {
-    pd_solve_passA_kernel<<<grid, PD_KB, 0, st>>>(w, h->red, sp);
+  return dim3(kblocks, ny);
+}
+
+int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev) {
+  SolvePlan* pl = plan_of(h);
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = h->n; sp.m = h->m; sp.K = h->kcount; sp.kbegin = h->kbegin; sp.N_t = h->cfg.N_t;
+  sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
+  sp.plane = (int64_t)h->n * h->kcount;
+  sp.nlev = pl->nlev;
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
+  Levels lv;
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.FL[l] = pl->FL[l]; }
+  const int top = pl->nlev;
+  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
+  if (top >= 1) {
+    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.FL[0], sp);
     PD_CHECK_LAUNCH();
     h->launches++;
-    const int kpb = pcr_kpb(sp.P);
-    const size_t smem = (size_t)sp.P * kpb * 64;
-    const int nblk = (sp.K + kpb - 1) / kpb;
-    switch (kpb) {
-      case 4:
-        PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-        pd_solve_pcr_kernel<4><<<nblk, PD_PCR_THREADS, smem, st>>>(w, h->red, h->zsep, sp);
-        break;
-      case 2:
-        PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-        pd_solve_pcr_kernel<2><<<nblk, PD_PCR_THREADS, smem, st>>>(w, h->red, h->zsep, sp);
-        break;
-      default:
-        PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-        pd_solve_pcr_kernel<1><<<nblk, PD_PCR_THREADS, smem, st>>>(w, h->red, h->zsep, sp);
-        break;
+    if (ev) cudaEventRecord(ev[0], st);
+    for (int lev = 1; lev < top; ++lev) {
+      pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(w, lv, sp, lev);
+      PD_CHECK_LAUNCH();
+      h->launches++;
     }
-    PD_CHECK_LAUNCH();
-    h->launches++;
+    {
+      const int n = sp.rows[top];
+      int kpb = (PD_PCR_THREADS * PD_PCR_MAXROWS) / n;
+      if (kpb > 32) kpb = 32;
+      // keep at least ~2 CTAs per SM when the frequency count allows it
+      while (kpb > 4 && (sp.K + kpb - 1) / kpb < 2 * h->num_sms) kpb >>= 1;
+      if (kpb < 1) kpb = 1;
+      const size_t smem = (size_t)n * kpb * 64;
+      const int nblk = (sp.K + kpb - 1) / kpb;
+      PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(w, lv, sp, top, kpb);
+      PD_CHECK_LAUNCH();
+      h->launches++;
+    }
+    for (int lev = top - 1; lev >= 1; --lev) {
+      pd_solve_level_back_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+      PD_CHECK_LAUNCH();
+      h->launches++;
+    }
+    if (ev) cudaEventRecord(ev[1], st);
+  } else if (ev) {
+    cudaEventRecord(ev[0], st);
+    cudaEventRecord(ev[1], st);
   }
-  pd_solve_passB_kernel<<<grid, PD_KB, 0, st>>>(w, h->zsep, sp);
+  pd_solve_passB_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;

@@ -91,6 +91,13 @@ class ParaDiagHandle:
                                    self._stream()))
         return y
 
+    def pc_apply_profile(self, x, y):
+        """One apply with per-kernel CUDA-event timing: dict of milliseconds."""
+        ms = (C.c_float * 5)()
+        check(self.lib.pd_pc_apply_profile(self._h, self._ptr(x, self.size, "x"), self._ptr(y, self.size, "y"),
+                                           self._stream(), ms, 5))
+        return dict(zip(("ifft", "passA", "pcr", "passB", "fft"), [float(v) for v in ms]))
+
     def pc_apply_host(self, x, y=None):
         """Same through host buffers (numpy complex128): H2D, apply, D2H."""
         x = np.ascontiguousarray(x, dtype=np.complex128).reshape(-1)
