@@ -87,8 +87,7 @@ struct pd_handle {
   int L;       // chunk length
   int P;       // separators (interface unknowns per system)
   int Llast;   // rows in the last chunk
-  cplx* red;   // [P+1][4][kcount]  chunk functionals (f+, l+, f-, l-)
-  cplx* zsep;  // [P][2][kcount]    interface solutions (zeta+, conj-form zeta-)
+  void* solve_plan;  // SolvePlan of pd_solve.cu: level sizes and interface workspaces
 
   // work vector (2, n, N_t) for the single-GPU apply
   cplx* work;

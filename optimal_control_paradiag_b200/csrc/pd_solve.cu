@@ -22,17 +22,18 @@
 // Algorithm.  Layout [field][node][k], k fastest, so a warp touches 512
 // contiguous bytes per node row and every access below is coalesced.  The
 // systems are solved by recursive partitioning:
-//   level 0  the m interior rows are cut into chunks of L = 16 rows with one
+//   level 0  the m interior rows are cut into chunks of PD_L = 16 rows with one
 //            separator row between chunks.  pass A (1 read sweep of the big
-//            array) runs a register-resident forward recurrence per (k, chunk)
-//            and emits the first/last entry of the local solve.
+//            array) runs a register-resident forward recurrence per (k, chunk),
+//            emits the first entry f_c of the local solve and folds the last
+//            entry l_c into the right-hand side of the separator that follows.
 //   level l  the separators of level l-1 form a tridiagonal interface system
 //            (Toeplitz except its last diagonal entry -- a structure the reduction
 //            preserves, so its coefficients too are regenerated, never stored).
 //            While it has more than PD_PCR_MAX rows it is reduced again the same way
-//            (generic kernels, 1/17 of the data per level).
+//            with chunks of PD_LG = 32 rows (generic kernels, ~3 % of the data).
 //   top      the last interface system (<= 128 rows per k) is solved by parallel
-//            cyclic reduction held in shared memory, several frequencies per CTA.
+//            cyclic reduction held in shared memory, up to 32 frequencies per CTA.
 //   back     the generic levels are back-substituted, then pass B (1 read + 1 write
 //            sweep of the big array) runs Thomas per (k, chunk) with the now-known
 //            separator values, rotates back and stores in place.
@@ -42,7 +43,8 @@
 
 #include "pd_common.cuh"
 
-#define PD_L 16            // chunk length (rows held in registers)
+#define PD_L 16            // level-0 chunk length (rows held in registers)
+#define PD_LG 32           // chunk length of the generic interface levels
 #define PD_KB 128          // frequencies per CTA in the streaming passes
 #define PD_PCR_MAX 128     // largest interface system handed to the PCR kernel
 #define PD_PCR_THREADS 256
@@ -53,7 +55,7 @@ struct SolveParams {
   int n, m, K, kbegin, N_t;
   double h, dt2, c;
   int64_t plane;            // elements per field plane = n * K
-  int nlev;                 // number of interface levels (0: single chunk, no interface)
+  int nlev;                 // top interface level (0: single chunk, no interface)
   int rows[PD_MAX_LEVELS];  // rows[l] = size of the level-l system (rows[0] = m)
 };
 
@@ -100,14 +102,15 @@ struct Sys {
   int n;
 };
 
-// Interface system obtained by cutting `s` into chunks of PD_L rows + separators.
-__device__ __forceinline__ Sys reduce_sys(const Sys& s) {
-  const int P = s.n / (PD_L + 1), Llast = s.n - P * (PD_L + 1);
+__device__ __host__ __forceinline__ int chunk_len(int level) { return level == 0 ? PD_L : PD_LG; }
+
+// Interface system obtained by cutting `s` into chunks of L rows + one separator each.
+__device__ __forceinline__ Sys reduce_sys(const Sys& s, int L) {
+  const int P = s.n / (L + 1), Llast = s.n - P * (L + 1);
   const cplx o2 = cmul(s.off, s.off);
   // full Toeplitz chunk: alpha = (T^-1)_{11} = m_L, beta = (T^-1)_{1L} = pi_L m_L
   cplx m = crcp(s.dmain), pi = cmake(1, 0);
-#pragma unroll
-  for (int i = 1; i < PD_L; ++i) {
+  for (int i = 1; i < L; ++i) {
     pi = cneg(cmul(pi, cmul(s.off, m)));
     m = crcp(cfms(o2, m, s.dmain));
   }
@@ -130,7 +133,7 @@ __device__ __forceinline__ Sys reduce_sys(const Sys& s) {
 __device__ __forceinline__ Sys level_sys(const KCoef& kc, const SolveParams& sp, int level) {
   Sys s;
   s.off = kc.a; s.dmain = kc.b; s.dlast = kc.b; s.n = sp.m;
-  for (int l = 0; l < level; ++l) s = reduce_sys(s);
+  for (int l = 0; l < level; ++l) s = reduce_sys(s, chunk_len(l));
   return s;
 }
 
@@ -147,14 +150,19 @@ __device__ __forceinline__ void fill_pivots(const KCoef& kc, cplx (*mtab)[PD_KB]
 }
 
 // Workspace of the interface levels (device pointers, by value in kernel params).
+//   R[l], l >= 1 : [rows[l]][2][K]       written by level l-1 as  rhs_sep - off_{l-1} l_c ; the
+//                                        final right-hand side of row q is R[l][q] - off_{l-1} F[l-1][q+1];
+//                                        overwritten by the solution on the way back
+//   F[l], l >= 0 : [rows[l+1] + 1][2][K] f_c = first entry of chunk c's local solve
 struct Levels {
-  cplx* R[PD_MAX_LEVELS];   // R[l], l >= 1: [rows[l]][2][K]  rhs, overwritten by the solution
-  cplx* FL[PD_MAX_LEVELS];  // FL[l], l >= 0: [rows[l+1] + 1][4][K]  (f+, l+, f-, l-) per chunk
+  cplx* R[PD_MAX_LEVELS];
+  cplx* F[PD_MAX_LEVELS];
 };
 
 // ------------------------------------------------------------------- pass A
 __global__ void __launch_bounds__(PD_KB)
-pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ fl0, SolveParams sp) {
+pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
+                      SolveParams sp) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = blockIdx.x * PD_KB + tid;
@@ -164,16 +172,18 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ fl0, SolveP
   fill_pivots(kc, mtab, tid);
   const cplx* wu = w + kc_idx;
   const cplx* wp = w + sp.plane + kc_idx;
+  const int64_t K = sp.K;
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
   for (int c = blockIdx.y; c <= P; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
-    cplx ru[PD_L], rp_[PD_L];
+    // chunk rows and (c < P) the separator row that follows: index PD_L
+    cplx ru[PD_L + 1], rp_[PD_L + 1];
 #pragma unroll
-    for (int i = 0; i < PD_L; ++i) {
-      if (i < Lc) {
-        ru[i] = wu[(int64_t)(j0 + i) * sp.K];
-        rp_[i] = wp[(int64_t)(j0 + i) * sp.K];
+    for (int i = 0; i < PD_L + 1; ++i) {
+      if (i < Lc || (i == PD_L && c < P)) {
+        ru[i] = wu[(int64_t)(j0 + i) * K];
+        rp_[i] = wp[(int64_t)(j0 + i) * K];
       }
     }
     cplx dP = cmake(0, 0), dM = cmake(0, 0), fP = cmake(0, 0), fM = cmake(0, 0);
@@ -195,60 +205,45 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ fl0, SolveP
       }
     }
     if (valid) {
-      cplx* r = fl0 + ((int64_t)c * 4) * sp.K + kk;
-      r[0] = fP;
-      r[sp.K] = dP;
-      r[2 * (int64_t)sp.K] = fM;
-      r[3 * (int64_t)sp.K] = dM;
+      F0[((int64_t)c * 2) * K + kk] = fP;
+      F0[((int64_t)c * 2 + 1) * K + kk] = fM;
+      if (c < P) {
+        cplx sP, sM;
+        rotate_in(kc, ru[PD_L], rp_[PD_L], sP, sM);
+        R1[((int64_t)c * 2) * K + kk] = cfms(kc.a, dP, sP);      // rho_sep - a l_c
+        R1[((int64_t)c * 2 + 1) * K + kk] = cfms(kc.a, dM, sM);
+      }
     }
   }
 }
 
-// Right-hand side of row q of the level-`lev` interface system (lev >= 1), assembled from the
-// level below: rhs_q = rhs_below(separator q) - off_below (l_q + f_{q+1}).
-__device__ __forceinline__ void assemble_row(const cplx* __restrict__ w, const Levels& lv, const SolveParams& sp,
-                                             const KCoef& kc, cplx off_below, int lev, int q, int kk, cplx& rP,
-                                             cplx& rM) {
-  const int64_t K = sp.K;
-  const int64_t srow = (int64_t)q * (PD_L + 1) + PD_L;  // separator row index in the level below
-  if (lev == 1) {
-    rotate_in(kc, w[(srow + 1) * K + kk], w[sp.plane + (srow + 1) * K + kk], rP, rM);
-  } else {
-    const cplx* rb = lv.R[lev - 1] + srow * 2 * K + kk;
-    rP = rb[0];
-    rM = rb[K];
-  }
-  const cplx* f0 = lv.FL[lev - 1] + ((int64_t)q * 4) * K + kk;  // chunk q   : (f+, l+, f-, l-)
-  const cplx* f1 = f0 + 4 * K;                                  // chunk q+1
-  rP = cfms(off_below, cadd(f0[K], f1[0]), rP);
-  rM = cfms(off_below, cadd(f0[3 * K], f1[2 * K]), rM);
-}
-
-// ------------------------------------------------ generic level: reduce (lev >= 1)
-// thread = (k, chunk c of level lev).  Assembles and stores the rhs of its PD_L rows and of its
-// trailing separator, runs the forward recurrences, emits (f, l) of the chunk.
+// ------------------------------------------------ generic level: reduce (1 <= lev < top)
+// thread = (k, chunk c of level lev).  Finalises and stores the rhs of its rows, runs the forward
+// recurrences, emits f_c and the partial rhs of its trailing separator for level lev + 1.
 __global__ void __launch_bounds__(PD_KB)
-pd_solve_level_reduce_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int lev) {
+pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const KCoef kc = make_coef(sp.kbegin + kk, sp);
   const Sys below = level_sys(kc, sp, lev - 1);
-  const Sys s = reduce_sys(below);
+  const Sys s = reduce_sys(below, chunk_len(lev - 1));
   const int64_t K = sp.K;
-  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_L + 1);
+  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_LG + 1);
   const cplx o2 = cmul(s.off, s.off);
   cplx* R = lv.R[lev];
+  const cplx* Fb = lv.F[lev - 1];
   for (int c = blockIdx.y; c <= P; c += gridDim.y) {
-    const int Lc = c < P ? PD_L : Llast;
-    const int q0 = c * (PD_L + 1);
+    const int Lc = c < P ? PD_LG : Llast;
+    const int q0 = c * (PD_LG + 1);
     cplx dP = cmake(0, 0), dM = cmake(0, 0), fP = cmake(0, 0), fM = cmake(0, 0);
     cplx pi = cmake(1, 0), m = cmake(0, 0);
+#pragma unroll 4
     for (int i = 0; i < Lc; ++i) {
-      const int q = q0 + i;
-      cplx rP, rM;
-      assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
-      R[((int64_t)q * 2) * K + kk] = rP;
-      R[((int64_t)q * 2 + 1) * K + kk] = rM;
+      const int64_t q = q0 + i;
+      const cplx rP = cfms(below.off, Fb[((q + 1) * 2) * K + kk], R[(q * 2) * K + kk]);
+      const cplx rM = cfms(below.off, Fb[((q + 1) * 2 + 1) * K + kk], R[(q * 2 + 1) * K + kk]);
+      R[(q * 2) * K + kk] = rP;
+      R[(q * 2 + 1) * K + kk] = rM;
       const cplx dq = (q == s.n - 1) ? s.dlast : s.dmain;
       if (i > 0) pi = cneg(cmul(pi, cmul(s.off, m)));
       m = crcp(cfms(o2, m, dq));
@@ -257,22 +252,19 @@ pd_solve_level_reduce_kernel(const cplx* __restrict__ w, Levels lv, SolveParams 
       fP = cfma(pi, dP, fP);
       fM = cfma(pi, dM, fM);
     }
-    if (c < P) {  // trailing separator row: only assembled and stored
-      const int q = q0 + PD_L;
-      cplx rP, rM;
-      assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
-      R[((int64_t)q * 2) * K + kk] = rP;
-      R[((int64_t)q * 2 + 1) * K + kk] = rM;
+    lv.F[lev][((int64_t)c * 2) * K + kk] = fP;
+    lv.F[lev][((int64_t)c * 2 + 1) * K + kk] = fM;
+    if (c < P) {
+      const int64_t q = q0 + PD_LG;
+      const cplx rP = cfms(below.off, Fb[((q + 1) * 2) * K + kk], R[(q * 2) * K + kk]);
+      const cplx rM = cfms(below.off, Fb[((q + 1) * 2 + 1) * K + kk], R[(q * 2 + 1) * K + kk]);
+      lv.R[lev + 1][((int64_t)c * 2) * K + kk] = cfms(s.off, dP, rP);
+      lv.R[lev + 1][((int64_t)c * 2 + 1) * K + kk] = cfms(s.off, dM, rM);
     }
-    cplx* r = lv.FL[lev] + ((int64_t)c * 4) * K + kk;
-    r[0] = fP;
-    r[K] = dP;
-    r[2 * K] = fM;
-    r[3 * K] = dM;
   }
 }
 
-// ------------------------------------------- generic level: back substitution (lev >= 1)
+// ------------------------------------------- generic level: back substitution (1 <= lev < top)
 // thread = (k, chunk c).  Separator solutions live in R[lev+1]; the chunk rows (and a copy of the
 // trailing separator) are overwritten by the solution in R[lev].
 __global__ void __launch_bounds__(PD_KB)
@@ -282,14 +274,14 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
   const KCoef kc = make_coef(sp.kbegin + kk, sp);
   const Sys s = level_sys(kc, sp, lev);
   const int64_t K = sp.K;
-  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_L + 1);
+  const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_LG + 1);
   const cplx o2 = cmul(s.off, s.off);
   cplx* R = lv.R[lev];
   const cplx* Z = lv.R[lev + 1];
   const cplx zero = cmake(0, 0);
   for (int c = blockIdx.y; c <= P; c += gridDim.y) {
-    const int Lc = c < P ? PD_L : Llast;
-    const int q0 = c * (PD_L + 1);
+    const int Lc = c < P ? PD_LG : Llast;
+    const int q0 = c * (PD_LG + 1);
     cplx zlP = zero, zlM = zero, zrP = zero, zrM = zero;
     if (c > 0) {
       zlP = Z[((int64_t)(c - 1) * 2) * K + kk];
@@ -298,16 +290,17 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
     if (c < P) {
       zrP = Z[((int64_t)c * 2) * K + kk];
       zrM = Z[((int64_t)c * 2 + 1) * K + kk];
-      R[((int64_t)(q0 + PD_L) * 2) * K + kk] = zrP;
-      R[((int64_t)(q0 + PD_L) * 2 + 1) * K + kk] = zrM;
+      R[((int64_t)(q0 + PD_LG) * 2) * K + kk] = zrP;
+      R[((int64_t)(q0 + PD_LG) * 2 + 1) * K + kk] = zrM;
     }
-    cplx dP[PD_L], dM[PD_L], mm[PD_L];
+    // forward: d_i overwrites the rhs in R (tiny, L2-resident data); pivots kept for the way back
+    cplx mm[PD_LG];
     cplx pP = zlP, pM = zlM, m = zero;
 #pragma unroll
-    for (int i = 0; i < PD_L; ++i) {
+    for (int i = 0; i < PD_LG; ++i) {
       if (i < Lc) {
-        const int q = q0 + i;
-        cplx rP = R[((int64_t)q * 2) * K + kk], rM = R[((int64_t)q * 2 + 1) * K + kk];
+        const int64_t q = q0 + i;
+        cplx rP = R[(q * 2) * K + kk], rM = R[(q * 2 + 1) * K + kk];
         if (i == Lc - 1) {
           rP = cfms(s.off, zrP, rP);
           rM = cfms(s.off, zrM, rM);
@@ -317,24 +310,20 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
         mm[i] = m;
         pP = cmul(cfms(s.off, pP, rP), m);
         pM = cmul(cfms(s.off, pM, rM), m);
-        dP[i] = pP;
-        dM[i] = pM;
+        R[(q * 2) * K + kk] = pP;
+        R[(q * 2 + 1) * K + kk] = pM;
       }
     }
-    cplx nP = zero, nM = zero;
+    cplx nP = pP, nM = pM;  // z of the last row = its d
 #pragma unroll
-    for (int i = PD_L - 1; i >= 0; --i) {
-      if (i < Lc) {
-        if (i < Lc - 1) {
-          const cplx cp = cmul(s.off, mm[i]);
-          nP = cfms(cp, nP, dP[i]);
-          nM = cfms(cp, nM, dM[i]);
-        } else {
-          nP = dP[i];
-          nM = dM[i];
-        }
-        R[((int64_t)(q0 + i) * 2) * K + kk] = nP;
-        R[((int64_t)(q0 + i) * 2 + 1) * K + kk] = nM;
+    for (int i = PD_LG - 2; i >= 0; --i) {
+      if (i < Lc - 1) {
+        const int64_t q = q0 + i;
+        const cplx cp = cmul(s.off, mm[i]);
+        nP = cfms(cp, nP, R[(q * 2) * K + kk]);
+        nM = cfms(cp, nM, R[(q * 2 + 1) * K + kk]);
+        R[(q * 2) * K + kk] = nP;
+        R[(q * 2 + 1) * K + kk] = nM;
       }
     }
   }
@@ -345,8 +334,9 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
 // each, two right-hand sides) by parallel cyclic reduction.  Rows are kept normalised (unit
 // diagonal): (lo, 1, up | rP, rM).  smem slot = ks * n + q.
 __global__ void __launch_bounds__(PD_PCR_THREADS)
-pd_solve_pcr_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int lev, int kpb) {
+pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  __shared__ cplx c_off[32], c_dmain[32], c_dlast[32], c_offb[32];
   const int n = sp.rows[lev];
   const int rows = n * kpb;
   cplx* s_lo = reinterpret_cast<cplx*>(pd_smem_raw);
@@ -357,20 +347,31 @@ pd_solve_pcr_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int l
   const int kk0 = blockIdx.x * kpb;
   const int64_t K = sp.K;
 
+  // coefficients of this CTA's frequencies, regenerated once
+  if (tid < kpb) {
+    int kk = kk0 + tid;
+    if (kk >= sp.K) kk = sp.K - 1;
+    const KCoef kc = make_coef(sp.kbegin + kk, sp);
+    const Sys below = level_sys(kc, sp, lev - 1);
+    const Sys s = reduce_sys(below, chunk_len(lev - 1));
+    c_off[tid] = s.off; c_dmain[tid] = s.dmain; c_dlast[tid] = s.dlast; c_offb[tid] = below.off;
+  }
+  __syncthreads();
+
   // build: idx -> (q = idx / kpb, ks = idx % kpb) so that consecutive threads read consecutive k
+  const cplx* R = lv.R[lev];
+  const cplx* Fb = lv.F[lev - 1];
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
     const int q = idx / kpb, ks = idx - q * kpb;
     int kk = kk0 + ks;
     if (kk >= sp.K) kk = sp.K - 1;
-    const KCoef kc = make_coef(sp.kbegin + kk, sp);
-    const Sys below = level_sys(kc, sp, lev - 1);
-    const Sys s = reduce_sys(below);
-    cplx rP, rM;
-    assemble_row(w, lv, sp, kc, below.off, lev, q, kk, rP, rM);
-    const cplx dinv = crcp(q == n - 1 ? s.dlast : s.dmain);
+    const cplx rP = cfms(c_offb[ks], Fb[((int64_t)(q + 1) * 2) * K + kk], R[((int64_t)q * 2) * K + kk]);
+    const cplx rM = cfms(c_offb[ks], Fb[((int64_t)(q + 1) * 2 + 1) * K + kk], R[((int64_t)q * 2 + 1) * K + kk]);
+    const cplx dinv = crcp(q == n - 1 ? c_dlast[ks] : c_dmain[ks]);
+    const cplx od = cmul(c_off[ks], dinv);
     const int slot = ks * n + q;
-    s_lo[slot] = q > 0 ? cmul(s.off, dinv) : cmake(0, 0);
-    s_up[slot] = q + 1 < n ? cmul(s.off, dinv) : cmake(0, 0);
+    s_lo[slot] = q > 0 ? od : cmake(0, 0);
+    s_up[slot] = q + 1 < n ? od : cmake(0, 0);
     s_rp[slot] = cmul(rP, dinv);
     s_rm[slot] = cmul(rM, dinv);
   }
@@ -424,14 +425,14 @@ pd_solve_pcr_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, int l
     __syncthreads();
   }
 
-  cplx* R = lv.R[lev];
+  cplx* Rw = lv.R[lev];
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
     const int q = idx / kpb, ks = idx - q * kpb;
     const int kk = kk0 + ks;
     if (kk >= sp.K) continue;
     const int slot = ks * n + q;
-    R[((int64_t)q * 2) * K + kk] = s_rp[slot];
-    R[((int64_t)q * 2 + 1) * K + kk] = s_rm[slot];
+    Rw[((int64_t)q * 2) * K + kk] = s_rp[slot];
+    Rw[((int64_t)q * 2 + 1) * K + kk] = s_rm[slot];
   }
 }
 
@@ -531,37 +532,37 @@ struct SolvePlan {
   int nlev;
   int rows[PD_MAX_LEVELS];
   cplx* R[PD_MAX_LEVELS];
-  cplx* FL[PD_MAX_LEVELS];
+  cplx* F[PD_MAX_LEVELS];
 };
 
-static SolvePlan* plan_of(pd_handle* h) { return reinterpret_cast<SolvePlan*>(h->red); }
+static SolvePlan* plan_of(pd_handle* h) { return reinterpret_cast<SolvePlan*>(h->solve_plan); }
 
 void pd_solve_free(pd_handle* h) {
   SolvePlan* pl = plan_of(h);
   if (!pl) return;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) {
     if (pl->R[l]) cudaFree(pl->R[l]);
-    if (pl->FL[l]) cudaFree(pl->FL[l]);
+    if (pl->F[l]) cudaFree(pl->F[l]);
   }
   delete pl;
-  h->red = nullptr;
+  h->solve_plan = nullptr;
 }
 
 int pd_solve_plan(pd_handle* h) {
   SolvePlan* pl = new SolvePlan();
   memset(pl, 0, sizeof(*pl));
-  h->red = reinterpret_cast<cplx*>(pl);
+  h->solve_plan = pl;
   h->L = PD_L;
   const size_t K = (size_t)h->kcount;
   // rows[0] = m; reduce while the interface is too large for the PCR kernel
   pl->rows[0] = h->m;
   int l = 0;
   while (true) {
-    const int next = pl->rows[l] / (PD_L + 1);
     if (l + 1 >= PD_MAX_LEVELS) {
       pd_set_error("N_x = %d needs more than %d partition levels", h->cfg.N_x, PD_MAX_LEVELS);
       return PD_ERR_INVALID;
     }
+    const int next = pl->rows[l] / (chunk_len(l) + 1);
     pl->rows[l + 1] = next;
     ++l;
     if (next <= PD_PCR_MAX) break;
@@ -577,8 +578,8 @@ int pd_solve_plan(pd_handle* h) {
       h->ws_bytes += bytes;
     }
     if (lev < pl->nlev) {
-      size_t bytes = sizeof(cplx) * (size_t)(pl->rows[lev + 1] + 1) * 4 * K;
-      PD_CUDA(cudaMalloc(&pl->FL[lev], bytes));
+      size_t bytes = sizeof(cplx) * (size_t)(pl->rows[lev + 1] + 1) * 2 * K;
+      PD_CUDA(cudaMalloc(&pl->F[lev], bytes));
       h->ws_bytes += bytes;
     }
   }
@@ -605,16 +606,16 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev) {
   sp.nlev = pl->nlev;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   Levels lv;
-  for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.FL[l] = pl->FL[l]; }
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   const int top = pl->nlev;
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   if (top >= 1) {
-    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.FL[0], sp);
+    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
     for (int lev = 1; lev < top; ++lev) {
-      pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(w, lv, sp, lev);
+      pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
       PD_CHECK_LAUNCH();
       h->launches++;
     }
@@ -628,7 +629,7 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev) {
       const size_t smem = (size_t)n * kpb * 64;
       const int nblk = (sp.K + kpb - 1) / kpb;
       PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(w, lv, sp, top, kpb);
+      pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
       PD_CHECK_LAUNCH();
       h->launches++;
     }
