@@ -31,7 +31,7 @@
 //            (Toeplitz except its last diagonal entry -- a structure the reduction
 //            preserves, so its coefficients too are regenerated, never stored).
 //            While it has more than PD_PCR_MAX rows it is reduced again the same way
-//            with chunks of PD_LG = 32 rows (generic kernels, ~3 % of the data).
+//            with chunks of PD_LG = 16 rows (generic kernels, ~6 % of the data).
 //   top      the last interface system (<= 128 rows per k) is solved by parallel
 //            cyclic reduction held in shared memory, up to 32 frequencies per CTA.
 //   back     the generic levels are back-substituted, then pass B (1 read + 1 write
@@ -44,7 +44,7 @@
 #include "pd_common.cuh"
 
 #define PD_L 16            // level-0 chunk length (rows held in registers)
-#define PD_LG 32           // chunk length of the generic interface levels
+#define PD_LG 16           // chunk length of the generic interface levels
 #define PD_KB 128          // frequencies per CTA in the streaming passes
 #define PD_PCR_MAX 128     // largest interface system handed to the PCR kernel
 #define PD_PCR_THREADS 256
@@ -269,6 +269,7 @@ pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
 // trailing separator) are overwritten by the solution in R[lev].
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
+  __shared__ cplx mtab[PD_LG][PD_KB];  // per-thread column of chunk pivots
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const KCoef kc = make_coef(sp.kbegin + kk, sp);
@@ -293,37 +294,47 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
       R[((int64_t)(q0 + PD_LG) * 2) * K + kk] = zrP;
       R[((int64_t)(q0 + PD_LG) * 2 + 1) * K + kk] = zrM;
     }
-    // forward: d_i overwrites the rhs in R (tiny, L2-resident data); pivots kept for the way back
-    cplx mm[PD_LG];
+    // all rows of the chunk are loaded up front (independent 128-bit loads), then Thomas in registers
+    cplx dP[PD_LG], dM[PD_LG];
+#pragma unroll
+    for (int i = 0; i < PD_LG; ++i) {
+      if (i < Lc) {
+        dP[i] = R[((int64_t)(q0 + i) * 2) * K + kk];
+        dM[i] = R[((int64_t)(q0 + i) * 2 + 1) * K + kk];
+      }
+    }
     cplx pP = zlP, pM = zlM, m = zero;
 #pragma unroll
     for (int i = 0; i < PD_LG; ++i) {
       if (i < Lc) {
-        const int64_t q = q0 + i;
-        cplx rP = R[(q * 2) * K + kk], rM = R[(q * 2 + 1) * K + kk];
+        cplx rP = dP[i], rM = dM[i];
         if (i == Lc - 1) {
           rP = cfms(s.off, zrP, rP);
           rM = cfms(s.off, zrM, rM);
         }
-        const cplx dq = (q == s.n - 1) ? s.dlast : s.dmain;
+        const cplx dq = (q0 + i == s.n - 1) ? s.dlast : s.dmain;
         m = crcp(cfms(o2, m, dq));
-        mm[i] = m;
+        mtab[i][threadIdx.x] = m;
         pP = cmul(cfms(s.off, pP, rP), m);
         pM = cmul(cfms(s.off, pM, rM), m);
-        R[(q * 2) * K + kk] = pP;
-        R[(q * 2 + 1) * K + kk] = pM;
+        dP[i] = pP;
+        dM[i] = pM;
       }
     }
-    cplx nP = pP, nM = pM;  // z of the last row = its d
+    cplx nP = zero, nM = zero;
 #pragma unroll
-    for (int i = PD_LG - 2; i >= 0; --i) {
-      if (i < Lc - 1) {
-        const int64_t q = q0 + i;
-        const cplx cp = cmul(s.off, mm[i]);
-        nP = cfms(cp, nP, R[(q * 2) * K + kk]);
-        nM = cfms(cp, nM, R[(q * 2 + 1) * K + kk]);
-        R[(q * 2) * K + kk] = nP;
-        R[(q * 2 + 1) * K + kk] = nM;
+    for (int i = PD_LG - 1; i >= 0; --i) {
+      if (i < Lc) {
+        if (i < Lc - 1) {
+          const cplx cp = cmul(s.off, mtab[i][threadIdx.x]);
+          nP = cfms(cp, nP, dP[i]);
+          nM = cfms(cp, nM, dM[i]);
+        } else {
+          nP = dP[i];
+          nM = dM[i];
+        }
+        R[((int64_t)(q0 + i) * 2) * K + kk] = nP;
+        R[((int64_t)(q0 + i) * 2 + 1) * K + kk] = nM;
       }
     }
   }

@@ -1,0 +1,158 @@
+"""Multi-GPU apply of the ParaDiag preconditioner: one process per GPU (torch.distributed).
+
+The reference has no parallel decomposition at all (its "parallel-in-time" is algebraic:
+all frequencies go into one monolithic MUMPS factorisation, Control_Wave_PC.py:481-484).
+The path shards naturally with ONE exchange step each way:
+
+    stage 1  time-axis inverse FFT        sharded by NODE slab   (rank r: nodes [j0_r, j1_r), all N_t)
+    ---- all-to-all: (2, n_r, N_t) -> (2, n, k_r) ----
+    stage 2  per-frequency solves          sharded by FREQUENCY   (rank r: k in [k0_r, k1_r), all nodes)
+    ---- all-to-all: (2, n, k_r) -> (2, n_r, N_t) ----
+    stage 3  time-axis forward FFT         sharded by node slab
+
+Vectors are distributed by node slab -- the layout a PETSc/Firedrake spatial decomposition of
+the reference would give: rank r holds x[:, j0_r:j1_r, :] as a contiguous (2, n_r, N_t) block.
+
+The compute backend is a ``ParaDiagHandle`` created with this rank's frequency slab
+(``pd_stage_fft`` / ``pd_stage_solve`` of include/paradiag.h).  The transposes use
+``all_to_all_single`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) with uneven splits,
+so neither n = N_x + 1 nor N_t has to be divisible by the world size.
+"""
+import numpy as np
+
+
+def slab_bounds(total, parts):
+    """Balanced contiguous split: the first ``total % parts`` slabs get one extra item."""
+    base, extra = divmod(total, parts)
+    counts = [base + (1 if r < extra else 0) for r in range(parts)]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    return counts, offs
+
+
+class DistributedDiagFFTPC:
+    def __init__(self, N_x, N_t, T=2.0, gamma=1.0, device=0, group=None, backend_factory=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.N_x, self.N_t, self.n = int(N_x), int(N_t), int(N_x) + 1
+        self.ncount, self.noff = slab_bounds(self.n, self.world)
+        self.kcount, self.koff = slab_bounds(self.N_t, self.world)
+        if min(self.kcount) < 1 or min(self.ncount) < 1:
+            raise ValueError(f"world size {self.world} exceeds N_t = {N_t} or the node count {self.n}")
+        self.n_r, self.k_r = self.ncount[self.rank], self.kcount[self.rank]
+        if backend_factory is None:
+            from .handle import ParaDiagHandle
+
+            def backend_factory(**kw):
+                return ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, device=device, **kw)
+            self.device = torch.device(f"cuda:{device}")
+        else:
+            self.device = torch.device("cpu")
+        self.backend = backend_factory(k_begin=self.koff[self.rank], k_count=self.k_r, n_local=self.n_r)
+        c128 = torch.complex128
+        self.local_size = 2 * self.n_r * self.N_t
+        self.freq_size = 2 * self.n * self.k_r
+        # work buffers: time-domain slab, frequency-domain slab, send / receive staging
+        self.w_time = torch.empty(self.local_size, dtype=c128, device=self.device)
+        self.w_freq = torch.empty(self.freq_size, dtype=c128, device=self.device)
+        self.sendbuf = torch.empty(max(self.local_size, self.freq_size), dtype=c128, device=self.device)
+        self.recvbuf = torch.empty(max(self.local_size, self.freq_size), dtype=c128, device=self.device)
+        # split sizes in complex elements
+        self.a_send = [2 * self.n_r * k for k in self.kcount]      # to rank s: (2, n_r, k_s)
+        self.a_recv = [2 * ns * self.k_r for ns in self.ncount]    # from rank s: (2, n_s, k_r)
+        self.comm_bytes_per_apply = 16 * 2 * (sum(self.a_send) - self.a_send[self.rank])
+
+    # -------------------------------------------------------------------------------
+    @property
+    def launch_count(self):
+        return getattr(self.backend, "launch_count", 0)
+
+    def describe(self):
+        return {"world": self.world, "node_slabs": self.ncount, "freq_slabs": self.kcount,
+                "alltoall_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply,
+                "collective": "all_to_all_single x2 (uneven splits), pack/unpack by strided copies"}
+
+    def random_local(self, seed=0):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(self.local_size) + 1j * rng.standard_normal(self.local_size)
+        return self.torch.tensor(x, device=self.device)
+
+    def scatter_from_global(self, x_global):
+        """This rank's (2, n_r, N_t) block of a replicated global vector (tests / set-up only)."""
+        xg = x_global.reshape(2, self.n, self.N_t)
+        j0, j1 = self.noff[self.rank], self.noff[self.rank + 1]
+        return xg[:, j0:j1, :].reshape(-1).contiguous().to(self.device)
+
+    def _a2a(self, out, inp, out_split, in_split):
+        # complex128 travels as pairs of float64 (NCCL has no complex type)
+        t = self.torch
+        self.dist.all_to_all_single(t.view_as_real(out).reshape(-1), t.view_as_real(inp).reshape(-1),
+                                    [2 * s for s in out_split], [2 * s for s in in_split], group=self.group)
+
+    # -------------------------------------------------------------------------------
+    def apply(self, x_local, y_local=None):
+        """y = P^-1 x for node-slab distributed vectors (DiagFFTPC.apply, Control_Wave_PC.py:491-553)."""
+        t = self.torch
+        if y_local is None:
+            y_local = t.empty_like(x_local)
+        n_r, k_r, n, N_t, G = self.n_r, self.k_r, self.n, self.N_t, self.world
+        # stage 1: inverse FFT along time of this rank's 2 n_r lines (:500-501)
+        self.backend.stage_fft(x_local.reshape(-1), self.w_time, 2 * n_r, True)
+        wt = self.w_time.view(2, n_r, N_t)
+        # pack: block for rank s = (2, n_r, k_s)
+        off = 0
+        for s in range(G):
+            k0, k1 = self.koff[s], self.koff[s + 1]
+            self.sendbuf[off:off + self.a_send[s]].view(2, n_r, k1 - k0).copy_(wt[:, :, k0:k1])
+            off += self.a_send[s]
+        self._a2a(self.recvbuf[:self.freq_size], self.sendbuf[:self.local_size], self.a_recv, self.a_send)
+        # unpack: block from rank s = (2, n_s, k_r) -> rows [j0_s, j1_s) of (2, n, k_r)
+        wf = self.w_freq.view(2, n, k_r)
+        off = 0
+        for s in range(G):
+            j0, j1 = self.noff[s], self.noff[s + 1]
+            wf[:, j0:j1, :].copy_(self.recvbuf[off:off + self.a_recv[s]].view(2, j1 - j0, k_r))
+            off += self.a_recv[s]
+        # stage 2: this rank's frequencies, all nodes (:445-540)
+        self.backend.stage_solve(self.w_freq)
+        # pack back: block for rank s = (2, n_s, k_r)
+        off = 0
+        for s in range(G):
+            j0, j1 = self.noff[s], self.noff[s + 1]
+            self.sendbuf[off:off + self.a_recv[s]].view(2, j1 - j0, k_r).copy_(wf[:, j0:j1, :])
+            off += self.a_recv[s]
+        self._a2a(self.recvbuf[:self.local_size], self.sendbuf[:self.freq_size], self.a_send, self.a_recv)
+        off = 0
+        for s in range(G):
+            k0, k1 = self.koff[s], self.koff[s + 1]
+            wt[:, :, k0:k1].copy_(self.recvbuf[off:off + self.a_send[s]].view(2, n_r, k1 - k0))
+            off += self.a_send[s]
+        # stage 3: forward FFT along time (:547-548)
+        self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * n_r, False)
+        return y_local
+
+    def gather_to_global(self, y_local):
+        """All ranks receive the full (2, n, N_t) vector (tests only)."""
+        t = self.torch
+        parts = [t.empty(2 * c * self.N_t, dtype=t.complex128, device=self.device) for c in self.ncount]
+        reals = [t.view_as_real(p) for p in parts]
+        self.dist.all_gather(reals, t.view_as_real(y_local.reshape(-1).contiguous()), group=self.group) \
+            if len(set(self.ncount)) == 1 else self._uneven_gather(reals, y_local)
+        full = t.empty(2, self.n, self.N_t, dtype=t.complex128, device=self.device)
+        for s, p in enumerate(parts):
+            full[:, self.noff[s]:self.noff[s + 1], :] = p.view(2, self.ncount[s], self.N_t)
+        return full.reshape(-1)
+
+    def _uneven_gather(self, reals, y_local):
+        t = self.torch
+        mine = t.view_as_real(y_local.reshape(-1).contiguous())
+        for s in range(self.world):
+            if s == self.rank:
+                reals[s].copy_(mine)
+            self.dist.broadcast(reals[s], src=self.dist.get_global_rank(self.group, s) if self.group else s,
+                                group=self.group)
