@@ -52,25 +52,46 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   const double d_i = (i == 0 && !op.circulant) ? 0.5 : 1.0;               // :117
   const double e_i = (i == op.N_t - 1 && !op.circulant) ? 0.5 : 1.0;      // :143
   const double q_i = (i == op.N_t - 1 && !op.circulant) ? op.qlast : 1.0; // :138
-  cplx yu = cmake(0, 0), yp = cmake(0, 0);
+  // Rounding matters here: the Krylov vectors of this problem are smooth, so both the second
+  // difference in time and the stiffness stencil in space cancel to O(dt^2), O(h^2) of their operands,
+  // and the ill-conditioned preconditioner amplifies whatever noise the matvec leaves (measured: extra
+  // GMRES iterations at N_x >= 4096).  Every cancelling combination is therefore formed from
+  // differences of neighbouring values -- exact in floating point (Sterbenz) -- before any scaling:
+  //   time:   D2 v = (v_i - v_{i-1}) - (v_{i-1} - v_{i-2})        per node, then M in space
+  //   space:  K v  = ((v_C - v_L) + (v_C - v_R)) / h               per time level, then summed
+  (void)k_dia;
+  cplx uv[3][3], pv[3][3];  // [node L,C,R][time level 0,1,2]: u at i-t, p at i+t
 #pragma unroll
-  for (int dj = -1; dj <= 1; ++dj) {
-    const double mw = dj == 0 ? m_dia : m_off;
-    const double kw = dj == 0 ? k_dia : k_off;
-    const int jj = j + dj;
-    const cplx u0 = ld_or_zero(u, jj, i, op), u1 = ld_or_zero(u, jj, i - 1, op),
-               u2 = ld_or_zero(u, jj, i - 2, op);
-    const cplx p0 = ld_or_zero(p, jj, i, op), p1 = ld_or_zero(p, jj, i + 1, op),
-               p2 = ld_or_zero(p, jj, i + 2, op);
-    // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
-    const double cu_m = mw, cu_k = q_i * op.dt2h * kw;
-    yu.x += cu_m * (u0.x - 2.0 * u1.x + u2.x) + cu_k * (u0.x + u2.x) - d_i * op.c * mw * p0.x;
-    yu.y += cu_m * (u0.y - 2.0 * u1.y + u2.y) + cu_k * (u0.y + u2.y) - d_i * op.c * mw * p0.y;
-    // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
-    const double cp_k = op.dt2h * kw;
-    yp.x += e_i * op.c * mw * u0.x + mw * (p0.x - 2.0 * p1.x + p2.x) + cp_k * (p0.x + p2.x);
-    yp.y += e_i * op.c * mw * u0.y + mw * (p0.y - 2.0 * p1.y + p2.y) + cp_k * (p0.y + p2.y);
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      uv[s][t] = ld_or_zero(u, j - 1 + s, i - t, op);
+      pv[s][t] = ld_or_zero(p, j - 1 + s, i + t, op);
+    }
+  cplx d2u[3], d2p[3], Ku0, Ku2, Kp0, Kp2;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    d2u[s] = csub(csub(uv[s][0], uv[s][1]), csub(uv[s][1], uv[s][2]));
+    d2p[s] = csub(csub(pv[s][0], pv[s][1]), csub(pv[s][1], pv[s][2]));
   }
+  const double ih = -k_off;  // 1/h
+  Ku0 = cscale(cadd(csub(uv[1][0], uv[0][0]), csub(uv[1][0], uv[2][0])), ih);
+  Ku2 = cscale(cadd(csub(uv[1][2], uv[0][2]), csub(uv[1][2], uv[2][2])), ih);
+  Kp0 = cscale(cadd(csub(pv[1][0], pv[0][0]), csub(pv[1][0], pv[2][0])), ih);
+  Kp2 = cscale(cadd(csub(pv[1][2], pv[0][2]), csub(pv[1][2], pv[2][2])), ih);
+  const cplx Md2u = cmake(m_off * (d2u[0].x + d2u[2].x) + m_dia * d2u[1].x, m_off * (d2u[0].y + d2u[2].y) + m_dia * d2u[1].y);
+  const cplx Md2p = cmake(m_off * (d2p[0].x + d2p[2].x) + m_dia * d2p[1].x, m_off * (d2p[0].y + d2p[2].y) + m_dia * d2p[1].y);
+  const cplx Mu0 = cmake(m_off * (uv[0][0].x + uv[2][0].x) + m_dia * uv[1][0].x, m_off * (uv[0][0].y + uv[2][0].y) + m_dia * uv[1][0].y);
+  const cplx Mp0 = cmake(m_off * (pv[0][0].x + pv[2][0].x) + m_dia * pv[1][0].x, m_off * (pv[0][0].y + pv[2][0].y) + m_dia * pv[1][0].y);
+  // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
+  cplx yu, yp;
+  const double ck = q_i * op.dt2h, cm = d_i * op.c;
+  yu.x = Md2u.x + ck * (Ku0.x + Ku2.x) - cm * Mp0.x;
+  yu.y = Md2u.y + ck * (Ku0.y + Ku2.y) - cm * Mp0.y;
+  // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
+  const double ce = e_i * op.c;
+  yp.x = Md2p.x + op.dt2h * (Kp0.x + Kp2.x) + ce * Mu0.x;
+  yp.y = Md2p.y + op.dt2h * (Kp0.y + Kp2.y) + ce * Mu0.y;
   y[o] = yu;
   y[op.plane + o] = yp;
 }
