@@ -157,7 +157,7 @@ def run_ours(args):
 
     if world > 1:
         from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
-        dpc = DistributedDiagFFTPC(N_x, N_t, device=local)
+        dpc = DistributedDiagFFTPC(N_x, N_t, device=local, mode=args.dist_mode)
         x = dpc.random_local(seed=rank)
         y = torch.empty_like(x)
         apply_fn = lambda: dpc.apply(x, y)
@@ -224,7 +224,10 @@ def run_ours(args):
             "workload": f"{args.workload}: 1D wave control N_x={N_x}, N_t={N_t}, T=2, gamma=1, alpha=1",
             "vector_bytes": S, "algorithmic_bytes_per_apply": B_pc,
             "l2": "inputs larger than L2" if flush is None else "L2 flushed between timed iterations",
-            "parallelism": "1 GPU" if world == 1 else f"space slabs <-> frequency slabs over {world} GPUs (all-to-all)",
+            "parallelism": "1 GPU" if world == 1 else (
+                f"x-slabs over {world} GPUs, distributed partition solve (one small all-gather)"
+                if args.dist_mode == "slab" else
+                f"space slabs <-> frequency slabs over {world} GPUs (all-to-all)"),
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -319,6 +322,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--dist-mode", default="slab", choices=["slab", "alltoall"],
+                    help="multi-GPU decomposition of the solve stage (see dist.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES time-to-solution leg")
     args = ap.parse_args()

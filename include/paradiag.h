@@ -65,7 +65,12 @@ typedef struct pd_config {
   /* Node slab transformed by this handle in pd_stage_fft (multi-GPU):
    * n_local lines per field.  0 means all n = N_x + 1 nodes.                    */
   int32_t n_local;
-  int32_t reserved[5];
+  /* Slab mode (multi-GPU without transposes): this handle owns x-slab `slab_rank` of `slab_count`
+   * (balanced contiguous split of the n nodes, the first n % slab_count slabs one node longer) for ALL
+   * frequencies; see pd_slab_reduce / pd_slab_finish.  slab_count <= 1: off.                        */
+  int32_t slab_rank;
+  int32_t slab_count;
+  int32_t reserved[3];
 } pd_config;
 
 typedef struct pd_handle pd_handle;
@@ -107,6 +112,18 @@ int pd_pc_apply_transpose(pd_handle* h, const void* x_dev, void* y_dev, void* st
 int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines,
                  int inverse, void* stream);
 int pd_stage_solve(pd_handle* h, void* w_dev, void* stream);
+
+/* Slab mode: the per-frequency solves with the x-direction distributed over `slab_count` ranks
+ * and NO transposes.  w = this rank's (2, n_r, N_t) block after pd_stage_fft(inverse).
+ *   pd_slab_reduce : local partial elimination; out_dev[6][N_t] receives, per frequency, the first
+ *                    and last entry of the slab-local solve (two right-hand sides each) and the
+ *                    right-hand side of the separator row this slab owns.
+ *   (caller all-gathers the 6*N_t values of every rank, slab order, into gathered_dev[G][6][N_t])
+ *   pd_slab_finish : every rank solves the (G-1)-row separator system of each frequency redundantly,
+ *                    then back-substitutes its slab in place (rotation, Dirichlet rows included).
+ * Together they replace pd_stage_solve (i.e. :445-540) for a distributed x-axis.                  */
+int pd_slab_reduce(pd_handle* h, void* w_dev, void* out_dev, void* stream);
+int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream);
 
 /* Matrix-free action of the Jacobian of Build_L (:86-179, pc=True branches):
  * y = A x with Dirichlet rows as identity.  x and y must not alias.             */

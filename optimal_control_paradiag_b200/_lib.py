@@ -28,7 +28,7 @@ class pd_config(C.Structure):
         ("abi_version", C.c_int32), ("N_x", C.c_int32), ("N_t", C.c_int32), ("bug138", C.c_int32),
         ("T", C.c_double), ("gamma", C.c_double), ("alpha", C.c_double),
         ("device", C.c_int32), ("k_begin", C.c_int32), ("k_count", C.c_int32), ("n_local", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("slab_rank", C.c_int32), ("slab_count", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -47,6 +47,8 @@ SYMBOLS = {
     "pd_pc_apply_transpose": (_I, [_VP, _VP, _VP, _VP]),
     "pd_stage_fft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "pd_stage_solve": (_I, [_VP, _VP, _VP]),
+    "pd_slab_reduce": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_slab_finish": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),

@@ -81,6 +81,23 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
   h->kbegin = cfg->k_count > 0 ? cfg->k_begin : 0;
   h->kcount = cfg->k_count > 0 ? cfg->k_count : cfg->N_t;
   h->nloc = cfg->n_local > 0 ? cfg->n_local : h->n;
+  h->slab_rank = cfg->slab_rank;
+  h->slab_count = cfg->slab_count > 1 ? cfg->slab_count : 1;
+  if (h->slab_count > 1) {
+    // this rank's node rows: row 0 is the Dirichlet node (rank 0) or the separator this slab owns;
+    // the body follows; the last rank ends with the Dirichlet node
+    if (cfg->slab_rank < 0 || cfg->slab_rank >= h->slab_count || cfg->k_count > 0) {
+      pd_set_error("pd_create: bad slab_rank %d of %d (or k_count set together with slab mode)", cfg->slab_rank,
+                   h->slab_count);
+      delete h;
+      return PD_ERR_INVALID;
+    }
+    const int ntot = cfg->N_x + 1, G = h->slab_count, r = h->slab_rank;
+    const int cnt = ntot / G + (r < ntot % G ? 1 : 0);
+    h->n = cnt;
+    h->m = cnt - 1 - (r == G - 1 ? 1 : 0);
+    h->nloc = cnt;
+  }
   if (h->kbegin < 0 || h->kbegin + h->kcount > cfg->N_t) {
     pd_set_error("pd_create: frequency shard [%d, %d) outside [0, %d)", h->kbegin, h->kbegin + h->kcount,
                  cfg->N_t);
@@ -135,13 +152,29 @@ extern "C" int pd_stage_solve(pd_handle* h, void* w_dev, void* stream) {
   return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream);
 }
 
+extern "C" int pd_slab_reduce(pd_handle* h, void* w_dev, void* out_dev, void* stream) {
+  if (!h || !w_dev || !out_dev || h->slab_count <= 1) {
+    pd_set_error("pd_slab_reduce: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  return pd_slab_reduce_launch(h, (cplx*)w_dev, (cplx*)out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream) {
+  if (!h || !w_dev || !gathered_dev || h->slab_count <= 1) {
+    pd_set_error("pd_slab_finish: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream);
+}
+
 extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
   if (!h || !x_dev || !y_dev) {
     pd_set_error("pd_pc_apply: invalid argument");
     return PD_ERR_INVALID;
   }
-  if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
-    pd_set_error("pd_pc_apply: handle is sharded (k_count/n_local set); use the stage API");
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
+    pd_set_error("pd_pc_apply: handle is sharded (k_count/n_local/slab set); use the stage API");
     return PD_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;

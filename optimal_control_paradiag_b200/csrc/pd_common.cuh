@@ -72,6 +72,7 @@ struct pd_handle {
   int kcount;    // frequencies solved by this handle
   int kbegin;
   int nloc;      // node lines per field transformed by this handle
+  int slab_rank, slab_count;  // slab mode (x-slab sharding through the solve); count <= 1: off
   double dt, h, c;
   int num_sms;
   size_t ws_bytes;
@@ -115,5 +116,7 @@ int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int i
                   cudaStream_t st);
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr);
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st);
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st);

@@ -57,6 +57,17 @@ struct SolveParams {
   int64_t plane;            // elements per field plane = n * K
   int nlev;                 // top interface level (0: single chunk, no interface)
   int rows[PD_MAX_LEVELS];  // rows[l] = size of the level-l system (rows[0] = m)
+  // geometry of the local node rows: row 0 precedes the body, rows 1..m are the body.
+  // Single-GPU: row 0 and row m+1 are the Dirichlet nodes.  Slab mode (x-slab r of G): row 0 is the
+  // inter-slab separator (r > 0) and the last body row is followed by the next slab's separator (r < G-1).
+  int first_dirichlet, last_dirichlet;
+};
+
+// Slab-mode extras (device pointers; all null in single-GPU mode)
+struct SlabPtrs {
+  cplx* lastl;        // [2][K]     last entry of the last chunk's local solve (pass A)
+  const cplx* green;  // [P][2][K]  interface Green's vectors T_1^-1 e_0 (slot 0), T_1^-1 e_{P-1} (slot 1)
+  const cplx* zout;   // [4][K]     outer separator values: left (+, -), right (+, -)
 };
 
 struct KCoef {
@@ -232,7 +243,7 @@ struct Levels {
 // ------------------------------------------------------------------- pass A
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
-                      SolveParams sp) {
+                      SolveParams sp, cplx* __restrict__ lastl) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = blockIdx.x * PD_KB + tid;
@@ -282,6 +293,9 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
         rotate_in(kc, ru[PD_L], rp_[PD_L], sP, sM);
         R1[((int64_t)c * 2) * K + kk] = cfms(kc.a, dP, sP);      // rho_sep - a l_c
         R1[((int64_t)c * 2 + 1) * K + kk] = cfms(kc.a, dM, sM);
+      } else if (lastl) {
+        lastl[kk] = dP;
+        lastl[K + kk] = dM;
       }
     }
   }
@@ -522,8 +536,9 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
 }
 
 // ------------------------------------------------------------------- pass B
+template <bool SLAB>
 __global__ void __launch_bounds__(PD_KB)
-pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp) {
+pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp, SlabPtrs sl) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = blockIdx.x * PD_KB + tid;
@@ -535,6 +550,29 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
   cplx* wp = w + sp.plane + kc_idx;
   const cplx zero = cmake(0, 0);
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
+  // slab mode: outer separator values and the coefficients with which they enter the first / last
+  // interface row: -off_1 z_left = -(a / V_L) z_left and -(a / V_Llast) z_right (-a z_right if Llast = 0)
+  cplx oLP = zero, oLM = zero, oRP = zero, oRM = zero, cLP = zero, cLM = zero, cRP = zero, cRM = zero;
+  if (SLAB) {
+    oLP = sl.zout[kc_idx]; oLM = sl.zout[sp.K + kc_idx];
+    oRP = sl.zout[2 * (int64_t)sp.K + kc_idx]; oRM = sl.zout[3 * (int64_t)sp.K + kc_idx];
+    if (P > 0) {
+      VRec v;
+      v.init(kc.a, kc.sh, zero);
+      cplx gl = zero, gr = kc.a;  // a / V_L and a / V_Llast (V_0 = 1)
+      if (!v.diag) {
+        for (int i = 1; i <= PD_L; ++i) {
+          v.step();
+          if (i == Llast) gr = cmul(kc.a, cscale(crcp(v.V), v.one));
+        }
+        gl = cmul(kc.a, cscale(crcp(v.V), v.one));
+      } else if (Llast > 0) {
+        gr = zero;
+      }
+      cLP = cneg(cmul(gl, oLP)); cLM = cneg(cmul(gl, oLM));
+      cRP = cneg(cmul(gr, oRP)); cRM = cneg(cmul(gr, oRM));
+    }
+  }
   for (int c = blockIdx.y; c <= P; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
@@ -546,14 +584,26 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
         dM[i] = wp[(int64_t)(j0 + i) * sp.K];
       }
     }
-    cplx zlP = zero, zlM = zero, zrP = zero, zrM = zero;
+    cplx zlP = oLP, zlM = oLM, zrP = oRP, zrM = oRM;  // zero in single-GPU mode
     if (c > 0) {
-      zlP = zsep[((int64_t)(c - 1) * 2) * sp.K + kc_idx];
-      zlM = zsep[((int64_t)(c - 1) * 2 + 1) * sp.K + kc_idx];
+      const int64_t o = ((int64_t)(c - 1) * 2) * sp.K + kc_idx;
+      zlP = zsep[o];
+      zlM = zsep[o + sp.K];
+      if (SLAB) {
+        const cplx g0 = sl.green[o], g1 = sl.green[o + sp.K];
+        zlP = cfma(cLP, g0, cfma(cRP, g1, zlP));
+        zlM = cfma(cLM, g0, cfma(cRM, g1, zlM));
+      }
     }
     if (c < P) {
-      zrP = zsep[((int64_t)c * 2) * sp.K + kc_idx];
-      zrM = zsep[((int64_t)c * 2 + 1) * sp.K + kc_idx];
+      const int64_t o = ((int64_t)c * 2) * sp.K + kc_idx;
+      zrP = zsep[o];
+      zrM = zsep[o + sp.K];
+      if (SLAB) {
+        const cplx g0 = sl.green[o], g1 = sl.green[o + sp.K];
+        zrP = cfma(cLP, g0, cfma(cRP, g1, zrP));
+        zrM = cfma(cLM, g0, cfma(cRM, g1, zrM));
+      }
     }
     // forward elimination (in place: d_i overwrites rho_i)
     cplx pP = zlP, pM = zlM;  // "d_{-1}" = known left neighbour value
@@ -600,16 +650,159 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       wu[(int64_t)(j0 + PD_L) * sp.K] = ou;
       wp[(int64_t)(j0 + PD_L) * sp.K] = op;
     }
-    // Dirichlet rows: output exactly 0 (:482, bcs :44-45)
+    // Dirichlet rows: output exactly 0 (:482, bcs :44-45); in slab mode row 0 may be the
+    // inter-slab separator this rank owns
     if (valid && c == 0) {
-      wu[0] = zero;
-      wp[0] = zero;
+      cplx ou = zero, op = zero;
+      if (SLAB && !sp.first_dirichlet) rotate_out(kc, oLP, oLM, ou, op);
+      wu[0] = ou;
+      wp[0] = op;
     }
-    if (valid && c == P) {
-      wu[(int64_t)(sp.n - 1) * sp.K] = zero;
-      wp[(int64_t)(sp.n - 1) * sp.K] = zero;
+    if (valid && c == P && sp.last_dirichlet) {
+      wu[(int64_t)(sp.m + 1) * sp.K] = zero;
+      wp[(int64_t)(sp.m + 1) * sp.K] = zero;
     }
   }
+}
+
+// ------------------------------------------------------------ slab-mode kernels
+// Slab mode = x-slab sharding kept through the solve (no transposes): rank r owns a contiguous node
+// slab for ALL frequencies; the first node of every slab r > 0 is a global separator.  Each slab body is
+// a pure Toeplitz block T_{m_r}; the G-1 separators of one frequency form a tiny tridiagonal system
+//   a rv_{r-1} z_{r-1} + a (eta - dvv_{r-1} - dvv_r) z_r + a rv_r z_{r+1} = rho_r - a (l_{r-1} + f_r)
+// with rv_s = 1/V_{m_s}, dvv_s = (V_{m_s} - V_{m_s - 1}) / V_{m_s} (cancellation-free, see Sys) and
+// f_s / l_s the first / last entry of the slab-local solve with zero neighbours.
+
+// out[6][K] = (f+, f-, l+, l-, rho_sep+, rho_sep-) of this slab
+__global__ void __launch_bounds__(PD_KB)
+pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
+                           cplx* __restrict__ out) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.K) return;
+  const int64_t K = sp.K;
+  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
+  cplx fP = lv.F[0] ? lv.F[0][kk] : cmake(0, 0), fM = lv.F[0] ? lv.F[0][K + kk] : cmake(0, 0);
+  cplx lP = cmake(0, 0), lM = cmake(0, 0);
+  if (Llast > 0) { lP = sl.lastl[kk]; lM = sl.lastl[K + kk]; }
+  if (P > 0) {
+    // first entry of chunk 0 and last entry of the last chunk, given the interface solution
+    VRec v;
+    v.init(kc.a, kc.sh, cmake(0, 0));
+    cplx rvL = cmake(0, 0), rvLl = cmake(0, 0);
+    if (!v.diag) {
+      for (int i = 1; i <= PD_L; ++i) {
+        v.step();
+        if (i == Llast) rvLl = cscale(crcp(v.V), v.one);
+      }
+      rvL = cscale(crcp(v.V), v.one);
+    }
+    const cplx z0P = lv.R[1][kk], z0M = lv.R[1][K + kk];
+    const cplx zeP = lv.R[1][((int64_t)(P - 1) * 2) * K + kk], zeM = lv.R[1][((int64_t)(P - 1) * 2 + 1) * K + kk];
+    fP = cfma(z0P, rvL, fP);  // f_0 - a z_sep0 (T_L^-1)_{1L} = f_0 + z_sep0 / V_L
+    fM = cfma(z0M, rvL, fM);
+    if (Llast > 0) {
+      lP = cfma(zeP, rvLl, lP);
+      lM = cfma(zeM, rvLl, lM);
+    } else {
+      lP = zeP;  // the last body row is the last separator itself
+      lM = zeM;
+    }
+  }
+  cplx sP = cmake(0, 0), sM = cmake(0, 0);
+  if (!sp.first_dirichlet) rotate_in(kc, w[kk], w[sp.plane + kk], sP, sM);
+  out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
+  out[4 * K + kk] = sP; out[5 * K + kk] = sM;
+}
+
+#define PD_MAX_SLABS 16
+struct SlabGeom {
+  int G, rank;
+  int body[PD_MAX_SLABS];  // m_s of every slab
+};
+
+// Per-slab Green's coefficients rv_s = 1/V_{m_s}, dvv_s = (V_{m_s} - V_{m_s-1})/V_{m_s}: a recurrence of
+// m_s steps per frequency, independent of the right-hand side -> computed once when the plan is built
+// (coef[G][2][K], a few hundred KB), not per apply.  One thread per (k, slab).
+__global__ void __launch_bounds__(PD_KB)
+pd_slab_coef_kernel(SolveParams sp, SlabGeom sg, cplx* __restrict__ coef) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  const int s = blockIdx.y;
+  if (kk >= sp.K) return;
+  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  VRec v;
+  v.init(kc.a, kc.sh, cmake(0, 0));
+  cplx rv = cmake(0, 0), dvv = cmake(1, 0);  // decoupled: V_{m-1}/V_m -> 0
+  if (!v.diag) {
+    for (int i = 1; i <= sg.body[s]; ++i) v.step();
+    const cplx r = crcp(v.V);
+    rv = cscale(r, v.one);
+    dvv = cmul(cmake(v.one + v.E.x, v.E.y), r);
+  }
+  coef[((int64_t)s * 2) * sp.K + kk] = rv;
+  coef[((int64_t)s * 2 + 1) * sp.K + kk] = dvv;
+}
+
+// gathered[G][6][K] -> zout[4][K] (left+, left-, right+, right-) of this rank
+__global__ void __launch_bounds__(PD_KB)
+pd_slab_global_kernel(const cplx* __restrict__ gathered, SolveParams sp, SlabGeom sg,
+                      const cplx* __restrict__ coef, cplx* __restrict__ zout) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.K) return;
+  const int64_t K = sp.K;
+  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const int G = sg.G;
+  cplx rv[PD_MAX_SLABS], dvv[PD_MAX_SLABS];
+  for (int s = 0; s < G; ++s) {
+    rv[s] = coef[((int64_t)s * 2) * K + kk];
+    dvv[s] = coef[((int64_t)s * 2 + 1) * K + kk];
+  }
+  // separators 1..G-1 -> rows 0..G-2; Thomas with two right-hand sides
+  const cplx roff = crcp(kc.a);
+  VRec t;
+  t.init(kc.a, kc.sh, cmake(0, 0));
+  const cplx eta = t.diag ? cmake(0, 0) : t.eta;
+  cplx cp[PD_MAX_SLABS], dP[PD_MAX_SLABS], dM[PD_MAX_SLABS];
+  cplx prevc = cmake(0, 0), pP = cmake(0, 0), pM = cmake(0, 0);
+  for (int r = 1; r < G; ++r) {
+    const cplx* gl = gathered + ((int64_t)(r - 1) * 6) * K + kk;  // slab left of separator r
+    const cplx* gr = gathered + ((int64_t)r * 6) * K + kk;        // slab right of it (owns the separator)
+    cplx di, lo, up;
+    if (t.diag) {
+      di = cmake(kc.sh.x - 2.0 * kc.a.x, kc.sh.y - 2.0 * kc.a.y);
+      lo = up = cmake(0, 0);
+    } else {
+      di = cmul(kc.a, csub(csub(eta, dvv[r - 1]), dvv[r]));
+      lo = r > 1 ? cmul(kc.a, rv[r - 1]) : cmake(0, 0);
+      up = r < G - 1 ? cmul(kc.a, rv[r]) : cmake(0, 0);
+    }
+    cplx rP = cfms(kc.a, cadd(gl[2 * K], gr[0]), gr[4 * K]);
+    cplx rM = cfms(kc.a, cadd(gl[3 * K], gr[K]), gr[5 * K]);
+    const cplx inv = crcp(cfms(lo, prevc, di));
+    prevc = cmul(up, inv);
+    pP = cmul(cfms(lo, pP, rP), inv);
+    pM = cmul(cfms(lo, pM, rM), inv);
+    cp[r] = prevc; dP[r] = pP; dM[r] = pM;
+  }
+  (void)roff;
+  cplx zP = cmake(0, 0), zM = cmake(0, 0);
+  cplx leftP = cmake(0, 0), leftM = cmake(0, 0), rightP = cmake(0, 0), rightM = cmake(0, 0);
+  for (int r = G - 1; r >= 1; --r) {
+    zP = cfms(cp[r], zP, dP[r]);
+    zM = cfms(cp[r], zM, dM[r]);
+    if (r == sg.rank) { leftP = zP; leftM = zM; }
+    if (r == sg.rank + 1) { rightP = zP; rightM = zM; }
+  }
+  zout[kk] = leftP; zout[K + kk] = leftM; zout[2 * K + kk] = rightP; zout[3 * K + kk] = rightM;
+}
+
+// R1 <- e_0 in slot 0, e_{P-1} in slot 1 (right-hand sides of the two interface Green's vectors)
+__global__ void pd_slab_unit_rhs_kernel(cplx* __restrict__ R1, int P, int64_t K) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)P * 2 * K) return;
+  const int64_t q = e / (2 * K);
+  const int slot = (int)((e / K) & 1);
+  R1[e] = ((slot == 0 && q == 0) || (slot == 1 && q == P - 1)) ? cmake(1, 0) : cmake(0, 0);
 }
 
 // --------------------------------------------------------------- host side
@@ -618,6 +811,12 @@ struct SolvePlan {
   int rows[PD_MAX_LEVELS];
   cplx* R[PD_MAX_LEVELS];
   cplx* F[PD_MAX_LEVELS];
+  // slab mode
+  cplx* lastl;
+  cplx* green;
+  cplx* zout;
+  cplx* slabcoef;
+  SlabGeom sg;
 };
 
 static SolvePlan* plan_of(pd_handle* h) { return reinterpret_cast<SolvePlan*>(h->solve_plan); }
@@ -629,8 +828,64 @@ void pd_solve_free(pd_handle* h) {
     if (pl->R[l]) cudaFree(pl->R[l]);
     if (pl->F[l]) cudaFree(pl->F[l]);
   }
+  if (pl->lastl) cudaFree(pl->lastl);
+  if (pl->green) cudaFree(pl->green);
+  if (pl->zout) cudaFree(pl->zout);
+  if (pl->slabcoef) cudaFree(pl->slabcoef);
   delete pl;
   h->solve_plan = nullptr;
+}
+
+static dim3 stream_grid(const pd_handle* h, int K, int nchunks) {
+  const int kblocks = (K + PD_KB - 1) / PD_KB;
+  // enough CTAs for ~8 resident per SM; more chunks than that are looped over
+  int ny = (h->num_sms * 8 + kblocks - 1) / kblocks;
+  if (ny > nchunks) ny = nchunks;
+  if (ny < 1) ny = 1;
+  if (ny > 65535) ny = 65535;
+  return dim3(kblocks, ny);
+}
+
+static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl) {
+  SolvePlan* pl = plan_of(h);
+  memset(&sp, 0, sizeof(sp));
+  sp.n = h->n; sp.m = h->m; sp.K = h->kcount; sp.kbegin = h->kbegin; sp.N_t = h->cfg.N_t;
+  sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
+  sp.plane = (int64_t)h->n * h->kcount;
+  sp.nlev = pl->nlev;
+  sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
+  sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
+  for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
+  sl.lastl = pl->lastl; sl.green = pl->green; sl.zout = pl->zout;
+}
+
+// levels 1..top: reduce, PCR on the top system, back-substitute; leaves the level-1 solution in R[1]
+static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, cudaStream_t st) {
+  const int top = sp.nlev;
+  for (int lev = 1; lev < top; ++lev) {
+    pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+  }
+  const int n = sp.rows[top];
+  int kpb = (PD_PCR_THREADS * PD_PCR_MAXROWS) / n;
+  if (kpb > 32) kpb = 32;
+  // keep at least ~2 CTAs per SM when the frequency count allows it
+  while (kpb > 4 && (sp.K + kpb - 1) / kpb < 2 * h->num_sms) kpb >>= 1;
+  if (kpb < 1) kpb = 1;
+  const size_t smem = (size_t)n * kpb * 64;
+  const int nblk = (sp.K + kpb - 1) / kpb;
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  for (int lev = top - 1; lev >= 1; --lev) {
+    pd_solve_level_back_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+  }
+  return PD_OK;
 }
 
 int pd_solve_plan(pd_handle* h) {
@@ -668,68 +923,116 @@ int pd_solve_plan(pd_handle* h) {
       h->ws_bytes += bytes;
     }
   }
+  if (h->slab_count > 1) {
+    // geometry of every slab (balanced split of the n nodes, first `extra` slabs one node longer)
+    const int G = h->slab_count, ntot = h->cfg.N_x + 1;
+    if (G > PD_MAX_SLABS) {
+      pd_set_error("slab_count %d exceeds %d", G, PD_MAX_SLABS);
+      return PD_ERR_INVALID;
+    }
+    pl->sg.G = G;
+    pl->sg.rank = h->slab_rank;
+    for (int s = 0; s < G; ++s) {
+      const int cnt = ntot / G + (s < ntot % G ? 1 : 0);
+      pl->sg.body[s] = cnt - 1 - (s == G - 1 ? 1 : 0);
+      if (pl->sg.body[s] < 1) {
+        pd_set_error("slab %d of %d has no interior rows (N_x = %d)", s, G, h->cfg.N_x);
+        return PD_ERR_INVALID;
+      }
+    }
+    PD_CUDA(cudaMalloc(&pl->lastl, sizeof(cplx) * 2 * K));
+    PD_CUDA(cudaMalloc(&pl->zout, sizeof(cplx) * 4 * K));
+    PD_CUDA(cudaMemset(pl->lastl, 0, sizeof(cplx) * 2 * K));
+    PD_CUDA(cudaMemset(pl->zout, 0, sizeof(cplx) * 4 * K));
+    PD_CUDA(cudaMalloc(&pl->slabcoef, sizeof(cplx) * (size_t)G * 2 * K));
+    h->ws_bytes += sizeof(cplx) * (6 + (size_t)G * 2) * K;
+    {
+      SolveParams sp; Levels lv; SlabPtrs sl;
+      fill_params(h, sp, lv, sl);
+      pd_slab_coef_kernel<<<dim3((unsigned)((K + PD_KB - 1) / PD_KB), G), PD_KB>>>(sp, pl->sg, pl->slabcoef);
+      PD_CHECK_LAUNCH();
+    }
+    if (pl->nlev >= 1) {
+      // interface Green's vectors: one run of the interface levels on unit right-hand sides
+      const int P = pl->rows[1];
+      size_t bytes = sizeof(cplx) * (size_t)P * 2 * K;
+      PD_CUDA(cudaMalloc(&pl->green, bytes));
+      h->ws_bytes += bytes;
+      SolveParams sp; Levels lv; SlabPtrs sl;
+      fill_params(h, sp, lv, sl);
+      PD_CUDA(cudaMemset(pl->F[0], 0, sizeof(cplx) * (size_t)(P + 1) * 2 * K));
+      const int64_t tot = (int64_t)P * 2 * K;
+      pd_slab_unit_rhs_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(pl->R[1], P, (int64_t)K);
+      PD_CHECK_LAUNCH();
+      int rc = run_interface(h, sp, lv, 0);
+      if (rc) return rc;
+      PD_CUDA(cudaMemcpy(pl->green, pl->R[1], bytes, cudaMemcpyDeviceToDevice));
+    }
+  }
   return PD_OK;
 }
 
-static dim3 stream_grid(const pd_handle* h, int K, int nchunks) {
-  const int kblocks = (K + PD_KB - 1) / PD_KB;
-  // enough CTAs for ~8 resident per SM; more chunks than that are looped over
-  int ny = (h->num_sms * 8 + kblocks - 1) / kblocks;
-  if (ny > nchunks) ny = nchunks;
-  if (ny < 1) ny = 1;
-  if (ny > 65535) ny = 65535;
-  return dim3(kblocks, ny);
-}
-
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev) {
-  SolvePlan* pl = plan_of(h);
-  SolveParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.n = h->n; sp.m = h->m; sp.K = h->kcount; sp.kbegin = h->kbegin; sp.N_t = h->cfg.N_t;
-  sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
-  sp.plane = (int64_t)h->n * h->kcount;
-  sp.nlev = pl->nlev;
-  for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
-  Levels lv;
-  for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
-  const int top = pl->nlev;
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl);
+  const int top = sp.nlev;
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   if (top >= 1) {
-    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp);
+    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
-    for (int lev = 1; lev < top; ++lev) {
-      pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
-      PD_CHECK_LAUNCH();
-      h->launches++;
-    }
-    {
-      const int n = sp.rows[top];
-      int kpb = (PD_PCR_THREADS * PD_PCR_MAXROWS) / n;
-      if (kpb > 32) kpb = 32;
-      // keep at least ~2 CTAs per SM when the frequency count allows it
-      while (kpb > 4 && (sp.K + kpb - 1) / kpb < 2 * h->num_sms) kpb >>= 1;
-      if (kpb < 1) kpb = 1;
-      const size_t smem = (size_t)n * kpb * 64;
-      const int nblk = (sp.K + kpb - 1) / kpb;
-      PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
-      PD_CHECK_LAUNCH();
-      h->launches++;
-    }
-    for (int lev = top - 1; lev >= 1; --lev) {
-      pd_solve_level_back_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
-      PD_CHECK_LAUNCH();
-      h->launches++;
-    }
+    int rc = run_interface(h, sp, lv, st);
+    if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], st);
   } else if (ev) {
     cudaEventRecord(ev[0], st);
     cudaEventRecord(ev[1], st);
   }
-  pd_solve_passB_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp);
+  pd_solve_passB_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches++;
+  return PD_OK;
+}
+
+// slab mode, first half: pass A, interface levels, slab functionals -> out[6][K]
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl);
+  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
+  const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
+  SolvePlan* pl = plan_of(h);
+  if (sp.nlev >= 1) {
+    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+    int rc = run_interface(h, sp, lv, st);
+    if (rc) return rc;
+  } else {
+    // a single chunk: its first / last entries come from one forward sweep; reuse pass A with a
+    // private F buffer (zout is free at this point: 4K entries >= 2K)
+    lv.F[0] = pl->zout;
+    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+  }
+  pd_slab_functionals_kernel<<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, out);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// slab mode, second half: global separator solve from the gathered functionals, then pass B
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl);
+  SolvePlan* pl = plan_of(h);
+  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
+  const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
+  pd_slab_global_kernel<<<kblocks, PD_KB, 0, st>>>(gathered, sp, pl->sg, pl->slabcoef, pl->zout);
+  PD_CHECK_LAUNCH();
+  pd_solve_passB_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  PD_CHECK_LAUNCH();
+  h->launches += 2;
   return PD_OK;
 }

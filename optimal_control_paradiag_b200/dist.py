@@ -17,6 +17,13 @@ The compute backend is a ``ParaDiagHandle`` created with this rank's frequency s
 (``pd_stage_fft`` / ``pd_stage_solve`` of include/paradiag.h).  The transposes use
 ``all_to_all_single`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) with uneven splits,
 so neither n = N_x + 1 nor N_t has to be divisible by the world size.
+
+``mode="slab"`` keeps the NODE-slab sharding through stage 2 instead: the partition method that
+already solves each x-line in chunks is extended across ranks -- every rank eliminates its slab
+(``pd_slab_reduce``), the first/last entries of the slab-local solves (6 N_t complex numbers per rank)
+are all-gathered, every rank solves the (G-1)-row separator system of each frequency redundantly
+and back-substitutes its slab (``pd_slab_finish``).  Communication drops from 2 x (G-1)/G x S/G bytes
+per rank (NVLink-bound) to 96 N_t bytes per rank; no transposes, no pack/unpack.
 """
 import numpy as np
 
@@ -32,7 +39,8 @@ def slab_bounds(total, parts):
 
 
 class DistributedDiagFFTPC:
-    def __init__(self, N_x, N_t, T=2.0, gamma=1.0, device=0, group=None, backend_factory=None):
+    def __init__(self, N_x, N_t, T=2.0, gamma=1.0, device=0, group=None, backend_factory=None,
+                 mode="alltoall"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -53,9 +61,19 @@ class DistributedDiagFFTPC:
             self.device = torch.device(f"cuda:{device}")
         else:
             self.device = torch.device("cpu")
-        self.backend = backend_factory(k_begin=self.koff[self.rank], k_count=self.k_r, n_local=self.n_r)
+        if mode not in ("alltoall", "slab"):
+            raise ValueError(f"unknown mode {mode!r}")
+        self.mode = mode
         c128 = torch.complex128
         self.local_size = 2 * self.n_r * self.N_t
+        if mode == "slab":
+            self.backend = backend_factory(slab_rank=self.rank, slab_count=self.world)
+            self.w_time = torch.empty(self.local_size, dtype=c128, device=self.device)
+            self.fl_out = torch.empty(6 * self.N_t, dtype=c128, device=self.device)
+            self.gathered = torch.empty(self.world * 6 * self.N_t, dtype=c128, device=self.device)
+            self.comm_bytes_per_apply = 16 * 6 * self.N_t
+            return
+        self.backend = backend_factory(k_begin=self.koff[self.rank], k_count=self.k_r, n_local=self.n_r)
         self.freq_size = 2 * self.n * self.k_r
         # work buffers: time-domain slab, frequency-domain slab, send / receive staging
         self.w_time = torch.empty(self.local_size, dtype=c128, device=self.device)
@@ -73,7 +91,11 @@ class DistributedDiagFFTPC:
         return getattr(self.backend, "launch_count", 0)
 
     def describe(self):
-        return {"world": self.world, "node_slabs": self.ncount, "freq_slabs": self.kcount,
+        if self.mode == "slab":
+            return {"world": self.world, "mode": "slab", "node_slabs": self.ncount,
+                    "allgather_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply,
+                    "collective": "one all_gather of 6 N_t complex values per rank (slab functionals)"}
+        return {"world": self.world, "mode": "alltoall", "node_slabs": self.ncount, "freq_slabs": self.kcount,
                 "alltoall_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply,
                 "collective": "all_to_all_single x2 (uneven splits), pack/unpack by strided copies"}
 
@@ -100,6 +122,8 @@ class DistributedDiagFFTPC:
         t = self.torch
         if y_local is None:
             y_local = t.empty_like(x_local)
+        if self.mode == "slab":
+            return self._apply_slab(x_local, y_local)
         n_r, k_r, n, N_t, G = self.n_r, self.k_r, self.n, self.N_t, self.world
         # stage 1: inverse FFT along time of this rank's 2 n_r lines (:500-501)
         self.backend.stage_fft(x_local.reshape(-1), self.w_time, 2 * n_r, True)
@@ -134,6 +158,16 @@ class DistributedDiagFFTPC:
             off += self.a_send[s]
         # stage 3: forward FFT along time (:547-548)
         self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * n_r, False)
+        return y_local
+
+    def _apply_slab(self, x_local, y_local):
+        t = self.torch
+        self.backend.stage_fft(x_local.reshape(-1), self.w_time, 2 * self.n_r, True)      # :500-501
+        self.backend.slab_reduce(self.w_time, self.fl_out)
+        self.dist.all_gather_into_tensor(t.view_as_real(self.gathered).reshape(-1),
+                                         t.view_as_real(self.fl_out).reshape(-1), group=self.group)
+        self.backend.slab_finish(self.w_time, self.gathered)                               # :445-540
+        self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * self.n_r, False)     # :547-548
         return y_local
 
     def gather_to_global(self, y_local):

@@ -21,7 +21,7 @@ def _torch():
 
 class ParaDiagHandle:
     def __init__(self, N_x, N_t, T=2.0, gamma=1.0, alpha=1.0, bug138=True, device=0,
-                 k_begin=0, k_count=0, n_local=0):
+                 k_begin=0, k_count=0, n_local=0, slab_rank=0, slab_count=0):
         self._h = C.c_void_p()
         self.lib = _lib.load_library()
         self.N_x, self.N_t, self.T, self.gamma = int(N_x), int(N_t), float(T), float(gamma)
@@ -33,7 +33,8 @@ class ParaDiagHandle:
         self.n_local = int(n_local) if n_local else self.n
         cfg = pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=self.N_x, N_t=self.N_t, bug138=int(bool(bug138)),
                         T=self.T, gamma=self.gamma, alpha=float(alpha), device=self.device,
-                        k_begin=int(k_begin), k_count=int(k_count), n_local=int(n_local))
+                        k_begin=int(k_begin), k_count=int(k_count), n_local=int(n_local),
+                        slab_rank=int(slab_rank), slab_count=int(slab_count))
         check(self.lib.pd_create(C.byref(cfg), C.byref(self._h)))
 
     # ------------------------------------------------------------------ lifetime
@@ -124,6 +125,18 @@ class ParaDiagHandle:
 
     def stage_solve(self, w):
         check(self.lib.pd_stage_solve(self._h, self._ptr(w, 2 * self.n * self.k_count, "w"), self._stream()))
+        return w
+
+    def slab_reduce(self, w, out):
+        """Slab mode, first half (pd_slab_reduce): out (6, N_t) <- slab functionals."""
+        check(self.lib.pd_slab_reduce(self._h, self._ptr(w, None, "w"), self._ptr(out, 6 * self.N_t, "out"),
+                                      self._stream()))
+        return out
+
+    def slab_finish(self, w, gathered):
+        """Slab mode, second half (pd_slab_finish): separator solve + back-substitution in place."""
+        check(self.lib.pd_slab_finish(self._h, self._ptr(w, None, "w"), self._ptr(gathered, None, "gathered"),
+                                      self._stream()))
         return w
 
     def matvec(self, x, y=None):

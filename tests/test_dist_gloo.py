@@ -18,12 +18,76 @@ class OracleStageBackend:
     """pd_stage_fft / pd_stage_solve semantics on CPU tensors, from the oracle's fast route."""
     launch_count = 0
 
-    def __init__(self, N_x, N_t, T, gamma, k_begin, k_count, n_local):
+    def __init__(self, N_x, N_t, T, gamma, k_begin=0, k_count=0, n_local=0, slab_rank=0, slab_count=0):
         from oracle.pc_fast import DiagFFTPCFast
         self.pc = DiagFFTPCFast(N_x, N_t, T, gamma, workers=1)
         self.N_t, self.n = N_t, N_x + 1
+        k_count = k_count or N_t
         self.ks = slice(k_begin, k_begin + k_count)
         self.k_count = k_count
+        self.G, self.r = slab_count, slab_rank
+        if slab_count > 1:
+            counts, offs = slab_bounds(self.n, slab_count)
+            self.n_r = counts[slab_rank]
+            self.body = [c - 1 - (1 if s == slab_count - 1 else 0) for s, c in enumerate(counts)]
+
+    # ---- slab mode, restated with dense little solves (SPIKE): independent of the CUDA algorithm
+    def _rot_in(self, W):
+        pc = self.pc
+        uz = W[0] * np.conj(pc.z)
+        ip = (1j * pc.sigma) * W[1]
+        return (uz + ip) / 2, np.conj((uz - ip) / 2)          # slot +, conj slot -
+
+    def _T(self, m, k):
+        a, b = self.pc.a[k], self.pc.b[k]
+        return (np.diag(np.full(m, b)) + np.diag(np.full(m - 1, a), 1) + np.diag(np.full(m - 1, a), -1))
+
+    def slab_reduce(self, w, out):
+        W = w.numpy().reshape(2, self.n_r, self.N_t)
+        rP, rM = self._rot_in(W)
+        m = self.body[self.r]
+        o = out.numpy().reshape(6, self.N_t)
+        for k in range(self.N_t):
+            T = self._T(m, k)
+            yP = np.linalg.solve(T, rP[1:1 + m, k])
+            yM = np.linalg.solve(T, rM[1:1 + m, k])
+            o[0, k], o[1, k], o[2, k], o[3, k] = yP[0], yM[0], yP[-1], yM[-1]
+            o[4, k], o[5, k] = (rP[0, k], rM[0, k]) if self.r > 0 else (0, 0)
+
+    def slab_finish(self, w, gathered):
+        pc, G, r = self.pc, self.G, self.r
+        W = w.numpy().reshape(2, self.n_r, self.N_t)
+        g = gathered.numpy().reshape(G, 6, self.N_t)
+        rP, rM = self._rot_in(W)
+        m = self.body[r]
+        for k in range(self.N_t):
+            a, b = pc.a[k], pc.b[k]
+            inv = [np.linalg.inv(self._T(ms, k)) for ms in self.body]
+            A = np.zeros((G - 1, G - 1), complex)
+            rhs = np.zeros((G - 1, 2), complex)
+            for s in range(1, G):                         # separator s between slab s-1 and slab s
+                A[s - 1, s - 1] = b - a * a * (inv[s - 1][-1, -1] + inv[s][0, 0])
+                if s > 1:
+                    A[s - 1, s - 2] = -a * a * inv[s - 1][-1, 0]
+                if s < G - 1:
+                    A[s - 1, s] = -a * a * inv[s][0, -1]
+                rhs[s - 1, 0] = g[s, 4, k] - a * (g[s - 1, 2, k] + g[s, 0, k])
+                rhs[s - 1, 1] = g[s, 5, k] - a * (g[s - 1, 3, k] + g[s, 1, k])
+            zs = np.linalg.solve(A, rhs)
+            zl = zs[r - 1] if r > 0 else np.zeros(2)
+            zr = zs[r] if r < G - 1 else np.zeros(2)
+            out = []
+            for slot, rr in ((0, rP), (1, rM)):
+                v = rr[1:1 + m, k].copy()
+                v[0] -= a * zl[slot]
+                v[-1] -= a * zr[slot]
+                out.append(np.linalg.solve(self._T(m, k), v))
+            zP = np.zeros(self.n_r, complex)
+            zM = np.zeros(self.n_r, complex)
+            zP[1:1 + m], zM[1:1 + m] = out[0], np.conj(out[1])
+            zP[0], zM[0] = zl[0], np.conj(zl[1])
+            W[0, :, k] = zP + zM
+            W[1, :, k] = (-1j * pc.sigma[k] * pc.z[k]) * (zP - zM)
 
     def stage_fft(self, src, dst, nlines, inverse):
         import scipy.fft as sfft
@@ -53,14 +117,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N_x, N_t, gamma, ret):
+def _worker(rank, world, port, N_x, N_t, gamma, ret, mode="alltoall"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle.pc_fast import DiagFFTPCFast
         factory = lambda **kw: OracleStageBackend(N_x, N_t, 2.0, gamma, **kw)
-        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=gamma, backend_factory=factory)
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=gamma, backend_factory=factory, mode=mode)
         rng = np.random.default_rng(0)
         size = 2 * (N_x + 1) * N_t
         xg = rng.standard_normal(size) + 1j * rng.standard_normal(size)
@@ -70,7 +134,7 @@ def _worker(rank, world, port, N_x, N_t, gamma, ret):
         ref = DiagFFTPCFast(N_x, N_t, 2.0, gamma).apply(xg)
         err = np.linalg.norm(yg - ref) / np.linalg.norm(ref)
         d = dpc.describe()
-        ok = err < 1e-12 and sum(d["node_slabs"]) == N_x + 1 and sum(d["freq_slabs"]) == N_t
+        ok = err < 1e-11 and sum(d["node_slabs"]) == N_x + 1 and (mode == "slab" or sum(d["freq_slabs"]) == N_t)
         ret[rank] = (bool(ok), float(err))
     finally:
         dist.destroy_process_group()
@@ -82,6 +146,15 @@ def test_distributed_apply_matches_single_process_oracle(world, N_x, N_t):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), N_x, N_t, 0.5, ret), nprocs=world, join=True)
     assert len(ret) == world
+    for r in range(world):
+        ok, err = ret[r]
+        assert ok, (r, err)
+
+
+@pytest.mark.parametrize("world,N_x,N_t", [(2, 16, 6), (3, 22, 5)])
+def test_slab_mode_apply_matches_single_process_oracle(world, N_x, N_t):
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), N_x, N_t, 0.5, ret, "slab"), nprocs=world, join=True)
     for r in range(world):
         ok, err = ret[r]
         assert ok, (r, err)

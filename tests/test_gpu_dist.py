@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N_x, N_t, gamma, ret):
+def _worker(rank, world, port, N_x, N_t, gamma, ret, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -28,7 +28,7 @@ def _worker(rank, world, port, N_x, N_t, gamma, ret):
     try:
         from optimal_control_paradiag_b200 import ParaDiagHandle
         from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
-        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=gamma, device=rank)
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=gamma, device=rank, mode=mode)
         rng = np.random.default_rng(0)
         size = 2 * (N_x + 1) * N_t
         xg = torch.tensor(rng.standard_normal(size) + 1j * rng.standard_normal(size), device=f"cuda:{rank}")
@@ -42,12 +42,14 @@ def _worker(rank, world, port, N_x, N_t, gamma, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N_x,N_t", [(80, 81), (255, 128), (1024, 1024)])
-def test_sharded_apply_equals_single_gpu_apply(N_x, N_t):
+@pytest.mark.parametrize("mode", ["alltoall", "slab"])
+@pytest.mark.parametrize("N_x,N_t", [(80, 81), (255, 128), (1024, 1024), (37, 16), (4096, 64)])
+def test_sharded_apply_equals_single_gpu_apply(N_x, N_t, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), N_x, N_t, 1.0, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), N_x, N_t, 1.0, ret, mode), nprocs=world, join=True)
     for r in range(world):
-        assert ret[r] < 1e-13, (r, ret[r])
+        # all-to-all: same kernels on the same data; slab: a different elimination order
+        assert ret[r] < (1e-13 if mode == "alltoall" else 1e-10), (r, ret[r])
