@@ -32,7 +32,7 @@
 //            preserves, so its coefficients too are regenerated, never stored).
 //            While it has more than PD_PCR_MAX rows it is reduced again the same way
 //            with chunks of PD_LG = 16 rows (generic kernels, ~6 % of the data).
-//   top      the last interface system (<= 128 rows per k) is solved by parallel
+//   top      the last interface system (<= 32 rows per k) is solved by parallel
 //            cyclic reduction held in shared memory, up to 32 frequencies per CTA.
 //   back     the generic levels are back-substituted, then pass B (1 read + 1 write
 //            sweep of the big array) runs Thomas per (k, chunk) with the now-known
@@ -46,7 +46,7 @@
 #define PD_L 16            // level-0 chunk length (rows held in registers)
 #define PD_LG 16           // chunk length of the generic interface levels
 #define PD_KB 128          // frequencies per CTA in the streaming passes
-#define PD_PCR_MAX 128     // largest interface system handed to the PCR kernel
+#define PD_PCR_MAX 32      // largest interface system handed to the PCR kernel
 #define PD_PCR_THREADS 256
 #define PD_PCR_MAXROWS 4   // rows per thread in the PCR kernel
 #define PD_MAX_LEVELS 8
@@ -131,14 +131,15 @@ __device__ __host__ __forceinline__ int chunk_len(int level) { return level == 0
 // The (V, E) recurrence in homogeneous form: (V, e, one) may be rescaled together at any time, only
 // ratios are ever used.  Far from resonance |eta| is large, V grows geometrically (the interface
 // couplings decay accordingly) and would overflow after two levels without the rescaling; when the
-// coupling is below 1e-150 of the diagonal the system is treated as decoupled (`diag`).
+// coupling is below 1e-60 of the diagonal the system is treated as decoupled (`diag`).
 struct VRec {
   cplx eta, V, e, E;  // E: the increment used in the last step (E_i = V_i - V_{i-1} - one)
   double one;
   bool diag;
   __device__ __forceinline__ void init(cplx off, cplx det, cplx extra /* added to eta in the first step */) {
     const double mo = fabs(off.x) + fabs(off.y), md = fabs(det.x) + fabs(det.y);
-    diag = !(mo > md * 1e-150);
+    // |eta| <= 1e60 keeps eta * V (|V| <= 1e100 after rescaling, one step of growth |eta|) finite
+    diag = !(mo > md * 1e-60);
     eta = diag ? cmake(0, 0) : cmul(det, crcp(off));
     V = cmake(1, 0);
     one = 1.0;

@@ -107,6 +107,27 @@ def test_pc_apply_gamma_sweep_4096_small_gamma():
             assert rel(h.pc_apply_host(x), ref) < PC_TOL
 
 
+@pytest.mark.parametrize("N_x,N_t", [(9536, 8), (9600, 8), (16384, 12), (20000, 5), (65536, 4)])
+def test_pc_apply_deep_partition_levels_against_long_double(N_x, N_t):
+    # 3 and 4 partition levels (rows 9599 -> 564 -> 33 -> 1 etc.); compared with the 80-bit oracle
+    with ParaDiagHandle(N_x, N_t) as h:
+        x = rand_x(h.size)
+        truth = DiagFFTPCFast(N_x, N_t, dtype=np.longdouble).apply(x)
+        y = h.pc_apply_host(x)
+        assert float(np.linalg.norm(y - truth) / np.linalg.norm(truth)) < 1e-10
+
+
+def test_cuda_path_is_closer_to_the_truth_than_fp64_lu():
+    # detuning-form coefficients: no cancellation near the discrete wave resonances (pd_solve.cu)
+    N_x, N_t = 4096, 128
+    with ParaDiagHandle(N_x, N_t) as h:
+        for x in (rand_x(h.size), AllAtOnce(N_x, N_t).rhs() + 0j):
+            truth = DiagFFTPCFast(N_x, N_t, dtype=np.longdouble).apply(x)
+            e_oracle = float(np.linalg.norm(DiagFFTPCFast(N_x, N_t).apply(x) - truth) / np.linalg.norm(truth))
+            e_cuda = float(np.linalg.norm(h.pc_apply_host(x) - truth) / np.linalg.norm(truth))
+            assert e_cuda < 1e-10 and e_cuda < 0.2 * e_oracle, (e_cuda, e_oracle)
+
+
 def test_pc_apply_conditioning_limited_case_against_long_double():
     # gamma = 1, N_x = 4096: cond ~ 2e8, two fp64 algorithms differ by ~1e-9; compare both with 80-bit
     N_x, N_t = 4096, 32
@@ -219,6 +240,24 @@ def test_gmres_restart_and_max_it():
         assert np.linalg.norm(r) <= 1.05e-8 * np.linalg.norm(pc.apply(b))
         x, its, hist, reason = h.gmres(bt, rtol=1e-14, restart=300, max_it=7)
         assert its == 7 and reason == "DIVERGED_ITS" and len(hist) == 8
+
+
+def test_gmres_iteration_parity_at_4096():
+    # beyond N_x ~ 2000 the 5-step termination of the manufactured problem is broken by rounding
+    # (cond ~ 2e8): the count then depends on how much noise each implementation injects.  The device
+    # path (cancellation-free solve and matvec) injects less than the fp64 oracle, so it may need FEWER
+    # iterations; it must never need more than the oracle's count + 1 (north star: +-1).
+    N_x, N_t = 4096, 512
+    from oracle import csolve
+    op = AllAtOnce(N_x, N_t)
+    pc = DiagFFTPCFast(N_x, N_t, solver=csolve.thomas_toeplitz_c)
+    with ParaDiagHandle(N_x, N_t) as h:
+        b = h.build_rhs()
+        for rtol in (1e-5, 1e-7):
+            _, its_o, hist_o, _ = oracle_gmres(op.matvec, pc.apply, op.rhs() + 0j, rtol=rtol, max_it=60)
+            _, its, hist, reason = h.gmres(b, rtol=rtol, max_it=60)
+            assert reason == "CONVERGED_RTOL" and its <= its_o + 1 and its >= 5, (rtol, its, its_o, hist, hist_o)
+            assert np.allclose(hist[:5], hist_o[:5], rtol=1e-6)          # identical until rounding takes over
 
 
 def test_gmres_config2_manufactured_rhs():
