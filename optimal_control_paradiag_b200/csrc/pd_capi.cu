@@ -27,6 +27,7 @@ extern "C" int pd_destroy(pd_handle* h) {
   cudaSetDevice(h->cfg.device);
   pd_krylov_free(h);
   if (h->twiddle) cudaFree(h->twiddle);
+  if (h->twiddle_half) cudaFree(h->twiddle_half);
   pd_solve_free(h);
 
   if (h->work) cudaFree(h->work);

@@ -80,6 +80,7 @@ struct pd_handle {
 
   // FFT plan
   cplx* twiddle;  // e^{-2 pi i j / N_t}, j < N_t
+  cplx* twiddle_half;  // same for N_t / 2 (only N_t = 16384)
   int fft_kind;   // 0 generic smem Stockham, 1 power-of-two register kernel
   int npass;
   int radix[PD_MAX_FFT_PASSES];

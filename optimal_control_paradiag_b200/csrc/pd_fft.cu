@@ -12,7 +12,11 @@
 //   kind 0  any other N_t (the upstream default is 81 = 3^4): mixed-radix
 //           Stockham with direct (O(R) per output) passes ping-ponging between
 //           two shared-memory buffers; prime factors of any size are accepted.
+#include <cooperative_groups.h>
+
 #include "pd_common.cuh"
+
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------ twiddle table
 __global__ void pd_twiddle_kernel(cplx* tw, int N) {
@@ -149,11 +153,14 @@ __device__ __forceinline__ void dft_pow2<16>(cplx* v) {
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 
 // One Stockham pass of radix R over the 16 elements this thread owns.
-// src/dst: either shared (padded) or global (first load / last store).
-template <int R, bool INV, bool FIRST, bool LAST>
+//   FIRST : inputs come from global memory (or, with PRE, are already in `io`)
+//   LAST  : outputs go to global memory (or, with KEEP, stay in `io`)
+//   io    : 16 registers; input order io[u*R + q] <-> element (t + u T) + q N/R,
+//           output order io[u*R + r] <-> element base(t + u T) + r Ns
+template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false>
 __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
                                           cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
-                                          int t, int T, double scale, bool live) {
+                                          int t, int T, double scale, bool live, cplx* io = nullptr) {
   constexpr int NB = 16 / R;  // butterflies per thread
   const int NR = N / R;
   const int tws = N / (Ns * R);
@@ -163,8 +170,13 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
     const int j = t + u * T;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
-      cplx x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
-      if (FIRST && INV) x.y = -x.y;
+      cplx x;
+      if (PRE) {
+        x = io[u * R + q];
+      } else {
+        x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
+        if (FIRST && INV) x.y = -x.y;
+      }
       v[u][q] = x;
     }
   }
@@ -197,7 +209,9 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       cplx x = v[u][r];
-      if (LAST) {
+      if (KEEP) {
+        io[u * R + r] = x;
+      } else if (LAST) {
         if (INV) x.y = -x.y;
         if (live) gdst[base + r * Ns] = cscale(x, scale);
       } else {
@@ -247,6 +261,84 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
   }
 }
 
+// N_t = 16384: a line is 256 KiB, more than one CTA's shared memory, so a 2-CTA thread-block cluster
+// transforms it as 2 x 8192: each CTA runs the 8192-point pipeline above entirely in its own shared
+// memory and ONE exchange through distributed shared memory performs the remaining radix-2 stage.
+//   TO_FREQ (time -> frequency, decimation in frequency): the radix-2 stage comes first,
+//       y0[n] = x[n] + x[n+N/2],  y1[n] = (x[n] - x[n+N/2]) W_N^n,  X[2c] = FFT(y0)[c], X[2c+1] = FFT(y1)[c];
+//       CTA 0 stores the even frequencies in the first half of the line, CTA 1 the odd ones in the second.
+//   !TO_FREQ (frequency -> time, decimation in time): input in that same even/odd order,
+//       y[i] = A[i] + W_N^i B[i],  y[i+N/2] = A[i] - W_N^i B[i]  with A, B the two half transforms.
+// The frequency axis of an N_t = 16384 problem is therefore stored as [even k | odd k]; the per-frequency
+// solves are independent and only need the index map (pd_freq_index), so no reordering pass exists.
+#define PD_BIGN 16384
+template <bool INV, bool TO_FREQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
+pd_fft_16k_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
+                  const cplx* __restrict__ tw, const cplx* __restrict__ tw_half, double scale) {
+  constexpr int N = PD_BIGN, H = N / 2, T = H / 16;  // T = 512 threads per CTA
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned c = cluster.block_rank();
+  cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw);
+  const cplx* peer = cluster.map_shared_rank(sm, c ^ 1u);
+  const int t = threadIdx.x;
+  const int64_t ncl = gridDim.x / 2;
+  for (int64_t line = blockIdx.x / 2; line < nlines; line += ncl) {
+    const cplx* gsrc = in + line * N + (int64_t)c * H;
+    cplx* gdst = out + line * N + (int64_t)c * H;
+    cplx io[16];
+    if (TO_FREQ) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        cplx x = gsrc[t + T * q];
+        if (INV) x.y = -x.y;
+        io[q] = x;
+        sm[pad16(t + T * q)] = x;
+      }
+      cluster.sync();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const cplx o = peer[pad16(t + T * q)];
+        io[q] = c == 0 ? cadd(io[q], o) : cmul(csub(o, io[q]), tw[t + T * q]);
+      }
+      cluster.sync();  // the peer has read my half before the local passes overwrite it
+      pow2_pass<16, false, true, false, true, false>(gsrc, gdst, sm, tw_half, H, 1, t, T, scale, true, io);
+      pow2_pass<16, false, false, false>(gsrc, gdst, sm, tw_half, H, 16, t, T, scale, true);
+      pow2_pass<8, false, false, false>(gsrc, gdst, sm, tw_half, H, 256, t, T, scale, true);
+      pow2_pass<4, INV, false, true>(gsrc, gdst, sm, tw_half, H, 2048, t, T, scale, true);
+      __syncthreads();
+    } else {
+      pow2_pass<16, INV, true, false>(gsrc, gdst, sm, tw_half, H, 1, t, T, scale, true);
+      pow2_pass<16, false, false, false>(gsrc, gdst, sm, tw_half, H, 16, t, T, scale, true);
+      pow2_pass<8, false, false, false>(gsrc, gdst, sm, tw_half, H, 256, t, T, scale, true);
+      pow2_pass<4, false, false, true, false, true>(gsrc, gdst, sm, tw_half, H, 2048, t, T, scale, true, io);
+      // io[u*4 + r] <-> element t + 512 u + 2048 r of this CTA's half transform
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = t + T * u + 2048 * r;
+          if (c == 1) io[u * 4 + r] = cmul(io[u * 4 + r], tw[i]);  // W_N^i B[i]
+          sm[pad16(i)] = io[u * 4 + r];
+        }
+      cluster.sync();
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = t + T * u + 2048 * r;
+          const cplx o = peer[pad16(i)];
+          cplx y = c == 0 ? cadd(io[u * 4 + r], o) : csub(o, io[u * 4 + r]);
+          if (INV) y.y = -y.y;
+          gdst[i] = cscale(y, scale);
+        }
+      cluster.sync();
+    }
+  }
+}
+
 // --------------------------------------------------------------- host side
 static void factorize(int N, PassList& pl) {
   pl.n = 0;
@@ -274,11 +366,17 @@ int pd_fft_plan(pd_handle* h) {
   h->ws_bytes += sizeof(cplx) * (size_t)N;
   pd_twiddle_kernel<<<(N + 255) / 256, 256>>>(h->twiddle, N);
   PD_CHECK_LAUNCH();
+  if (N == PD_BIGN) {  // the two half transforms of the 2-CTA kernel use the N/2 table
+    PD_CUDA(cudaMalloc(&h->twiddle_half, sizeof(cplx) * (size_t)(N / 2)));
+    h->ws_bytes += sizeof(cplx) * (size_t)(N / 2);
+    pd_twiddle_kernel<<<(N / 2 + 255) / 256, 256>>>(h->twiddle_half, N / 2);
+    PD_CHECK_LAUNCH();
+  }
   PassList pl;
   factorize(N, pl);
   h->npass = pl.n;
   for (int i = 0; i < pl.n; ++i) h->radix[i] = pl.r[i];
-  h->fft_kind = (is_pow2(N) && N >= 64 && N <= 8192) ? 1 : 0;
+  h->fft_kind = (is_pow2(N) && N >= 64 && N <= 16384) ? 1 : 0;
   if (h->fft_kind == 0) {
     size_t smem = 2 * sizeof(cplx) * (size_t)N;
     if (smem > 227 * 1024) {
@@ -318,6 +416,25 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   return PD_OK;
 }
 
+static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
+  const size_t smem = (size_t)(PD_BIGN / 2 + PD_BIGN / 32) * sizeof(cplx);
+  int64_t ncl = nlines < (int64_t)h->num_sms * 4 ? nlines : (int64_t)h->num_sms * 4;
+  const double scale = inverse ? 1.0 / (double)PD_BIGN : 1.0;
+  // inverse (time -> frequency, :500-501) leaves the even/odd frequency order, forward (:547-548) consumes it
+  if (inverse) {
+    auto k = pd_fft_16k_kernel<true, true>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)(2 * ncl), 512, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half, scale);
+  } else {
+    auto k = pd_fft_16k_kernel<false, false>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)(2 * ncl), 512, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half, scale);
+  }
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
                   cudaStream_t st) {
   const int N = h->cfg.N_t;
@@ -332,6 +449,7 @@ int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int i
       case 2048: return launch_pow2<16, 16, 8, 1>(h, in, out, nlines, inverse, st);
       case 4096: return launch_pow2<16, 16, 16, 1>(h, in, out, nlines, inverse, st);
       case 8192: return launch_pow2<16, 16, 8, 4>(h, in, out, nlines, inverse, st);
+      case 16384: return launch_16k(h, in, out, nlines, inverse, st);
       default: break;
     }
   }

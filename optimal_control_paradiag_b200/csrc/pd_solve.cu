@@ -61,6 +61,7 @@ struct SolveParams {
   // Single-GPU: row 0 and row m+1 are the Dirichlet nodes.  Slab mode (x-slab r of G): row 0 is the
   // inter-slab separator (r > 0) and the last body row is followed by the next slab's separator (r < G-1).
   int first_dirichlet, last_dirichlet;
+  int freq_perm;  // 1: columns hold [even k | odd k] (the N_t = 16384 FFT kernel's frequency order)
 };
 
 // Slab-mode extras (device pointers; all null in single-GPU mode)
@@ -76,6 +77,14 @@ struct KCoef {
   cplx zc;       // conj(z) = e^{-i theta}
   double sigma;  // sign(cos theta)
 };
+
+// frequency index of column `kk` of this handle's frequency block
+__device__ __forceinline__ int freq_of(const SolveParams& sp, int kk) {
+  const int col = sp.kbegin + kk;
+  if (!sp.freq_perm) return col;
+  const int half = sp.N_t >> 1;
+  return col < half ? 2 * col : 2 * (col - half) + 1;
+}
 
 __device__ __forceinline__ KCoef make_coef(int kglob, const SolveParams& sp) {
   KCoef kc;
@@ -250,7 +259,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
   const int kk = blockIdx.x * PD_KB + tid;
   const bool valid = kk < sp.K;
   const int kc_idx = valid ? kk : sp.K - 1;
-  const KCoef kc = make_coef(sp.kbegin + kc_idx, sp);
+  const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   const cplx* wu = w + kc_idx;
   const cplx* wp = w + sp.plane + kc_idx;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
-  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const Sys below = level_sys(kc, sp, lev - 1);
   const Sys s = reduce_sys(below, chunk_len(lev - 1));
   const int64_t K = sp.K;
@@ -358,7 +367,7 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
   __shared__ cplx mtab[PD_LG][PD_KB];  // per-thread column of chunk pivots
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
-  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const Sys s = level_sys(kc, sp, lev);
   const int64_t K = sp.K;
   const int P = sp.rows[lev + 1], Llast = s.n - P * (PD_LG + 1);
@@ -449,7 +458,7 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
   if (tid < kpb) {
     int kk = kk0 + tid;
     if (kk >= sp.K) kk = sp.K - 1;
-    const KCoef kc = make_coef(sp.kbegin + kk, sp);
+    const KCoef kc = make_coef(freq_of(sp, kk), sp);
     const Sys below = level_sys(kc, sp, lev - 1);
     const Sys s = reduce_sys(below, chunk_len(lev - 1));
     // at the top level the detuning has been amplified by (L+1)^2 per level: plain sums are safe here
@@ -545,7 +554,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
   const int kk = blockIdx.x * PD_KB + tid;
   const bool valid = kk < sp.K;
   const int kc_idx = valid ? kk : sp.K - 1;
-  const KCoef kc = make_coef(sp.kbegin + kc_idx, sp);
+  const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   cplx* wu = w + kc_idx;
   cplx* wp = w + sp.plane + kc_idx;
@@ -681,7 +690,7 @@ pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const int64_t K = sp.K;
-  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
   cplx fP = lv.F[0] ? lv.F[0][kk] : cmake(0, 0), fM = lv.F[0] ? lv.F[0][K + kk] : cmake(0, 0);
   cplx lP = cmake(0, 0), lM = cmake(0, 0);
@@ -730,7 +739,7 @@ pd_slab_coef_kernel(SolveParams sp, SlabGeom sg, cplx* __restrict__ coef) {
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   const int s = blockIdx.y;
   if (kk >= sp.K) return;
-  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
   VRec v;
   v.init(kc.a, kc.sh, cmake(0, 0));
   cplx rv = cmake(0, 0), dvv = cmake(1, 0);  // decoupled: V_{m-1}/V_m -> 0
@@ -751,7 +760,7 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, SolveParams sp, SlabGeo
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const int64_t K = sp.K;
-  const KCoef kc = make_coef(sp.kbegin + kk, sp);
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const int G = sg.G;
   cplx rv[PD_MAX_SLABS], dvv[PD_MAX_SLABS];
   for (int s = 0; s < G; ++s) {
@@ -856,6 +865,7 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl)
   sp.nlev = pl->nlev;
   sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
   sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
+  sp.freq_perm = h->cfg.N_t == 16384;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = pl->green; sl.zout = pl->zout;

@@ -37,7 +37,7 @@ def rand_x(size, seed=0, real=False):
 
 
 # ---------------------------------------------------------------------------- time-axis FFT
-@pytest.mark.parametrize("N_t", [3, 5, 13, 64, 81, 96, 97, 100, 128, 256, 512, 625, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("N_t", [3, 5, 13, 64, 81, 96, 97, 100, 128, 256, 512, 625, 1024, 2048, 4096, 8192, 16384])
 def test_fft_matches_scipy(N_t):
     import scipy.fft as sfft
     nl = 19
@@ -45,6 +45,18 @@ def test_fft_matches_scipy(N_t):
     with ParaDiagHandle(8, N_t) as h:
         xt = torch.tensor(x, device=DEV).reshape(-1)
         yt = torch.empty_like(xt)
+        if N_t == 16384:
+            # 2-CTA kernel: time -> frequency leaves [even k | odd k]; frequency -> time consumes it
+            perm = np.concatenate([np.arange(0, N_t, 2), np.arange(1, N_t, 2)])
+            h.stage_fft(xt, yt, nl, True)
+            assert rel(yt.cpu().numpy().reshape(nl, N_t), sfft.ifft(x, axis=1)[:, perm]) < 5e-15
+            xp = torch.tensor(np.ascontiguousarray(x[:, perm]), device=DEV).reshape(-1)
+            h.stage_fft(xp, yt, nl, False)
+            assert rel(yt.cpu().numpy().reshape(nl, N_t), sfft.fft(x, axis=1)) < 5e-15
+            h.stage_fft(xt, yt, nl, True)
+            h.stage_fft(yt, yt, nl, False)
+            assert rel(yt.cpu().numpy().reshape(nl, N_t), x) < 5e-15
+            return
         h.stage_fft(xt, yt, nl, False)
         assert rel(yt.cpu().numpy().reshape(nl, N_t), sfft.fft(x, axis=1)) < 5e-15
         h.stage_fft(xt, yt, nl, True)
@@ -54,7 +66,7 @@ def test_fft_matches_scipy(N_t):
 
 
 # ------------------------------------------------------------------------------- PC apply
-SMALL = [(2, 3, 1.0), (3, 4, 1.0), (16, 13, 1.0), (17, 64, 1.0), (18, 64, 1.0), (34, 8, 1.0), (35, 12, 1e-2),
+SMALL = [(20, 16384, 1.0), (2, 3, 1.0), (3, 4, 1.0), (16, 13, 1.0), (17, 64, 1.0), (18, 64, 1.0), (34, 8, 1.0), (35, 12, 1e-2),
          (16, 16, 1.0), (20, 81, 1.0), (80, 81, 1.0), (24, 64, 1e-4), (40, 96, 1e-2), (100, 128, 1.0),
          (257, 60, 1.0), (256, 256, 1.0), (300, 81, 1e-6)]
 
