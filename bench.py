@@ -264,8 +264,27 @@ def run_ours(args):
         names = {"ifft": "pd_fft_pow2_kernel<inv>", "fft": "pd_fft_pow2_kernel<fwd>", "passA": "pd_solve_passA_kernel",
                  "pcr": "pd_solve_pcr_kernel", "passB": "pd_solve_passB_kernel"}
         ach = alg / (prof[dom] * 1e-3) / 1e9
+        # DRAM traffic of that kernel per launch, from the committed `ncu --set full` capture of this
+        # command (profiles/r01_ncu_full_final.txt; cfg3 only)
+        traffic = None
+        try:
+            if args.workload == "cfg3":
+                key = {"ifft": "pd_fft_pow2_kernel<16, 16, 16, 1, 1>", "fft": "pd_fft_pow2_kernel<16, 16, 16, 1, 0>",
+                       "passA": "pd_solve_passA_kernel", "passB": "pd_solve_passB_kernel", "pcr": "pd_solve_pcr_kernel"}[dom]
+                blocks = open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.txt")).read().split("== ")
+                for blk in blocks:
+                    if blk.strip() and key in blk.splitlines()[0]:
+                        tot = 0.0
+                        for ln in blk.splitlines():
+                            if "dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln:
+                                val, unit = ln.split()[-2], ln.split()[-1]
+                                tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+                        traffic = tot
+                        break
+        except Exception:
+            traffic = None
         line["roofline"] = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg, "ms_per_launch": prof[dom],
                             "share_of_apply": prof[dom] / tot}
         line["kernels_ms"] = prof

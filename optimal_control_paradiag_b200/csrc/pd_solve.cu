@@ -46,7 +46,8 @@
 #define PD_L 16            // level-0 chunk length (rows held in registers)
 #define PD_LG 16           // chunk length of the generic interface levels
 #define PD_KB 128          // frequencies per CTA in the streaming passes
-#define PD_PCR_MAX 32      // largest interface system handed to the PCR kernel
+#define PD_PCR_MAX 32      // largest interface system handed to the PCR kernel (many frequencies)
+#define PD_PCR_MAX_SMALLK 128  // ... when there are few frequencies (launch-bound sizes: fewer kernels win)
 #define PD_PCR_THREADS 256
 #define PD_PCR_MAXROWS 4   // rows per thread in the PCR kernel
 #define PD_MAX_LEVELS 8
@@ -916,7 +917,7 @@ int pd_solve_plan(pd_handle* h) {
     const int next = pl->rows[l] / (chunk_len(l) + 1);
     pl->rows[l + 1] = next;
     ++l;
-    if (next <= PD_PCR_MAX) break;
+    if (next <= (K <= 2048 ? PD_PCR_MAX_SMALLK : PD_PCR_MAX)) break;
   }
   // l is the top level: solved by PCR when it has rows, absent when rows == 0
   pl->nlev = pl->rows[l] > 0 ? l : l - 1;
