@@ -223,6 +223,20 @@ def run_ours(args):
     ms = float(t.item())
     clocks = sampler.stop() if sampler else None
 
+    gmres_dist = None
+    if world > 1 and args.dist_mode == "slab" and not args.no_gmres:
+        # GMRES time-to-solution on the reference's manufactured problem, all ranks (collective)
+        try:
+            b = handle.build_rhs()
+            handle.gmres(b, rtol=1e-7)
+            barrier()
+            t1 = time.perf_counter()
+            _, its, hist, reason = handle.gmres(b, rtol=1e-7)
+            barrier()
+            gmres_dist = {"seconds": time.perf_counter() - t1, "iterations": its, "reason": reason, "rtol": 1e-7,
+                          "rhs": "manufactured (Build_f/g/IC)"}
+        except Exception as ex:  # pragma: no cover
+            gmres_dist = {"error": str(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -346,6 +360,7 @@ def run_ours(args):
     else:
         line["e2e"] = None
         line["dist"] = handle.describe()
+        line["gmres"] = gmres_dist
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

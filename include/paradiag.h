@@ -129,6 +129,11 @@ int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_dev, void* st
  * y = A x with Dirichlet rows as identity.  x and y must not alias.             */
 int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 
+/* Slab-mode version of pd_matvec: x, y are this rank's (2, n_r, N_t) blocks; halo_lo / halo_hi are the
+ * (2, N_t) node rows just below / above the slab (from the neighbouring ranks; NULL at the domain ends). */
+int pd_matvec_slab(pd_handle* h, const void* x_dev, const void* halo_lo_dev, const void* halo_hi_dev,
+                   void* y_dev, void* stream);
+
 /* y = P x for the block-circulant matrix P that DiagFFTPC inverts (the operator above
  * with the time stencils of :121, :137 made periodic -- C1, C2 of mat_test.ipynb cells
  * 8-9 -- and the half weights :117, :143 and the :138 factor replaced by 1).  Lets a
@@ -155,6 +160,11 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
  * out[i] = sum_j conj(V[i*ld + j]) * w[j], i < nv  (PETSc VecMDot order).       */
 int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* w_dev,
             int64_t len, void* out_dev, void* stream);
+
+/* w += sign * sum_{i<nv} coef[i] V[i*ld + .] with device-resident coefficients (PETSc VecMAXPY);
+ * norm2_out_dev (optional, one complex) receives ||w_new||^2 of the local part.                     */
+int pd_maxpy(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* coef_dev, double sign,
+             void* w_dev, int64_t len, void* norm2_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
     h->n = cnt;
     h->m = cnt - 1 - (r == G - 1 ? 1 : 0);
     h->nloc = cnt;
+    h->node_begin = r * (ntot / G) + (r < ntot % G ? r : ntot % G);
   }
   if (h->kbegin < 0 || h->kbegin + h->kcount > cfg->N_t) {
     pd_set_error("pd_create: frequency shard [%d, %d) outside [0, %d)", h->kbegin, h->kbegin + h->kcount,
@@ -250,7 +251,21 @@ extern "C" int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* str
     pd_set_error("pd_matvec: invalid argument (x and y must be distinct device vectors)");
     return PD_ERR_INVALID;
   }
+  if (h->slab_count > 1) {
+    pd_set_error("pd_matvec: handle is in slab mode; use pd_matvec_slab");
+    return PD_ERR_INVALID;
+  }
   return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0);
+}
+
+extern "C" int pd_matvec_slab(pd_handle* h, const void* x_dev, const void* halo_lo_dev, const void* halo_hi_dev,
+                              void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev || x_dev == y_dev || h->slab_count <= 1) {
+    pd_set_error("pd_matvec_slab: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0, (const cplx*)halo_lo_dev,
+                          (const cplx*)halo_hi_dev);
 }
 
 extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {

@@ -73,6 +73,7 @@ struct pd_handle {
   int kbegin;
   int nloc;      // node lines per field transformed by this handle
   int slab_rank, slab_count;  // slab mode (x-slab sharding through the solve); count <= 1: off
+  int node_begin;             // global index of local node row 0 (0 unless slab mode)
   double dt, h, c;
   int num_sms;
   size_t ws_bytes;
@@ -119,5 +120,6 @@ int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr);
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st);
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st);
-int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant);
+int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
+                     const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st);

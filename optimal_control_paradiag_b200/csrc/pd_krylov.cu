@@ -16,7 +16,10 @@
 
 // --------------------------------------------------------------------- matvec
 struct OpParams {
-  int n, N_t;
+  int n, N_t;      // n: global node count
+  int nloc, j0;    // local rows and the global index of local row 0 (slab mode; else n, 0)
+  const cplx* halo_lo;  // [2][N_t] rows j0-1 of (u, p), from the left neighbour (slab mode)
+  const cplx* halo_hi;  // [2][N_t] rows j0+nloc
   double h, dt2h;  // dt^2 / 2
   double c;        // dt^2 / sqrt(gamma)
   double qlast;    // sqrt(gamma) if bug138 else 1
@@ -24,24 +27,29 @@ struct OpParams {
   int64_t plane;
 };
 
-__device__ __forceinline__ cplx ld_or_zero(const cplx* __restrict__ v, int j, int i, const OpParams& op) {
+// v: local plane of field f; j: GLOBAL node index
+__device__ __forceinline__ cplx ld_or_zero(const cplx* __restrict__ v, int f, int j, int i, const OpParams& op) {
   // Dirichlet columns are dropped: boundary-node values never enter interior rows
   if (j < 1 || j > op.n - 2) return cmake(0, 0);
   if (i < 0 || i >= op.N_t) {
     if (!op.circulant) return cmake(0, 0);
     i = i < 0 ? i + op.N_t : i - op.N_t;  // C1, C2 wrap around (mat_test.ipynb cells 8-9)
   }
-  return v[(int64_t)j * op.N_t + i];
+  const int jl = j - op.j0;
+  if (jl < 0) return op.halo_lo[(int64_t)f * op.N_t + i];
+  if (jl >= op.nloc) return op.halo_hi[(int64_t)f * op.N_t + i];
+  return v[(int64_t)jl * op.N_t + i];
 }
 
 __global__ void __launch_bounds__(256)
 pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
+  const int jl = blockIdx.y;
+  const int j = op.j0 + jl;  // global node
   if (i >= op.N_t) return;
   const cplx* u = x;
   const cplx* p = x + op.plane;
-  const int64_t o = (int64_t)j * op.N_t + i;
+  const int64_t o = (int64_t)jl * op.N_t + i;
   if (j == 0 || j == op.n - 1) {
     y[o] = u[o];
     y[op.plane + o] = p[o];
@@ -65,8 +73,8 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      uv[s][t] = ld_or_zero(u, j - 1 + s, i - t, op);
-      pv[s][t] = ld_or_zero(p, j - 1 + s, i + t, op);
+      uv[s][t] = ld_or_zero(u, 0, j - 1 + s, i - t, op);
+      pv[s][t] = ld_or_zero(p, 1, j - 1 + s, i + t, op);
     }
   cplx d2u[3], d2p[3], Ku0, Ku2, Kp0, Kp2;
 #pragma unroll
@@ -96,12 +104,18 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   y[op.plane + o] = yp;
 }
 
-int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant) {
+int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
+                     const cplx* halo_lo, const cplx* halo_hi) {
   OpParams op;
   op.circulant = circulant;
-  op.n = h->n; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
+  op.n = h->cfg.N_x + 1; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
+  op.nloc = h->n; op.j0 = h->node_begin; op.halo_lo = halo_lo; op.halo_hi = halo_hi;
   op.qlast = h->cfg.bug138 ? sqrt(h->cfg.gamma) : 1.0;
   op.plane = (int64_t)h->n * h->cfg.N_t;
+  if (h->slab_count > 1 && ((h->slab_rank > 0 && !halo_lo) || (h->slab_rank < h->slab_count - 1 && !halo_hi))) {
+    pd_set_error("matvec in slab mode needs the neighbour rows (halo_lo / halo_hi)");
+    return PD_ERR_INVALID;
+  }
   dim3 grid((op.N_t + 255) / 256, h->n);
   pd_matvec_kernel<<<grid, 256, 0, st>>>(x, y, op);
   PD_CHECK_LAUNCH();
@@ -111,7 +125,8 @@ int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int 
 
 // ------------------------------------------------------------------------ rhs
 struct RhsParams {
-  int n, N_t, N_x;
+  int n, N_t, N_x;  // n: global node count
+  int j0;           // global index of local row 0
   double h, dt, T, gamma;
   int64_t plane;
 };
@@ -119,9 +134,9 @@ struct RhsParams {
 __global__ void __launch_bounds__(256)
 pd_rhs_kernel(cplx* __restrict__ b, RhsParams rp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
+  const int j = rp.j0 + blockIdx.y;
   if (i >= rp.N_t) return;
-  const int64_t o = (int64_t)j * rp.N_t + i;
+  const int64_t o = (int64_t)blockIdx.y * rp.N_t + i;
   if (j == 0 || j == rp.n - 1) {
     b[o] = cmake(0, 0);
     b[rp.plane + o] = cmake(0, 0);
@@ -154,7 +169,7 @@ pd_rhs_kernel(cplx* __restrict__ b, RhsParams rp) {
 
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st) {
   RhsParams rp;
-  rp.n = h->n; rp.N_t = h->cfg.N_t; rp.N_x = h->cfg.N_x; rp.h = h->h; rp.dt = h->dt;
+  rp.n = h->cfg.N_x + 1; rp.j0 = h->node_begin; rp.N_t = h->cfg.N_t; rp.N_x = h->cfg.N_x; rp.h = h->h; rp.dt = h->dt;
   rp.T = h->cfg.T; rp.gamma = h->cfg.gamma; rp.plane = (int64_t)h->n * h->cfg.N_t;
   dim3 grid((rp.N_t + 255) / 256, h->n);
   pd_rhs_kernel<<<grid, 256, 0, st>>>(b, rp);
@@ -395,6 +410,19 @@ extern "C" int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, cons
   return mdot_list(h, vs.data(), nv, (const cplx*)w_dev, len, (cplx*)out_dev, (cudaStream_t)stream);
 }
 
+// w += sign * sum_i coef[i] V_i (coefficients on the device); norm2_out (optional) <- ||w_new||^2 (local)
+extern "C" int pd_maxpy(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* coef_dev, double sign,
+                        void* w_dev, int64_t len, void* norm2_out_dev, void* stream) {
+  if (!h || !V_dev || !w_dev || !coef_dev || nv < 1) {
+    pd_set_error("pd_maxpy: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  std::vector<const cplx*> vs(nv);
+  for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
+  return maxpy_list(h, vs.data(), nv, (const cplx*)coef_dev, sign, (cplx*)w_dev, len, (cplx*)norm2_out_dev,
+                    (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------- GMRES
 struct hcplx {
   double re, im;
@@ -498,7 +526,7 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     if (first) {
       if ((rc = pd_pc_apply(h, b, v0, st))) return rc;
     } else {
-      if ((rc = pd_matvec_launch(h, x, t, st, 0))) return rc;
+      if ((rc = pd_matvec_launch(h, x, t, st, 0, nullptr, nullptr))) return rc;
       pd_axpby_kernel<<<nb1, 256, 0, st>>>(1.0, b, -1.0, t, len);
       PD_CHECK_LAUNCH();
       h->launches++;
@@ -535,7 +563,7 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
         break;
       }
       cplx* w = kc->V[j + 1];
-      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0))) return rc;
+      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0, nullptr, nullptr))) return rc;
       if ((rc = pd_pc_apply(h, t, w, st))) return rc;
       // classical Gram-Schmidt: all inner products against the unmodified w first
       if ((rc = mdot_list(h, kc->V.data(), j + 1, w, len, hdev, st))) return rc;

@@ -25,6 +25,8 @@ are all-gathered, every rank solves the (G-1)-row separator system of each frequ
 and back-substitutes its slab (``pd_slab_finish``).  Communication drops from 2 x (G-1)/G x S/G bytes
 per rank (NVLink-bound) to 96 N_t bytes per rank; no transposes, no pack/unpack.
 """
+import math
+
 import numpy as np
 
 
@@ -169,6 +171,116 @@ class DistributedDiagFFTPC:
         self.backend.slab_finish(self.w_time, self.gathered)                               # :445-540
         self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * self.n_r, False)     # :547-548
         return y_local
+
+    # ------------------------------------------------------------------ distributed Krylov solve
+    def build_rhs(self):
+        """This rank's block of the manufactured right-hand side (Build_f/g/IC, :48-83)."""
+        b = self.torch.empty(self.local_size, dtype=self.torch.complex128, device=self.device)
+        return self.backend.build_rhs(b)
+
+    def matvec(self, x_local, y_local=None):
+        """y = A x (Build_L, :86-179) on node-slab distributed vectors: one small all-gather brings the
+        neighbours' edge rows (2 x 2 x N_t complex per rank), then the local stencil kernel runs."""
+        t = self.torch
+        if self.mode != "slab":
+            raise NotImplementedError("the distributed matvec / GMRES use the slab decomposition")
+        if y_local is None:
+            y_local = t.empty_like(x_local)
+        X = x_local.view(2, self.n_r, self.N_t)
+        edges = t.stack([X[:, 0, :], X[:, -1, :]]).contiguous()            # (edge, field, N_t)
+        alle = t.empty((self.world,) + tuple(edges.shape), dtype=edges.dtype, device=self.device)
+        self.dist.all_gather_into_tensor(t.view_as_real(alle).reshape(-1), t.view_as_real(edges).reshape(-1),
+                                         group=self.group)
+        lo = alle[self.rank - 1, 1].reshape(-1) if self.rank > 0 else None          # last row of the left slab
+        hi = alle[self.rank + 1, 0].reshape(-1) if self.rank < self.world - 1 else None
+        self._halo_keepalive = alle
+        return self.backend.matvec_slab(x_local.reshape(-1), lo, hi, y_local.reshape(-1))
+
+    def _allreduce(self, v):
+        self.dist.all_reduce(self.torch.view_as_real(v), group=self.group)
+        return v
+
+    def gmres(self, b_local, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
+        """Left-preconditioned GMRES with the options of Control_Wave_PC.py:347-359 (classical
+        Gram-Schmidt, zero initial guess, preconditioned-residual test) on slab-distributed vectors.
+        Same arithmetic as pd_gmres; inner products are local pd_mdot + one all-reduce.
+        Returns (x_local, iterations, history, reason)."""
+        t, be = self.torch, self.backend
+        c128, ln = t.complex128, self.local_size
+        x = t.zeros(ln, dtype=c128, device=self.device)
+        tmp = t.empty(ln, dtype=c128, device=self.device)
+        cap = min(restart + 1, 8)
+        V = t.empty((cap, ln), dtype=c128, device=self.device)
+        hist, its, reason, first, converged = [], 0, "DIVERGED_ITS", True, False
+        beta0 = target = 0.0
+        hbuf = t.zeros(restart + 2, dtype=c128, device=self.device)
+        while not converged and (its < max_it or first):
+            if first:
+                self.apply(b_local, V[0])
+            else:
+                self.matvec(x, tmp)
+                tmp.mul_(-1).add_(b_local)
+                self.apply(tmp, V[0])
+            beta = math.sqrt(self._allreduce(be.mdot(V[:1], V[0]))[0].real.item())
+            if first:
+                beta0, first = beta, False
+                target = max(rtol * beta0, atol)
+                hist.append(beta0)
+                if beta0 <= target or beta0 == 0.0:
+                    converged, reason = True, ("CONVERGED_ATOL" if beta0 <= atol else "CONVERGED_RTOL")
+                    break
+                if max_it == 0:
+                    break
+            V[0].mul_(1.0 / beta)
+            m = restart
+            H = np.zeros((m + 1, m), dtype=complex)
+            cs, sn, g = np.zeros(m, complex), np.zeros(m, complex), np.zeros(m + 1, complex)
+            g[0] = beta
+            jdone = 0
+            for j in range(m):
+                if j + 1 >= V.shape[0]:                         # grow the basis storage geometrically
+                    Vn = t.empty((min(restart + 1, 2 * V.shape[0]), ln), dtype=c128, device=self.device)
+                    Vn[: V.shape[0]] = V
+                    V = Vn
+                w = V[j + 1]
+                self.matvec(V[j], tmp)
+                self.apply(tmp, w)
+                hd = self._allreduce(be.mdot(V[: j + 1], w))                 # classical Gram-Schmidt
+                hbuf[: j + 1] = hd
+                be.maxpy(V[: j + 1], hbuf[: j + 1], -1.0, w, hbuf[j + 1: j + 2])
+                self._allreduce(hbuf[j + 1: j + 2])
+                hh = hbuf[: j + 2].cpu().numpy()
+                H[: j + 1, j] = hh[: j + 1]
+                hn = math.sqrt(max(hh[j + 1].real, 0.0))
+                H[j + 1, j] = hn
+                for i in range(j):
+                    a_, b_ = H[i, j], H[i + 1, j]
+                    H[i, j] = np.conj(cs[i]) * a_ + np.conj(sn[i]) * b_
+                    H[i + 1, j] = cs[i] * b_ - sn[i] * a_
+                a_, b_ = H[j, j], H[j + 1, j]
+                den = math.sqrt(abs(a_) ** 2 + abs(b_) ** 2)
+                cs[j], sn[j] = (1.0, 0.0) if den == 0 else (a_ / den, b_ / den)
+                H[j, j] = np.conj(cs[j]) * a_ + np.conj(sn[j]) * b_
+                H[j + 1, j] = 0
+                g[j + 1] = -sn[j] * g[j]
+                g[j] = np.conj(cs[j]) * g[j]
+                its += 1
+                jdone = j + 1
+                rn = abs(g[j + 1])
+                hist.append(rn)
+                if rn <= target:
+                    converged, reason = True, ("CONVERGED_RTOL" if rn > atol else "CONVERGED_ATOL")
+                    break
+                if its >= max_it or hn == 0.0:
+                    break
+                w.mul_(1.0 / hn)
+            if jdone:
+                yk = np.linalg.solve(np.triu(H[:jdone, :jdone]), g[:jdone])
+                coef = t.tensor(yk, dtype=c128, device=self.device)
+                be.maxpy(V[:jdone], coef, 1.0, x)
+            if its >= max_it:
+                break
+        return x, its, hist, reason
 
     def gather_to_global(self, y_local):
         """All ranks receive the full (2, n, N_t) vector (tests only)."""

@@ -147,6 +147,23 @@ class ParaDiagHandle:
                                  self._stream()))
         return y
 
+    def matvec_slab(self, x, halo_lo, halo_hi, y):
+        """Slab-mode matvec (pd_matvec_slab): halos are (2, N_t) tensors or None at the domain ends."""
+        lo = self._ptr(halo_lo, 2 * self.N_t, "halo_lo") if halo_lo is not None else None
+        hi = self._ptr(halo_hi, 2 * self.N_t, "halo_hi") if halo_hi is not None else None
+        check(self.lib.pd_matvec_slab(self._h, self._ptr(x, None, "x"), lo, hi, self._ptr(y, None, "y"),
+                                      self._stream()))
+        return y
+
+    def maxpy(self, V, coef, sign, w, norm2_out=None):
+        """w += sign * sum_i coef[i] V[i] (pd_maxpy); V is (nv, len), coef a device tensor."""
+        nv, ln = V.shape
+        no = self._ptr(norm2_out, 1, "norm2_out") if norm2_out is not None else None
+        check(self.lib.pd_maxpy(self._h, self._ptr(V, None, "V"), int(V.stride(0)), int(nv),
+                                self._ptr(coef, None, "coef"), float(sign), self._ptr(w, ln, "w"), int(ln), no,
+                                self._stream()))
+        return w
+
     def pc_matvec(self, x, y=None):
         """y = P x, the block-circulant matrix whose inverse ``pc_apply`` applies."""
         if y is None:
@@ -158,7 +175,7 @@ class ParaDiagHandle:
     def build_rhs(self, b=None):
         if b is None:
             b = self.empty()
-        check(self.lib.pd_build_rhs(self._h, self._ptr(b, self.size, "b"), self._stream()))
+        check(self.lib.pd_build_rhs(self._h, self._ptr(b, None, "b"), self._stream()))
         return b
 
     def gmres(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):

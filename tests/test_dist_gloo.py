@@ -54,6 +54,43 @@ class OracleStageBackend:
             o[0, k], o[1, k], o[2, k], o[3, k] = yP[0], yM[0], yP[-1], yM[-1]
             o[4, k], o[5, k] = (rP[0, k], rM[0, k]) if self.r > 0 else (0, 0)
 
+    # ---- Krylov pieces (numpy), same contracts as ParaDiagHandle
+    def _op(self):
+        if not hasattr(self, "_aao"):
+            from oracle.operator import AllAtOnce
+            self._aao = AllAtOnce(self.pc.N_x, self.N_t, self.pc.T, self.pc.gamma)
+            _, self._offs = slab_bounds(self.n, self.G)
+        return self._aao
+
+    def build_rhs(self, b):
+        op = self._op()
+        j0 = self._offs[self.r]
+        b.copy_(torch.from_numpy(op.rhs().reshape(2, self.n, self.N_t)[:, j0:j0 + self.n_r].reshape(-1) + 0j))
+        return b
+
+    def matvec_slab(self, x, lo, hi, y):
+        op = self._op()
+        j0 = self._offs[self.r]
+        full = np.zeros((2, self.n, self.N_t), complex)      # only the slab and its halo rows matter
+        full[:, j0:j0 + self.n_r] = x.numpy().reshape(2, self.n_r, self.N_t)
+        if lo is not None:
+            full[:, j0 - 1] = lo.numpy().reshape(2, self.N_t)
+        if hi is not None:
+            full[:, j0 + self.n_r] = hi.numpy().reshape(2, self.N_t)
+        out = op.matvec(full.reshape(-1)).reshape(2, self.n, self.N_t)[:, j0:j0 + self.n_r]
+        y.copy_(torch.from_numpy(np.ascontiguousarray(out).reshape(-1)))
+        return y
+
+    def mdot(self, V, w):
+        return torch.from_numpy(V.numpy().conj() @ w.numpy())
+
+    def maxpy(self, V, coef, sign, w, norm2_out=None):
+        wn = w.numpy()
+        wn += sign * (coef.numpy()[: V.shape[0]] @ V.numpy())
+        if norm2_out is not None:
+            norm2_out[0] = float(np.vdot(wn, wn).real)
+        return w
+
     def slab_finish(self, w, gathered):
         pc, G, r = self.pc, self.G, self.r
         W = w.numpy().reshape(2, self.n_r, self.N_t)
@@ -158,6 +195,40 @@ def test_slab_mode_apply_matches_single_process_oracle(world, N_x, N_t):
     for r in range(world):
         ok, err = ret[r]
         assert ok, (r, err)
+
+
+def _gmres_worker(rank, world, port, N_x, N_t, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.gmres import gmres as ogmres
+        from oracle.operator import AllAtOnce
+        from oracle.pc_fast import DiagFFTPCFast
+        factory = lambda **kw: OracleStageBackend(N_x, N_t, 2.0, 1.0, **kw)
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=1.0, backend_factory=factory, mode="slab")
+        b = dpc.build_rhs()
+        x, its, hist, reason = dpc.gmres(b, rtol=1e-7)
+        xg = dpc.gather_to_global(x).numpy()
+        op = AllAtOnce(N_x, N_t)
+        xo, its_o, hist_o, _ = ogmres(op.matvec, DiagFFTPCFast(N_x, N_t).apply, op.rhs() + 0j, rtol=1e-7)
+        # distributed matvec against the global one
+        rng = np.random.default_rng(1)
+        vg = rng.standard_normal(2 * (N_x + 1) * N_t) + 0j
+        yl = dpc.matvec(dpc.scatter_from_global(torch.from_numpy(vg)))
+        mv_err = np.linalg.norm(dpc.gather_to_global(yl).numpy() - op.matvec(vg)) / np.linalg.norm(op.matvec(vg))
+        ret[rank] = (its, its_o, reason, float(np.linalg.norm(xg - xo) / np.linalg.norm(xo)), float(mv_err))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_gmres_matches_oracle():
+    world, N_x, N_t = 2, 20, 12
+    ret = mp.Manager().dict()
+    mp.spawn(_gmres_worker, args=(world, _free_port(), N_x, N_t, ret), nprocs=world, join=True)
+    for r in range(world):
+        its, its_o, reason, err, mv_err = ret[r]
+        assert reason == "CONVERGED_RTOL" and abs(its - its_o) <= 1 and err < 1e-6 and mv_err < 1e-13, ret[r]
 
 
 def test_slab_bounds():

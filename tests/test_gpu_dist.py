@@ -53,3 +53,41 @@ def test_sharded_apply_equals_single_gpu_apply(N_x, N_t, mode):
     for r in range(world):
         # all-to-all: same kernels on the same data; slab: a different elimination order
         assert ret[r] < (1e-13 if mode == "alltoall" else 1e-10), (r, ret[r])
+
+
+def _gmres_worker(rank, world, port, N_x, N_t, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from optimal_control_paradiag_b200 import ParaDiagHandle
+        from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
+        dpc = DistributedDiagFFTPC(N_x, N_t, device=rank, mode="slab")
+        b = dpc.build_rhs()
+        x, its, hist, reason = dpc.gmres(b, rtol=1e-7)
+        xg = dpc.gather_to_global(x)
+        with ParaDiagHandle(N_x, N_t, device=rank) as h:
+            bg = h.build_rhs()
+            assert float(torch.linalg.norm(dpc.gather_to_global(b) - bg) / torch.linalg.norm(bg)) < 1e-14
+            v = torch.randn(h.size, dtype=torch.float64, device=f"cuda:{rank}",
+                            generator=torch.Generator(device=f"cuda:{rank}").manual_seed(5)).to(torch.complex128)
+            mv = dpc.gather_to_global(dpc.matvec(dpc.scatter_from_global(v)))
+            mv_err = float(torch.linalg.norm(mv - h.matvec(v)) / torch.linalg.norm(mv))
+            xs, its_s, hist_s, reason_s = h.gmres(bg, rtol=1e-7)
+            err = float(torch.linalg.norm(xg - xs) / torch.linalg.norm(xs))
+        ret[rank] = (its, its_s, reason, err, mv_err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N_x,N_t", [(80, 81), (1024, 256)])
+def test_distributed_gmres_equals_single_gpu(N_x, N_t):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ret = mp.Manager().dict()
+    mp.spawn(_gmres_worker, args=(world, _free_port(), N_x, N_t, ret), nprocs=world, join=True)
+    for r in range(world):
+        its, its_s, reason, err, mv_err = ret[r]
+        assert reason == "CONVERGED_RTOL" and abs(its - its_s) <= 1 and err < 1e-6 and mv_err == 0.0, ret[r]
