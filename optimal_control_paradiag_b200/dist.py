@@ -209,19 +209,36 @@ class DistributedDiagFFTPC:
         c128, ln = t.complex128, self.local_size
         x = t.zeros(ln, dtype=c128, device=self.device)
         tmp = t.empty(ln, dtype=c128, device=self.device)
-        cap = min(restart + 1, 8)
-        V = t.empty((cap, ln), dtype=c128, device=self.device)
+        # Krylov basis in blocks of BS vectors, allocated as the iteration proceeds (a cfg3 vector is
+        # 2.1 GB / G per rank: the restart length of 300 cannot be pre-allocated)
+        BS = 8
+        blocks = [t.empty((BS, ln), dtype=c128, device=self.device)]
+
+        def vec(j):
+            while j // BS >= len(blocks):
+                blocks.append(t.empty((BS, ln), dtype=c128, device=self.device))
+            return blocks[j // BS][j % BS]
+
+        def mdot_all(nv, w):
+            return t.cat([be.mdot(blocks[b][: min(BS, nv - b * BS)], w) for b in range((nv + BS - 1) // BS)])
+
+        def maxpy_all(nv, coef, sign, w, norm2_out=None):
+            nb = (nv + BS - 1) // BS
+            for b in range(nb):
+                cnt = min(BS, nv - b * BS)
+                be.maxpy(blocks[b][:cnt], coef[b * BS: b * BS + cnt], sign, w, norm2_out if b == nb - 1 else None)
         hist, its, reason, first, converged = [], 0, "DIVERGED_ITS", True, False
         beta0 = target = 0.0
         hbuf = t.zeros(restart + 2, dtype=c128, device=self.device)
         while not converged and (its < max_it or first):
+            v0 = vec(0)
             if first:
-                self.apply(b_local, V[0])
+                self.apply(b_local, v0)
             else:
                 self.matvec(x, tmp)
                 tmp.mul_(-1).add_(b_local)
-                self.apply(tmp, V[0])
-            beta = math.sqrt(self._allreduce(be.mdot(V[:1], V[0]))[0].real.item())
+                self.apply(tmp, v0)
+            beta = math.sqrt(self._allreduce(mdot_all(1, v0))[0].real.item())
             if first:
                 beta0, first = beta, False
                 target = max(rtol * beta0, atol)
@@ -231,23 +248,19 @@ class DistributedDiagFFTPC:
                     break
                 if max_it == 0:
                     break
-            V[0].mul_(1.0 / beta)
+            v0.mul_(1.0 / beta)
             m = restart
             H = np.zeros((m + 1, m), dtype=complex)
             cs, sn, g = np.zeros(m, complex), np.zeros(m, complex), np.zeros(m + 1, complex)
             g[0] = beta
             jdone = 0
             for j in range(m):
-                if j + 1 >= V.shape[0]:                         # grow the basis storage geometrically
-                    Vn = t.empty((min(restart + 1, 2 * V.shape[0]), ln), dtype=c128, device=self.device)
-                    Vn[: V.shape[0]] = V
-                    V = Vn
-                w = V[j + 1]
-                self.matvec(V[j], tmp)
+                w = vec(j + 1)
+                self.matvec(vec(j), tmp)
                 self.apply(tmp, w)
-                hd = self._allreduce(be.mdot(V[: j + 1], w))                 # classical Gram-Schmidt
+                hd = self._allreduce(mdot_all(j + 1, w))                     # classical Gram-Schmidt
                 hbuf[: j + 1] = hd
-                be.maxpy(V[: j + 1], hbuf[: j + 1], -1.0, w, hbuf[j + 1: j + 2])
+                maxpy_all(j + 1, hbuf, -1.0, w, hbuf[j + 1: j + 2])
                 self._allreduce(hbuf[j + 1: j + 2])
                 hh = hbuf[: j + 2].cpu().numpy()
                 H[: j + 1, j] = hh[: j + 1]
@@ -277,7 +290,7 @@ class DistributedDiagFFTPC:
             if jdone:
                 yk = np.linalg.solve(np.triu(H[:jdone, :jdone]), g[:jdone])
                 coef = t.tensor(yk, dtype=c128, device=self.device)
-                be.maxpy(V[:jdone], coef, 1.0, x)
+                maxpy_all(jdone, coef, 1.0, x)
             if its >= max_it:
                 break
         return x, its, hist, reason
