@@ -91,6 +91,18 @@ int64_t pd_launch_count(const pd_handle* h);
 int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 /* Same with host buffers (PETSc Vec arrays): H2D, apply, D2H, synchronises.     */
 int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host);
+/* Real-input fast path.  The vectors GMRES feeds the PC in this (real) problem are real: x_dev and
+ * y_dev are float64 arrays in the same (field, node, time) layout, 2 n N_t doubles.  Their time spectra
+ * are Hermitian, so only the frequencies 0..N_t/2 are transformed and solved: half the bytes of
+ * pd_pc_apply in every stage.  Result = real part of pd_pc_apply on (x + 0i) (the imaginary part of that
+ * is rounding noise).  Needs a power-of-two N_t in [128, 16384]; PD_ERR_UNSUPPORTED otherwise.        */
+int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+/* The stages of the real-input path: real lines of N_t samples <-> half spectra of N_t/2 + 1 complex
+ * numbers (to_freq != 0: scipy ifft restricted to k <= N_t/2; to_freq == 0: scipy fft of the Hermitian
+ * extension, real output), and the per-frequency stage on w = (2, n, Kp), in place; rows of a half
+ * spectrum are padded to Kp = (N_t/2 + 1 rounded up to a multiple of 8) complex numbers.            */
+int pd_stage_rfft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int to_freq, void* stream);
+int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream);
 /* One apply with CUDA events recorded on `stream` between its kernels; ms[0..4] receive
  * the device durations (milliseconds) of {inverse FFT, solve pass A, interface PCR, solve
  * pass B, forward FFT}.  Synchronises the stream.  Measurement aid for bench.py.           */

@@ -43,6 +43,9 @@ SYMBOLS = {
     "pd_launch_count": (_I64, [_VP]),
     "pd_pc_apply": (_I, [_VP, _VP, _VP, _VP]),
     "pd_pc_apply_host": (_I, [_VP, _VP, _VP]),
+    "pd_pc_apply_real": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_stage_rfft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
+    "pd_stage_solve_half": (_I, [_VP, _VP, _VP]),
     "pd_pc_apply_profile": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_float), _I]),
     "pd_pc_apply_transpose": (_I, [_VP, _VP, _VP, _VP]),
     "pd_stage_fft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),

@@ -220,6 +220,47 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
   return rc;
 }
 
+extern "C" int pd_stage_rfft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int to_freq,
+                             void* stream) {
+  if (!h || !in_dev || !out_dev || nlines < 0) {
+    pd_set_error("pd_stage_rfft: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_rfft_launch(h, in_dev, out_dev, nlines, to_freq, (cudaStream_t)stream);
+}
+
+extern "C" int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream) {
+  if (!h || !w_dev || h->kcount != h->cfg.N_t || h->slab_count > 1) {
+    pd_set_error("pd_stage_solve_half: invalid argument or sharded handle");
+    return PD_ERR_INVALID;
+  }
+  return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream, nullptr, 1);
+}
+
+extern "C" int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev) {
+    pd_set_error("pd_pc_apply_real: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
+    pd_set_error("pd_pc_apply_real: handle is sharded; the real-input path is single-GPU");
+    return PD_ERR_INVALID;
+  }
+  if (!pd_rfft_supported(h)) {
+    pd_set_error("pd_pc_apply_real: needs a power-of-two N_t in [128, 16384] (got %d); use pd_pc_apply", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_work(h);
+  if (rc) return rc;
+  const int64_t nlines = 2 * (int64_t)h->n;
+  // real lines -> half spectra (k = 0..N_t/2), the same per-frequency stage on half as many columns, back
+  if ((rc = pd_rfft_launch(h, x_dev, h->work, nlines, 1, st))) return rc;
+  if ((rc = pd_solve_launch(h, h->work, st, nullptr, 1))) return rc;
+  if ((rc = pd_rfft_launch(h, h->work, y_dev, nlines, 0, st))) return rc;
+  return PD_OK;
+}
+
 extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {
   pd_set_error("applyTranspose is not implemented (the upstream PC raises NotImplementedError)");
   return PD_ERR_UNSUPPORTED;

@@ -339,6 +339,114 @@ pd_fft_16k_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t n
   }
 }
 
+// ------------------------------------------------------------ real-input fast path
+// The Krylov vectors of this (real) optimal-control problem are real, so their time spectra are
+// Hermitian and the frequencies k = 0..N_t/2 suffice: half the bytes in every stage.  A real line of
+// N = 2M samples is read as M complex numbers z[n] = x[2n] + i x[2n+1]; with Z = FFT_M(z) and
+//     G(A)[k] = (A[k] + conj A[M-k])/2 - (i/2) W_N^k (A[k] - conj A[M-k])           (indices mod M)
+//   TO_FREQ  : x-hat[k] = conj(G(Z)[k]) / N for k = 0..M          (= scipy ifft(x)[k], :500-501)
+//   !TO_FREQ : y = fft of the Hermitian extension of Y[0..M]: F = FFT_M(G(Y)[0..M-1]),
+//              y[2n] + i y[2n+1] = 2 conj(F[n])                    (= scipy fft, :547-548, real part)
+// Both directions reuse the M-point register pipeline above plus one extra shared-memory exchange.
+template <int R0, int R1, int R2, int R3, bool TO_FREQ>
+__global__ void __launch_bounds__(512)
+pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nlines,
+               const cplx* __restrict__ twN, const cplx* __restrict__ twM) {
+  constexpr int M = R0 * R1 * R2 * R3;  // complex length = N_t / 2
+  constexpr int T = M / 16;
+  constexpr int KP = (M + 1 + 7) & ~7;   // row stride of a half spectrum: M + 1 rounded up to 128 bytes
+  constexpr int NL = (R3 > 1) ? R3 : (R2 > 1 ? R2 : R1);  // radix of the last pass
+  constexpr int NsL = M / NL;
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  const int lpb = blockDim.x / T;
+  const int lane_line = threadIdx.x / T;
+  const int t = threadIdx.x - lane_line * T;
+  cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw) + (size_t)lane_line * (M + M / 16 + 16);
+  const double invN = 1.0 / (2.0 * M);
+  for (int64_t line0 = (int64_t)blockIdx.x * lpb; line0 < nlines; line0 += (int64_t)gridDim.x * lpb) {
+    const int64_t line = line0 + lane_line;
+    const int64_t ln = line < nlines ? line : nlines - 1;
+    const bool live = line < nlines;
+    cplx io[16];
+    if (TO_FREQ) {
+      const cplx* gsrc = reinterpret_cast<const cplx*>(in_) + ln * M;       // N doubles = M complex
+      cplx* gdst = reinterpret_cast<cplx*>(out_) + ln * KP;
+      // M-point transform, last pass kept in registers
+      if (R1 == 1) {
+        pow2_pass<R0, false, true, true, false, true>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live, io);
+      } else {
+        pow2_pass<R0, false, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live);
+        if (R2 == 1) {
+          pow2_pass<(R1 > 1 ? R1 : 2), false, false, true, false, true>(gsrc, gdst, sm, twM, M, R0, t, T, 1.0, live, io);
+        } else {
+          pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0, t, T, 1.0, live);
+          if (R3 == 1) {
+            pow2_pass<(R2 > 1 ? R2 : 2), false, false, true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 1.0, live, io);
+          } else {
+            pow2_pass<(R2 > 1 ? R2 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 1.0, live);
+            pow2_pass<(R3 > 1 ? R3 : 2), false, false, true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1 * R2, t, T, 1.0, live, io);
+          }
+        }
+      }
+      __syncthreads();
+      // io[u*NL + r] <-> Z[(t + u T) + r NsL]
+#pragma unroll
+      for (int u = 0; u < 16 / NL; ++u)
+#pragma unroll
+        for (int r = 0; r < NL; ++r) sm[pad16(t + u * T + r * NsL)] = io[u * NL + r];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int k = t + T * q;
+        const cplx a = sm[pad16(k)], b = cconj(sm[pad16((M - k) & (M - 1))]);
+        const cplx s2 = cadd(a, b), d2 = csub(a, b);
+        const cplx wd = cmul(twN[k], d2);
+        // G = s2/2 - (i/2) wd ; output conj(G)/N
+        const cplx G = cmake(0.5 * (s2.x + wd.y), 0.5 * (s2.y - wd.x));
+        if (live) gdst[k] = cmake(G.x * invN, -G.y * invN);
+        if (k == 0 && live) {
+          gdst[M] = cmake((a.x - a.y) * invN, 0.0);   // k = M: Re Z0 - Im Z0
+          for (int kk = M + 1; kk < KP; ++kk) gdst[kk] = cmake(0.0, 0.0);  // padding columns
+        }
+      }
+      __syncthreads();
+    } else {
+      const cplx* gsrc = reinterpret_cast<const cplx*>(in_) + ln * KP;
+      cplx* gdst = reinterpret_cast<cplx*>(out_) + ln * M;
+      // stage the half spectrum Y[0..M] in shared memory
+      for (int k = t; k <= M; k += T) sm[pad16(k)] = gsrc[k];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int k = t + T * q;                                           // first-pass input order
+        const cplx a = sm[pad16(k)], b = cconj(sm[pad16(M - k)]);
+        const cplx s2 = cadd(a, b), d2 = csub(a, b);
+        const cplx wd = cmul(twN[k], d2);
+        io[q] = cmake(0.5 * (s2.x + wd.y), 0.5 * (s2.y - wd.x));
+      }
+      __syncthreads();
+      // F = FFT_M(io); stored as 2 conj(F): the real samples y[2n], y[2n+1]
+      if (R1 == 1) {
+        pow2_pass<R0, true, true, true, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 2.0, live, io);
+      } else {
+        pow2_pass<R0, false, true, false, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 2.0, live, io);
+        if (R2 == 1) {
+          pow2_pass<(R1 > 1 ? R1 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0, t, T, 2.0, live);
+        } else {
+          pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0, t, T, 2.0, live);
+          if (R3 == 1) {
+            pow2_pass<(R2 > 1 ? R2 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 2.0, live);
+          } else {
+            pow2_pass<(R2 > 1 ? R2 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 2.0, live);
+            pow2_pass<(R3 > 1 ? R3 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1 * R2, t, T, 2.0, live);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // --------------------------------------------------------------- host side
 static void factorize(int N, PassList& pl) {
   pl.n = 0;
@@ -360,13 +468,18 @@ static void factorize(int N, PassList& pl) {
 
 static bool is_pow2(int N) { return N > 0 && (N & (N - 1)) == 0; }
 
+bool pd_rfft_supported(const pd_handle* h) {
+  const int N = h->cfg.N_t;
+  return is_pow2(N) && N >= 128 && N <= 16384 && h->twiddle_half != nullptr;
+}
+
 int pd_fft_plan(pd_handle* h) {
   const int N = h->cfg.N_t;
   PD_CUDA(cudaMalloc(&h->twiddle, sizeof(cplx) * (size_t)N));
   h->ws_bytes += sizeof(cplx) * (size_t)N;
   pd_twiddle_kernel<<<(N + 255) / 256, 256>>>(h->twiddle, N);
   PD_CHECK_LAUNCH();
-  if (N == PD_BIGN) {  // the two half transforms of the 2-CTA kernel use the N/2 table
+  if (is_pow2(N) && N >= 128) {  // N/2 table: real-input fast path and the 2-CTA kernel's half transforms
     PD_CUDA(cudaMalloc(&h->twiddle_half, sizeof(cplx) * (size_t)(N / 2)));
     h->ws_bytes += sizeof(cplx) * (size_t)(N / 2);
     pd_twiddle_kernel<<<(N / 2 + 255) / 256, 256>>>(h->twiddle_half, N / 2);
@@ -433,6 +546,50 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
+}
+
+template <int R0, int R1, int R2, int R3>
+static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st) {
+  constexpr int M = R0 * R1 * R2 * R3;
+  constexpr int T = M / 16;
+  int threads = T < 256 ? 256 : T;
+  int lpb = threads / T;
+  size_t smem = (size_t)lpb * (M + M / 16 + 16) * sizeof(cplx);
+  int64_t nblk = (nlines + lpb - 1) / lpb;
+  if (to_freq) {
+    auto k = pd_rfft_kernel<R0, R1, R2, R3, true>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
+  } else {
+    auto k = pd_rfft_kernel<R0, R1, R2, R3, false>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
+  }
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// real lines of N_t samples <-> half spectra of N_t/2 + 1 complex numbers (power-of-two N_t in [128, 16384])
+int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st) {
+  if (nlines <= 0) return PD_OK;
+  if (!pd_rfft_supported(h)) {
+    pd_set_error("the real-input path needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  switch (h->cfg.N_t / 2) {
+    case 64:   return launch_rfft<16, 4, 1, 1>(h, in, out, nlines, to_freq, st);
+    case 128:  return launch_rfft<16, 8, 1, 1>(h, in, out, nlines, to_freq, st);
+    case 256:  return launch_rfft<16, 16, 1, 1>(h, in, out, nlines, to_freq, st);
+    case 512:  return launch_rfft<16, 8, 4, 1>(h, in, out, nlines, to_freq, st);
+    case 1024: return launch_rfft<16, 16, 4, 1>(h, in, out, nlines, to_freq, st);
+    case 2048: return launch_rfft<16, 16, 8, 1>(h, in, out, nlines, to_freq, st);
+    case 4096: return launch_rfft<16, 16, 16, 1>(h, in, out, nlines, to_freq, st);
+    case 8192: return launch_rfft<16, 16, 8, 4>(h, in, out, nlines, to_freq, st);
+    default: break;
+  }
+  pd_set_error("pd_rfft_launch: unsupported N_t %d", h->cfg.N_t);
+  return PD_ERR_UNSUPPORTED;
 }
 
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,

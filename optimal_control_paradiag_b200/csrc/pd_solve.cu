@@ -857,16 +857,20 @@ static dim3 stream_grid(const pd_handle* h, int K, int nchunks) {
   return dim3(kblocks, ny);
 }
 
-static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl) {
+static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl, int half_spectrum = 0) {
   SolvePlan* pl = plan_of(h);
   memset(&sp, 0, sizeof(sp));
   sp.n = h->n; sp.m = h->m; sp.K = h->kcount; sp.kbegin = h->kbegin; sp.N_t = h->cfg.N_t;
+  if (half_spectrum) {  // real-input path: frequencies 0 .. N_t/2 in natural order
+    sp.K = (h->cfg.N_t / 2 + 1 + 7) & ~7;  // padded to 128-byte rows; the padding columns hold zeros
+    sp.kbegin = 0;
+  }
   sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
-  sp.plane = (int64_t)h->n * h->kcount;
+  sp.plane = (int64_t)h->n * sp.K;
   sp.nlev = pl->nlev;
   sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
   sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
-  sp.freq_perm = h->cfg.N_t == 16384;
+  sp.freq_perm = h->cfg.N_t == 16384 && !half_spectrum;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = pl->green; sl.zout = pl->zout;
@@ -984,9 +988,9 @@ int pd_solve_plan(pd_handle* h) {
   return PD_OK;
 }
 
-int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev) {
+int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int half_spectrum) {
   SolveParams sp; Levels lv; SlabPtrs sl;
-  fill_params(h, sp, lv, sl);
+  fill_params(h, sp, lv, sl, half_spectrum);
   const int top = sp.nlev;
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   if (top >= 1) {

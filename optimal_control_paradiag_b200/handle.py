@@ -92,6 +92,26 @@ class ParaDiagHandle:
                                    self._stream()))
         return y
 
+    def pc_apply_real(self, x, y=None):
+        """Real-input fast path (pd_pc_apply_real): x, y float64 CUDA tensors of 2 n N_t entries."""
+        torch = _torch()
+        if y is None:
+            y = torch.empty_like(x)
+        for name, v in (("x", x), ("y", y)):
+            if v.dtype != torch.float64 or not v.is_cuda or not v.is_contiguous() or v.numel() != self.size:
+                raise ValueError(f"{name}: need a contiguous float64 CUDA tensor with {self.size} entries")
+        check(self.lib.pd_pc_apply_real(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), self._stream()))
+        return y
+
+    def stage_rfft(self, src, dst, nlines, to_freq):
+        check(self.lib.pd_stage_rfft(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), int(nlines),
+                                     int(bool(to_freq)), self._stream()))
+        return dst
+
+    def stage_solve_half(self, w):
+        check(self.lib.pd_stage_solve_half(self._h, C.c_void_p(w.data_ptr()), self._stream()))
+        return w
+
     def pc_apply_profile(self, x, y):
         """One apply with per-kernel CUDA-event timing: dict of milliseconds."""
         ms = (C.c_float * 5)()

@@ -169,7 +169,11 @@ class DiagFFTPC(PCBase):
         if is_dev:
             if self.node_order is not None:
                 raise NotImplementedError("node_order is only supported on the host-Vec path")
-            self.handle.pc_apply(x.reshape(-1), y.reshape(-1))
+            if x.dtype == torch.float64:
+                # real vectors (what GMRES feeds the PC in this problem): half-spectrum fast path
+                self.handle.pc_apply_real(x.reshape(-1), y.reshape(-1))
+            else:
+                self.handle.pc_apply(x.reshape(-1), y.reshape(-1))
             return
         xa = _host_array(x, readonly=True)
         ya = _host_array(y, readonly=False)

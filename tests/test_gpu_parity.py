@@ -92,6 +92,32 @@ def test_pc_apply_matches_oracle(N_x, N_t, gamma):
         assert np.abs(yr.imag).max() <= 1e-11 * np.abs(yr.real).max()
 
 
+@pytest.mark.parametrize("N_x,N_t,gamma", [(16, 128, 1.0), (33, 256, 1e-2), (100, 512, 1.0), (64, 1024, 1e-4),
+                                           (20, 2048, 1.0), (17, 4096, 1.0), (9, 8192, 1.0), (8, 16384, 1.0),
+                                           (1024, 1024, 1.0)])
+def test_real_input_fast_path_matches_oracle(N_x, N_t, gamma):
+    # pd_pc_apply_real: half spectrum (k <= N_t/2), real vectors in and out
+    with ParaDiagHandle(N_x, N_t, gamma=gamma) as h:
+        x = np.random.default_rng(1).standard_normal(h.size)
+        ref = DiagFFTPCFast(N_x, N_t, 2.0, gamma).apply(x + 0j)
+        xt = torch.tensor(x, device=DEV)
+        y = h.pc_apply_real(xt).cpu().numpy()
+        assert float(np.linalg.norm(y - ref.real) / np.linalg.norm(ref)) < PC_TOL
+        yc = h.pc_apply(torch.tensor(x + 0j, device=DEV)).cpu().numpy()
+        assert float(np.linalg.norm(y - yc.real) / np.linalg.norm(yc)) < 1e-13     # same kernels, half the columns
+        assert np.abs(y.reshape(2, N_x + 1, N_t)[:, [0, -1], :]).max() == 0.0
+        h.pc_apply_real(xt, xt)                                                      # in place
+        assert np.array_equal(xt.cpu().numpy(), y)
+
+
+def test_real_input_fast_path_unsupported_sizes_fail_loudly():
+    from optimal_control_paradiag_b200 import ParaDiagError
+    with ParaDiagHandle(16, 81) as h:
+        x = torch.zeros(h.size, dtype=torch.float64, device=DEV)
+        with pytest.raises(ParaDiagError):
+            h.pc_apply_real(x)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "pc_apply_*.npz"))))
 def test_pc_apply_matches_golden(path):
     g = np.load(path)
