@@ -343,6 +343,33 @@ def run_ours(args):
                 line["gmres"] = {"seconds": time.perf_counter() - t1, "iterations": its, "reason": reason,
                                  "rtol": 1e-7, "rhs": "manufactured (Build_f/g/IC)"}
                 del b
+                # the same solve on float64 vectors (real problem): half-spectrum PC, half the BLAS-1 bytes
+                try:
+                    br = handle.build_rhs_real()
+                    handle.gmres_real(br, rtol=1e-7)
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                    _, its, hist, reason = handle.gmres_real(br, rtol=1e-7)
+                    torch.cuda.synchronize()
+                    line["gmres_real_vectors"] = {"seconds": time.perf_counter() - t1, "iterations": its,
+                                                  "reason": reason, "rtol": 1e-7}
+                    xr = torch.randn(handle.size, dtype=torch.float64, device=dev)
+                    yr = torch.empty_like(xr)
+                    for _ in range(3):
+                        handle.pc_apply_real(xr, yr)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(10):
+                        handle.pc_apply_real(xr, yr)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    line["real_input_apply"] = {"ms_per_step": e0.elapsed_time(e1) / 10,
+                                                "applies_per_sec": 1e4 / e0.elapsed_time(e1),
+                                                "note": "pd_pc_apply_real on float64 vectors (half spectrum)"}
+                    del br, xr, yr
+                except Exception as ex:  # unsupported N_t etc.
+                    line["gmres_real_vectors"] = {"error": str(ex)}
             except Exception as ex:  # pragma: no cover
                 line["gmres"] = {"error": str(ex)}
 

@@ -168,6 +168,14 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
              int restart, int max_it, int* its, double* hist, int* reason,
              void* stream);
 
+/* float64 variants for the real problem (vectors of 2 n N_t doubles, same layout): the matvec, the
+ * right-hand side and the whole GMRES solve with the half-spectrum preconditioner pd_pc_apply_real.
+ * Same iteration as pd_gmres at half the memory traffic.                                          */
+int pd_matvec_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+int pd_build_rhs_real(pd_handle* h, void* b_dev, void* stream);
+int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
+                  int max_it, int* its, double* hist, int* reason, void* stream);
+
 /* Batched reductions used by the multi-GPU Krylov loop (device results):
  * out[i] = sum_j conj(V[i*ld + j]) * w[j], i < nv  (PETSc VecMDot order).       */
 int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* w_dev,

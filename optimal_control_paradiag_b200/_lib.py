@@ -57,6 +57,9 @@ SYMBOLS = {
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),
     "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
+    "pd_matvec_real": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_build_rhs_real": (_I, [_VP, _VP, _VP]),
+    "pd_gmres_real": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
     "pd_mdot": (_I, [_VP, _VP, _I64, _I, _VP, _I64, _VP, _VP]),
     "pd_maxpy": (_I, [_VP, _VP, _I64, _I, _VP, _D, _VP, _I64, _VP, _VP]),
 }

@@ -317,6 +317,22 @@ extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* 
   return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 1);
 }
 
+extern "C" int pd_matvec_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev || x_dev == y_dev || h->slab_count > 1) {
+    pd_set_error("pd_matvec_real: invalid argument (distinct float64 device vectors, unsharded handle)");
+    return PD_ERR_INVALID;
+  }
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0, nullptr, nullptr, 1);
+}
+
+extern "C" int pd_build_rhs_real(pd_handle* h, void* b_dev, void* stream) {
+  if (!h || !b_dev) {
+    pd_set_error("pd_build_rhs_real: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_rhs_launch(h, (cplx*)b_dev, (cudaStream_t)stream, 1);
+}
+
 extern "C" int pd_build_rhs(pd_handle* h, void* b_dev, void* stream) {
   if (!h || !b_dev) {
     pd_set_error("pd_build_rhs: invalid argument");

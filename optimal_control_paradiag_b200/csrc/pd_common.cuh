@@ -104,6 +104,7 @@ struct pd_handle {
   // Krylov workspace (lazily allocated)
   cplx* kry_V;      // basis vectors, allocated in blocks
   int kry_cap;
+  int kry_real;     // 1 while a real-vector solve runs (reductions zero the pair-wise imaginary parts)
   cplx* kry_w;
   cplx* kry_t;
   cplx* kry_partial;
@@ -123,5 +124,5 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nu
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st);
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
-                     const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr);
-int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st);
+                     const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr, int real_vectors = 0);
+int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors = 0);

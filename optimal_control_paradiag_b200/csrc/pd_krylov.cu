@@ -27,28 +27,50 @@ struct OpParams {
   int64_t plane;
 };
 
+// scalar helpers so that the stencil kernels exist for complex128 and for float64 vectors
+__device__ __forceinline__ double vzero(double) { return 0.0; }
+__device__ __forceinline__ cplx vzero(cplx) { return cmake(0, 0); }
+__device__ __forceinline__ double vsub(double a, double b) { return a - b; }
+__device__ __forceinline__ cplx vsub(cplx a, cplx b) { return csub(a, b); }
+__device__ __forceinline__ double vadd(double a, double b) { return a + b; }
+__device__ __forceinline__ cplx vadd(cplx a, cplx b) { return cadd(a, b); }
+__device__ __forceinline__ double vscale(double a, double s) { return a * s; }
+__device__ __forceinline__ cplx vscale(cplx a, double s) { return cscale(a, s); }
+// w_off (a + c) + w_dia b
+__device__ __forceinline__ double vlin3(double a, double b, double c, double wo, double wd) { return wo * (a + c) + wd * b; }
+__device__ __forceinline__ cplx vlin3(cplx a, cplx b, cplx c, double wo, double wd) {
+  return cmake(wo * (a.x + c.x) + wd * b.x, wo * (a.y + c.y) + wd * b.y);
+}
+// a + s1 b - s2 c   (the state row)  /  a + s1 b + s2 c (the adjoint row, pass -s2)
+__device__ __forceinline__ double vcomb(double a, double s1, double b, double s2, double c) { return a + s1 * b - s2 * c; }
+__device__ __forceinline__ cplx vcomb(cplx a, double s1, cplx b, double s2, cplx c) {
+  return cmake(a.x + s1 * b.x - s2 * c.x, a.y + s1 * b.y - s2 * c.y);
+}
+
 // v: local plane of field f; j: GLOBAL node index
-__device__ __forceinline__ cplx ld_or_zero(const cplx* __restrict__ v, int f, int j, int i, const OpParams& op) {
+template <class T>
+__device__ __forceinline__ T ld_or_zero(const T* __restrict__ v, int f, int j, int i, const OpParams& op) {
   // Dirichlet columns are dropped: boundary-node values never enter interior rows
-  if (j < 1 || j > op.n - 2) return cmake(0, 0);
+  if (j < 1 || j > op.n - 2) return vzero(T());
   if (i < 0 || i >= op.N_t) {
-    if (!op.circulant) return cmake(0, 0);
+    if (!op.circulant) return vzero(T());
     i = i < 0 ? i + op.N_t : i - op.N_t;  // C1, C2 wrap around (mat_test.ipynb cells 8-9)
   }
   const int jl = j - op.j0;
-  if (jl < 0) return op.halo_lo[(int64_t)f * op.N_t + i];
-  if (jl >= op.nloc) return op.halo_hi[(int64_t)f * op.N_t + i];
+  if (jl < 0) return reinterpret_cast<const T*>(op.halo_lo)[(int64_t)f * op.N_t + i];
+  if (jl >= op.nloc) return reinterpret_cast<const T*>(op.halo_hi)[(int64_t)f * op.N_t + i];
   return v[(int64_t)jl * op.N_t + i];
 }
 
+template <class T>
 __global__ void __launch_bounds__(256)
-pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) {
+pd_matvec_kernel(const T* __restrict__ x, T* __restrict__ y, OpParams op) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int jl = blockIdx.y;
   const int j = op.j0 + jl;  // global node
   if (i >= op.N_t) return;
-  const cplx* u = x;
-  const cplx* p = x + op.plane;
+  const T* u = x;
+  const T* p = x + op.plane;
   const int64_t o = (int64_t)jl * op.N_t + i;
   if (j == 0 || j == op.n - 1) {
     y[o] = u[o];
@@ -56,7 +78,7 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
     return;
   }
   const double m_off = op.h / 6.0, m_dia = 2.0 * op.h / 3.0;
-  const double k_off = -1.0 / op.h, k_dia = 2.0 / op.h;
+  const double ih = 1.0 / op.h;
   const double d_i = (i == 0 && !op.circulant) ? 0.5 : 1.0;               // :117
   const double e_i = (i == op.N_t - 1 && !op.circulant) ? 0.5 : 1.0;      // :143
   const double q_i = (i == op.N_t - 1 && !op.circulant) ? op.qlast : 1.0; // :138
@@ -67,45 +89,36 @@ pd_matvec_kernel(const cplx* __restrict__ x, cplx* __restrict__ y, OpParams op) 
   // differences of neighbouring values -- exact in floating point (Sterbenz) -- before any scaling:
   //   time:   D2 v = (v_i - v_{i-1}) - (v_{i-1} - v_{i-2})        per node, then M in space
   //   space:  K v  = ((v_C - v_L) + (v_C - v_R)) / h               per time level, then summed
-  (void)k_dia;
-  cplx uv[3][3], pv[3][3];  // [node L,C,R][time level 0,1,2]: u at i-t, p at i+t
+  T uv[3][3], pv[3][3];  // [node L,C,R][time level 0,1,2]: u at i-t, p at i+t
 #pragma unroll
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      uv[s][t] = ld_or_zero(u, 0, j - 1 + s, i - t, op);
-      pv[s][t] = ld_or_zero(p, 1, j - 1 + s, i + t, op);
+      uv[s][t] = ld_or_zero<T>(u, 0, j - 1 + s, i - t, op);
+      pv[s][t] = ld_or_zero<T>(p, 1, j - 1 + s, i + t, op);
     }
-  cplx d2u[3], d2p[3], Ku0, Ku2, Kp0, Kp2;
+  T d2u[3], d2p[3];
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
-    d2u[s] = csub(csub(uv[s][0], uv[s][1]), csub(uv[s][1], uv[s][2]));
-    d2p[s] = csub(csub(pv[s][0], pv[s][1]), csub(pv[s][1], pv[s][2]));
+    d2u[s] = vsub(vsub(uv[s][0], uv[s][1]), vsub(uv[s][1], uv[s][2]));
+    d2p[s] = vsub(vsub(pv[s][0], pv[s][1]), vsub(pv[s][1], pv[s][2]));
   }
-  const double ih = -k_off;  // 1/h
-  Ku0 = cscale(cadd(csub(uv[1][0], uv[0][0]), csub(uv[1][0], uv[2][0])), ih);
-  Ku2 = cscale(cadd(csub(uv[1][2], uv[0][2]), csub(uv[1][2], uv[2][2])), ih);
-  Kp0 = cscale(cadd(csub(pv[1][0], pv[0][0]), csub(pv[1][0], pv[2][0])), ih);
-  Kp2 = cscale(cadd(csub(pv[1][2], pv[0][2]), csub(pv[1][2], pv[2][2])), ih);
-  const cplx Md2u = cmake(m_off * (d2u[0].x + d2u[2].x) + m_dia * d2u[1].x, m_off * (d2u[0].y + d2u[2].y) + m_dia * d2u[1].y);
-  const cplx Md2p = cmake(m_off * (d2p[0].x + d2p[2].x) + m_dia * d2p[1].x, m_off * (d2p[0].y + d2p[2].y) + m_dia * d2p[1].y);
-  const cplx Mu0 = cmake(m_off * (uv[0][0].x + uv[2][0].x) + m_dia * uv[1][0].x, m_off * (uv[0][0].y + uv[2][0].y) + m_dia * uv[1][0].y);
-  const cplx Mp0 = cmake(m_off * (pv[0][0].x + pv[2][0].x) + m_dia * pv[1][0].x, m_off * (pv[0][0].y + pv[2][0].y) + m_dia * pv[1][0].y);
+  const T Ku0 = vscale(vadd(vsub(uv[1][0], uv[0][0]), vsub(uv[1][0], uv[2][0])), ih);
+  const T Ku2 = vscale(vadd(vsub(uv[1][2], uv[0][2]), vsub(uv[1][2], uv[2][2])), ih);
+  const T Kp0 = vscale(vadd(vsub(pv[1][0], pv[0][0]), vsub(pv[1][0], pv[2][0])), ih);
+  const T Kp2 = vscale(vadd(vsub(pv[1][2], pv[0][2]), vsub(pv[1][2], pv[2][2])), ih);
+  const T Md2u = vlin3(d2u[0], d2u[1], d2u[2], m_off, m_dia);
+  const T Md2p = vlin3(d2p[0], d2p[1], d2p[2], m_off, m_dia);
+  const T Mu0 = vlin3(uv[0][0], uv[1][0], uv[2][0], m_off, m_dia);
+  const T Mp0 = vlin3(pv[0][0], pv[1][0], pv[2][0], m_off, m_dia);
   // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
-  cplx yu, yp;
-  const double ck = q_i * op.dt2h, cm = d_i * op.c;
-  yu.x = Md2u.x + ck * (Ku0.x + Ku2.x) - cm * Mp0.x;
-  yu.y = Md2u.y + ck * (Ku0.y + Ku2.y) - cm * Mp0.y;
+  y[o] = vcomb(Md2u, q_i * op.dt2h, vadd(Ku0, Ku2), d_i * op.c, Mp0);
   // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
-  const double ce = e_i * op.c;
-  yp.x = Md2p.x + op.dt2h * (Kp0.x + Kp2.x) + ce * Mu0.x;
-  yp.y = Md2p.y + op.dt2h * (Kp0.y + Kp2.y) + ce * Mu0.y;
-  y[o] = yu;
-  y[op.plane + o] = yp;
+  y[op.plane + o] = vcomb(Md2p, op.dt2h, vadd(Kp0, Kp2), -e_i * op.c, Mu0);
 }
 
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
-                     const cplx* halo_lo, const cplx* halo_hi) {
+                     const cplx* halo_lo, const cplx* halo_hi, int real_vectors) {
   OpParams op;
   op.circulant = circulant;
   op.n = h->cfg.N_x + 1; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
@@ -117,7 +130,10 @@ int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int 
     return PD_ERR_INVALID;
   }
   dim3 grid((op.N_t + 255) / 256, h->n);
-  pd_matvec_kernel<<<grid, 256, 0, st>>>(x, y, op);
+  if (real_vectors)
+    pd_matvec_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(x), reinterpret_cast<double*>(y), op);
+  else
+    pd_matvec_kernel<cplx><<<grid, 256, 0, st>>>(x, y, op);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -131,15 +147,19 @@ struct RhsParams {
   int64_t plane;
 };
 
+__device__ __forceinline__ void rhs_store(cplx* b, int64_t o, double v) { b[o] = cmake(v, 0.0); }
+__device__ __forceinline__ void rhs_store(double* b, int64_t o, double v) { b[o] = v; }
+
+template <class T>
 __global__ void __launch_bounds__(256)
-pd_rhs_kernel(cplx* __restrict__ b, RhsParams rp) {
+pd_rhs_kernel(T* __restrict__ b, RhsParams rp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = rp.j0 + blockIdx.y;
   if (i >= rp.N_t) return;
   const int64_t o = (int64_t)blockIdx.y * rp.N_t + i;
   if (j == 0 || j == rp.n - 1) {
-    b[o] = cmake(0, 0);
-    b[rp.plane + o] = cmake(0, 0);
+    rhs_store(b, o, 0.0);
+    rhs_store(b, rp.plane + o, 0.0);
     return;
   }
   // nodal sin(pi x) at j-1, j, j+1 (full vectors: boundary nodal values enter M f)
@@ -163,16 +183,19 @@ pd_rhs_kernel(cplx* __restrict__ b, RhsParams rp) {
   }
   double bp = dt2 * Ms * G;                               // :123, :164
   if (i == rp.N_t - 1) bp *= 0.5;                         // :144
-  b[o] = cmake(bu, 0.0);
-  b[rp.plane + o] = cmake(bp, 0.0);
+  rhs_store(b, o, bu);
+  rhs_store(b, rp.plane + o, bp);
 }
 
-int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st) {
+int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors) {
   RhsParams rp;
   rp.n = h->cfg.N_x + 1; rp.j0 = h->node_begin; rp.N_t = h->cfg.N_t; rp.N_x = h->cfg.N_x; rp.h = h->h; rp.dt = h->dt;
   rp.T = h->cfg.T; rp.gamma = h->cfg.gamma; rp.plane = (int64_t)h->n * h->cfg.N_t;
   dim3 grid((rp.N_t + 255) / 256, h->n);
-  pd_rhs_kernel<<<grid, 256, 0, st>>>(b, rp);
+  if (real_vectors)
+    pd_rhs_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double*>(b), rp);
+  else
+    pd_rhs_kernel<cplx><<<grid, 256, 0, st>>>(b, rp);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -226,7 +249,7 @@ pd_mdot_kernel(VecBatch vb, const cplx* __restrict__ w, int64_t len, cplx* __res
 
 // out[i] = sum_blk partial[blk * nv + i]   (fixed order: deterministic)
 __global__ void pd_reduce_partials_kernel(const cplx* __restrict__ partial, int nblk, int nv,
-                                          cplx* __restrict__ out) {
+                                          cplx* __restrict__ out, int real_only) {
   const int i = blockIdx.x;
   double r = 0, im = 0;
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
@@ -241,7 +264,7 @@ __global__ void pd_reduce_partials_kernel(const cplx* __restrict__ partial, int 
   if (threadIdx.x == 0) {
     double tr = 0, ti = 0;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { tr += sr[k]; ti += si[k]; }
-    out[i] = cmake(tr, ti);
+    out[i] = cmake(tr, real_only ? 0.0 : ti);
   }
 }
 
@@ -315,7 +338,7 @@ static int mdot_batch(pd_handle* h, const cplx* const* vs, const cplx* w, int64_
   const int nb = red_blocks(h, len);
   pd_mdot_kernel<NV><<<nb, PD_RED_THREADS, 0, st>>>(vb, w, len, h->kry_partial);
   PD_CHECK_LAUNCH();
-  pd_reduce_partials_kernel<<<NV, 256, 0, st>>>(h->kry_partial, nb, NV, out);
+  pd_reduce_partials_kernel<<<NV, 256, 0, st>>>(h->kry_partial, nb, NV, out, h->kry_real);
   PD_CHECK_LAUNCH();
   h->launches += 2;
   return PD_OK;
@@ -362,7 +385,7 @@ static int maxpy_batch(pd_handle* h, const cplx* const* vs, const cplx* coef, do
   if (norm) {
     pd_maxpy_kernel<NV, true><<<nb, PD_RED_THREADS, 0, st>>>(vb, coef, sign, w, len, h->kry_partial);
     PD_CHECK_LAUNCH();
-    pd_reduce_partials_kernel<<<1, 256, 0, st>>>(h->kry_partial, nb, 1, norm_out);
+    pd_reduce_partials_kernel<<<1, 256, 0, st>>>(h->kry_partial, nb, 1, norm_out, 0);
     PD_CHECK_LAUNCH();
     h->launches += 2;
   } else {
@@ -407,6 +430,7 @@ extern "C" int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, cons
   }
   std::vector<const cplx*> vs(nv);
   for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
+  h->kry_real = 0;
   return mdot_list(h, vs.data(), nv, (const cplx*)w_dev, len, (cplx*)out_dev, (cudaStream_t)stream);
 }
 
@@ -454,6 +478,7 @@ static int ensure_basis(pd_handle* h, std::vector<cplx*>& V, int need, int64_t l
 
 struct KrylovCache {
   std::vector<cplx*> V;
+  int64_t veclen = 0;  // complex elements per cached vector
 };
 
 static KrylovCache* cache_of(pd_handle* h) {
@@ -476,8 +501,8 @@ void pd_krylov_free(pd_handle* h) {
   h->kry_host = nullptr;
 }
 
-extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
-                        int max_it, int* its_out, double* hist, int* reason_out, void* stream) {
+static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
+                      int max_it, int* its_out, double* hist, int* reason_out, void* stream, int real_vectors) {
   if (!h || !b_dev || !x_dev || restart < 1 || max_it < 0) {
     pd_set_error("pd_gmres: invalid argument");
     return PD_ERR_INVALID;
@@ -487,10 +512,22 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     return PD_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t len = 2 * (int64_t)h->n * h->cfg.N_t;
+  // real vectors: 2 n N_t doubles, handled by the BLAS-1 kernels as n N_t complex pairs (the real part of
+  // a pair-wise conj(v) w sum is the real inner product; imaginary parts are zeroed in the reduction)
+  const int64_t len = (real_vectors ? 1 : 2) * (int64_t)h->n * h->cfg.N_t;
+  h->kry_real = real_vectors;
+  auto PC = [&](const cplx* in, cplx* out) {
+    return real_vectors ? pd_pc_apply_real(h, in, out, stream) : pd_pc_apply(h, in, out, stream);
+  };
   const cplx* b = (const cplx*)b_dev;
   cplx* x = (cplx*)x_dev;
   KrylovCache* kc = cache_of(h);
+  if (kc->veclen < len) {  // cached basis vectors from a smaller (real) solve: start over
+    for (cplx* p : kc->V) cudaFree(p);
+    kc->V.clear();
+    kc->veclen = len;
+  }
+  const int64_t alloc_len = kc->veclen;
   int rc;
   if ((rc = ensure_partial(h))) return rc;
   const int hcap = restart + 2;
@@ -502,8 +539,9 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     h->kry_cap = hcap;
   }
   if (!h->kry_t) {
-    PD_CUDA(cudaMalloc(&h->kry_t, sizeof(cplx) * (size_t)len));
-    h->ws_bytes += sizeof(cplx) * (size_t)len;
+    const size_t full = 2 * (size_t)h->n * h->cfg.N_t;  // sized for the complex solve
+    PD_CUDA(cudaMalloc(&h->kry_t, sizeof(cplx) * full));
+    h->ws_bytes += sizeof(cplx) * full;
   }
   cplx* t = h->kry_t;
   cplx* hdev = h->kry_h;
@@ -520,17 +558,17 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
   auto Hat = [&](int i, int j) -> hcplx& { return H[(size_t)j * (restart + 1) + i]; };
 
   while (!converged && (its < max_it || first)) {
-    if ((rc = ensure_basis(h, kc->V, 1, len))) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
+    if ((rc = ensure_basis(h, kc->V, 1, alloc_len))) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
     cplx* v0 = kc->V[0];
     // r = P^-1 (b - A x)   (x = 0 on the first cycle)
     if (first) {
-      if ((rc = pd_pc_apply(h, b, v0, st))) return rc;
+      if ((rc = PC(b, v0))) return rc;
     } else {
-      if ((rc = pd_matvec_launch(h, x, t, st, 0, nullptr, nullptr))) return rc;
+      if ((rc = pd_matvec_launch(h, x, t, st, 0, nullptr, nullptr, real_vectors))) return rc;
       pd_axpby_kernel<<<nb1, 256, 0, st>>>(1.0, b, -1.0, t, len);
       PD_CHECK_LAUNCH();
       h->launches++;
-      if ((rc = pd_pc_apply(h, t, v0, st))) return rc;
+      if ((rc = PC(t, v0))) return rc;
     }
     const cplx* vs0[1] = {v0};
     if ((rc = mdot_list(h, vs0, 1, v0, len, hdev, st))) return rc;
@@ -557,14 +595,14 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     int jdone = 0;
     for (int j = 0; j < restart; ++j) {
       // a basis slot for w; if memory runs out, restart early with what we have
-      rc = ensure_basis(h, kc->V, j + 2, len);
+      rc = ensure_basis(h, kc->V, j + 2, alloc_len);
       if (rc == PD_ERR_NOMEM) {
         if (j == 0) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
         break;
       }
       cplx* w = kc->V[j + 1];
-      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0, nullptr, nullptr))) return rc;
-      if ((rc = pd_pc_apply(h, t, w, st))) return rc;
+      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0, nullptr, nullptr, real_vectors))) return rc;
+      if ((rc = PC(t, w))) return rc;
       // classical Gram-Schmidt: all inner products against the unmodified w first
       if ((rc = mdot_list(h, kc->V.data(), j + 1, w, len, hdev, st))) return rc;
       if ((rc = maxpy_list(h, kc->V.data(), j + 1, hdev, -1.0, w, len, hdev + (j + 1), st))) return rc;
@@ -625,4 +663,21 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
     return PD_ERR_NOT_CONVERGED;
   }
   return PD_OK;
+}
+
+extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
+                        int max_it, int* its_out, double* hist, int* reason_out, void* stream) {
+  return gmres_impl(h, b_dev, x_dev, rtol, atol, restart, max_it, its_out, hist, reason_out, stream, 0);
+}
+
+// Same solve on float64 vectors (2 n N_t doubles): real matvec, half-spectrum preconditioner, half the bytes
+// in every BLAS-1 sweep.  Valid because b, A and P are real for this problem (the imaginary parts the complex
+// solve carries are rounding noise).
+extern "C" int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
+                             int max_it, int* its_out, double* hist, int* reason_out, void* stream) {
+  if (h && !pd_rfft_supported(h)) {
+    pd_set_error("pd_gmres_real: needs a power-of-two N_t in [128, 16384] (got %d); use pd_gmres", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  return gmres_impl(h, b_dev, x_dev, rtol, atol, restart, max_it, its_out, hist, reason_out, stream, 1);
 }

@@ -212,6 +212,40 @@ class ParaDiagHandle:
         check(st, allow=(_lib.PD_ERR_NOT_CONVERGED,))
         return x, its.value, list(hist[: its.value + 1]), CONVERGED_REASONS.get(reason.value, str(reason.value))
 
+    # ---- float64 variants (real problem): half the bytes everywhere
+    def _rptr(self, t, name):
+        torch = _torch()
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or t.numel() != self.size:
+            raise ValueError(f"{name}: need a contiguous float64 CUDA tensor with {self.size} entries")
+        return C.c_void_p(t.data_ptr())
+
+    def empty_real(self):
+        torch = _torch()
+        return torch.empty(self.size, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def matvec_real(self, x, y=None):
+        if y is None:
+            y = self.empty_real()
+        check(self.lib.pd_matvec_real(self._h, self._rptr(x, "x"), self._rptr(y, "y"), self._stream()))
+        return y
+
+    def build_rhs_real(self, b=None):
+        if b is None:
+            b = self.empty_real()
+        check(self.lib.pd_build_rhs_real(self._h, self._rptr(b, "b"), self._stream()))
+        return b
+
+    def gmres_real(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
+        """pd_gmres_real: the same Krylov solve on float64 vectors with the half-spectrum preconditioner."""
+        if x is None:
+            x = self.empty_real()
+        its, reason = C.c_int(0), C.c_int(0)
+        hist = (C.c_double * (max_it + 1))()
+        st = self.lib.pd_gmres_real(self._h, self._rptr(b, "b"), self._rptr(x, "x"), float(rtol), float(atol),
+                                    int(restart), int(max_it), C.byref(its), hist, C.byref(reason), self._stream())
+        check(st, allow=(_lib.PD_ERR_NOT_CONVERGED,))
+        return x, its.value, list(hist[: its.value + 1]), CONVERGED_REASONS.get(reason.value, str(reason.value))
+
     def mdot(self, V, w):
         """V^H w for a (nv, len) basis tensor: PETSc VecMDot order."""
         torch = _torch()

@@ -78,7 +78,7 @@ class Optimal_Control_Wave_Equation:
     def matvec(self, x, y=None):
         return self.handle.matvec(x, y)
 
-    def solve(self, parameters=None, complex=False, rtol=None, verbose=True):
+    def solve(self, parameters=None, complex=False, rtol=None, verbose=True, real_vectors=False):
         """:182-244.  With the GMRES + python-PC parameters (:347-359) runs the device
         Krylov solve and returns (u_sol, p_sol) as (n, N_t) tensors (node-major, time fastest)."""
         import torch
@@ -102,7 +102,14 @@ class Optimal_Control_Wave_Equation:
         rtol = float(params.get('ksp_rtol', 1e-7)) if rtol is None else rtol
         atol = float(params.get('ksp_atol', 1e-50))
         solver_setted = time.time()
-        x, its, hist, reason = self.handle.gmres(self.b, rtol=rtol, atol=atol, restart=restart, max_it=max_it)
+        if real_vectors:
+            # the problem is real: float64 Krylov vectors and the half-spectrum preconditioner
+            # (pd_gmres_real); the result is promoted so that callers see the same complex layout
+            xr, its, hist, reason = self.handle.gmres_real(self.handle.build_rhs_real(), rtol=rtol, atol=atol,
+                                                           restart=restart, max_it=max_it)
+            x = xr.to(torch.complex128)
+        else:
+            x, its, hist, reason = self.handle.gmres(self.b, rtol=rtol, atol=atol, restart=restart, max_it=max_it)
         torch.cuda.synchronize(self.handle.device)
         solver_solved = time.time()
         self.ksp_its, self.ksp_reason, self.ksp_history = its, reason, hist

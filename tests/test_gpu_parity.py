@@ -298,6 +298,31 @@ def test_gmres_iteration_parity_at_4096():
             assert np.allclose(hist[:5], hist_o[:5], rtol=1e-6)          # identical until rounding takes over
 
 
+@pytest.mark.parametrize("N_x,N_t,gamma", [(64, 128, 1.0), (200, 256, 1e-2), (1024, 1024, 1.0)])
+def test_real_vector_gmres_equals_complex_gmres(N_x, N_t, gamma):
+    with ParaDiagHandle(N_x, N_t, gamma=gamma) as h:
+        bc = h.build_rhs()
+        br = h.build_rhs_real()
+        assert np.array_equal(br.cpu().numpy(), bc.cpu().numpy().real)
+        v = torch.randn(h.size, dtype=torch.float64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+        assert rel(h.matvec_real(v).cpu().numpy(), h.matvec(v.to(torch.complex128)).cpu().numpy().real) < 1e-15
+        xc, its_c, hist_c, reason_c = h.gmres(bc, rtol=1e-7)
+        xr, its_r, hist_r, reason_r = h.gmres_real(br, rtol=1e-7)
+        assert reason_r == "CONVERGED_RTOL" and abs(its_r - its_c) <= 1
+        assert np.allclose(hist_r[: min(its_r, its_c)], hist_c[: min(its_r, its_c)], rtol=1e-5)
+        assert rel(xr.cpu().numpy(), xc.cpu().numpy().real) < 1e-6
+        # and again complex after real on the same handle (basis cache is re-sized)
+        xc2, its_c2, _, _ = h.gmres(bc, rtol=1e-7)
+        assert its_c2 == its_c
+        # random right-hand side, tens of iterations
+        rng = np.random.default_rng(0)
+        b = rng.standard_normal((2, N_x + 1, N_t))
+        b[:, 0] = b[:, -1] = 0
+        _, its_rc, _, _ = h.gmres(torch.tensor(b.reshape(-1) + 0j, device=DEV), rtol=1e-7, max_it=400)
+        _, its_rr, _, _ = h.gmres_real(torch.tensor(b.reshape(-1), device=DEV), rtol=1e-7, max_it=400)
+        assert abs(its_rc - its_rr) <= 1
+
+
 def test_gmres_config2_manufactured_rhs():
     with ParaDiagHandle(1024, 1024) as h:
         b = h.build_rhs()
