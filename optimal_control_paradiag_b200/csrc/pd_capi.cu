@@ -255,10 +255,15 @@ extern "C" int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, vo
   if (rc) return rc;
   const int64_t nlines = 2 * (int64_t)h->n;
   // real lines -> half spectra (k = 0..N_t/2), the same per-frequency stage on half as many columns, back
-  if ((rc = pd_rfft_launch(h, x_dev, h->work, nlines, 1, st))) return rc;
+  // u- and p-line of a node go through ONE complex N_t-point transform (pd_rfft_pair_kernel); sizes it does
+  // not cover use the per-line packed kernel
+  rc = pd_rfft_pair_launch(h, x_dev, h->work, h->n, 1, st);
+  if (rc == -100) rc = pd_rfft_launch(h, x_dev, h->work, nlines, 1, st);
+  if (rc) return rc;
   if ((rc = pd_solve_launch(h, h->work, st, nullptr, 1))) return rc;
-  if ((rc = pd_rfft_launch(h, h->work, y_dev, nlines, 0, st))) return rc;
-  return PD_OK;
+  rc = pd_rfft_pair_launch(h, h->work, y_dev, h->n, 0, st);
+  if (rc == -100) rc = pd_rfft_launch(h, h->work, y_dev, nlines, 0, st);
+  return rc;
 }
 
 extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {

@@ -548,6 +548,158 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
   return PD_OK;
 }
 
+// Two-for-one variant used by the apply: the u-line and the p-line of one node are transformed together
+// as ONE complex N_t-point line c = u + i p through the full-size register pipeline (same bytes per CTA
+// and the same efficiency as the complex kernel):
+//   TO_FREQ : C = FFT(c);  A = (C[k] + conj C[N-k])/2,  B = -i (C[k] - conj C[N-k])/2,
+//             u-hat[k] = conj(A)/N,  p-hat[k] = conj(B)/N          for k = 0..N/2
+//   !TO_FREQ: D[k] = Wu[k] + i Wp[k] (k <= N/2), D[k] = conj(Wu[N-k]) + i conj(Wp[N-k]) (k > N/2);
+//             y_u + i y_p = FFT(D)
+// x / y are (2, n, N_t) float64, the half spectra (2, n, KP) complex; one "line" = one node.
+template <int R0, int R1, int R2, int R3, bool TO_FREQ>
+__global__ void __launch_bounds__(512)
+pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nnodes,
+                    const cplx* __restrict__ tw) {
+  constexpr int N = R0 * R1 * R2 * R3;
+  constexpr int T = N / 16;
+  constexpr int H = N / 2;
+  constexpr int KP = (H + 1 + 7) & ~7;
+  constexpr int NL = (R3 > 1) ? R3 : (R2 > 1 ? R2 : R1);
+  constexpr int NsL = N / NL;
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  const int lpb = blockDim.x / T;
+  const int lane_line = threadIdx.x / T;
+  const int t = threadIdx.x - lane_line * T;
+  cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw) + (size_t)lane_line * (N + N / 16);
+  const double invN = 1.0 / (double)N;
+  for (int64_t n0 = (int64_t)blockIdx.x * lpb; n0 < nnodes; n0 += (int64_t)gridDim.x * lpb) {
+    const int64_t node = n0 + lane_line;
+    const int64_t nd = node < nnodes ? node : nnodes - 1;
+    const bool live = node < nnodes;
+    cplx io[16];
+    if (TO_FREQ) {
+      const double* xu = reinterpret_cast<const double*>(in_) + nd * N;
+      const double* xp = xu + nnodes * N;
+      cplx* gu = reinterpret_cast<cplx*>(out_) + nd * KP;
+      cplx* gp = gu + nnodes * KP;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) io[q] = cmake(xu[t + T * q], xp[t + T * q]);
+      if (R2 == 1) {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live, io);
+      } else if (R3 == 1) {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live);
+        pow2_pass<(R2 > 1 ? R2 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0 * R1, t, T, 1.0, live, io);
+      } else {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live);
+        pow2_pass<(R2 > 1 ? R2 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0 * R1, t, T, 1.0, live);
+        pow2_pass<(R3 > 1 ? R3 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0 * R1 * R2, t, T, 1.0, live, io);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 16 / NL; ++u)
+#pragma unroll
+        for (int r = 0; r < NL; ++r) sm[pad16(t + u * T + r * NsL)] = io[u * NL + r];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int k = t + T * q;
+        if (k <= H) {
+          const cplx a = sm[pad16(k)], b = cconj(sm[pad16((N - k) & (N - 1))]);
+          // conj(A)/N and conj(B)/N with A = (a + b)/2, B = -i (a - b)/2
+          const double s = 0.5 * invN;
+          if (live) {
+            gu[k] = cmake((a.x + b.x) * s, -(a.y + b.y) * s);
+            gp[k] = cmake((a.y - b.y) * s, (a.x - b.x) * s);
+          }
+        }
+      }
+      if (t == 0 && live)
+        for (int kk = H + 1; kk < KP; ++kk) { gu[kk] = cmake(0, 0); gp[kk] = cmake(0, 0); }
+      __syncthreads();
+    } else {
+      const cplx* wu = reinterpret_cast<const cplx*>(in_) + nd * KP;
+      const cplx* wp = wu + nnodes * KP;
+      double* yu = reinterpret_cast<double*>(out_) + nd * N;
+      double* yp = yu + nnodes * N;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int k = t + T * q;
+        const bool lo = k <= H;
+        const int kk = lo ? k : N - k;
+        cplx a = wu[kk], b = wp[kk];
+        if (!lo) { a.y = -a.y; b.y = -b.y; }
+        io[q] = cmake(a.x - b.y, a.y + b.x);   // a + i b
+      }
+      if (R2 == 1) {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live, io);
+      } else if (R3 == 1) {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live);
+        pow2_pass<(R2 > 1 ? R2 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0 * R1, t, T, 1.0, live, io);
+      } else {
+        pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
+        pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live);
+        pow2_pass<(R2 > 1 ? R2 : 2), false, false, false>(nullptr, nullptr, sm, tw, N, R0 * R1, t, T, 1.0, live);
+        pow2_pass<(R3 > 1 ? R3 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0 * R1 * R2, t, T, 1.0, live, io);
+      }
+      // io[u*NL + r] <-> time index (t + u T) + r NsL: real part -> u line, imaginary part -> p line
+      if (live) {
+#pragma unroll
+        for (int u = 0; u < 16 / NL; ++u)
+#pragma unroll
+          for (int r = 0; r < NL; ++r) {
+            const int i = t + u * T + r * NsL;
+            yu[i] = io[u * NL + r].x;
+            yp[i] = io[u * NL + r].y;
+          }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int R0, int R1, int R2, int R3>
+static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st) {
+  constexpr int N = R0 * R1 * R2 * R3;
+  constexpr int T = N / 16;
+  int threads = T < 256 ? 256 : T;
+  int lpb = threads / T;
+  size_t smem = (size_t)lpb * (N + N / 16) * sizeof(cplx);
+  int64_t nblk = (nnodes + lpb - 1) / lpb;
+  if (to_freq) {
+    auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, true>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
+  } else {
+    auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, false>;
+    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
+  }
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// both fields of `nnodes` nodes at once: (2, nnodes, N_t) float64 <-> (2, nnodes, KP) complex half spectra
+int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st) {
+  if (nnodes <= 0) return PD_OK;
+  switch (h->cfg.N_t) {
+    case 128:  return launch_rfft_pair<16, 8, 1, 1>(h, in, out, nnodes, to_freq, st);
+    case 256:  return launch_rfft_pair<16, 16, 1, 1>(h, in, out, nnodes, to_freq, st);
+    case 512:  return launch_rfft_pair<16, 8, 4, 1>(h, in, out, nnodes, to_freq, st);
+    case 1024: return launch_rfft_pair<16, 16, 4, 1>(h, in, out, nnodes, to_freq, st);
+    case 2048: return launch_rfft_pair<16, 16, 8, 1>(h, in, out, nnodes, to_freq, st);
+    case 4096: return launch_rfft_pair<16, 16, 16, 1>(h, in, out, nnodes, to_freq, st);
+    case 8192: return launch_rfft_pair<16, 16, 8, 4>(h, in, out, nnodes, to_freq, st);
+    default: break;
+  }
+  return -100;  // not covered (N_t = 16384): the caller falls back to the per-line kernel
+}
+
 template <int R0, int R1, int R2, int R3>
 static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st) {
   constexpr int M = R0 * R1 * R2 * R3;
