@@ -63,6 +63,7 @@ struct SolveParams {
   // inter-slab separator (r > 0) and the last body row is followed by the next slab's separator (r < G-1).
   int first_dirichlet, last_dirichlet;
   int freq_perm;  // 1: columns hold [even k | odd k] (the N_t = 16384 FFT kernel's frequency order)
+  int koff, kend; // column range [koff, kend) this launch works on (row stride stays K)
 };
 
 // Slab-mode extras (device pointers; all null in single-GPU mode)
@@ -257,9 +258,9 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
                       SolveParams sp, cplx* __restrict__ lastl) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
-  const int kk = blockIdx.x * PD_KB + tid;
-  const bool valid = kk < sp.K;
-  const int kc_idx = valid ? kk : sp.K - 1;
+  const int kk = sp.koff + blockIdx.x * PD_KB + tid;
+  const bool valid = kk < sp.kend;
+  const int kc_idx = valid ? kk : sp.kend - 1;
   const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   const cplx* wu = w + kc_idx;
@@ -317,8 +318,8 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
 // recurrences, emits f_c and the partial rhs of its trailing separator for level lev + 1.
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
-  const int kk = blockIdx.x * PD_KB + threadIdx.x;
-  if (kk >= sp.K) return;
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.kend) return;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const Sys below = level_sys(kc, sp, lev - 1);
   const Sys s = reduce_sys(below, chunk_len(lev - 1));
@@ -366,8 +367,8 @@ pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
   __shared__ cplx mtab[PD_LG][PD_KB];  // per-thread column of chunk pivots
-  const int kk = blockIdx.x * PD_KB + threadIdx.x;
-  if (kk >= sp.K) return;
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.kend) return;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const Sys s = level_sys(kc, sp, lev);
   const int64_t K = sp.K;
@@ -452,13 +453,13 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
   cplx* s_rp = s_up + rows;
   cplx* s_rm = s_rp + rows;
   const int tid = threadIdx.x;
-  const int kk0 = blockIdx.x * kpb;
+  const int kk0 = sp.koff + blockIdx.x * kpb;
   const int64_t K = sp.K;
 
   // coefficients of this CTA's frequencies, regenerated once
   if (tid < kpb) {
     int kk = kk0 + tid;
-    if (kk >= sp.K) kk = sp.K - 1;
+    if (kk >= sp.kend) kk = sp.kend - 1;
     const KCoef kc = make_coef(freq_of(sp, kk), sp);
     const Sys below = level_sys(kc, sp, lev - 1);
     const Sys s = reduce_sys(below, chunk_len(lev - 1));
@@ -474,7 +475,7 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
     const int q = idx / kpb, ks = idx - q * kpb;
     int kk = kk0 + ks;
-    if (kk >= sp.K) kk = sp.K - 1;
+    if (kk >= sp.kend) kk = sp.kend - 1;
     const cplx rP = cfms(c_offb[ks], Fb[((int64_t)(q + 1) * 2) * K + kk], R[((int64_t)q * 2) * K + kk]);
     const cplx rM = cfms(c_offb[ks], Fb[((int64_t)(q + 1) * 2 + 1) * K + kk], R[((int64_t)q * 2 + 1) * K + kk]);
     const cplx dinv = crcp(q == n - 1 ? c_dlast[ks] : c_dmain[ks]);
@@ -539,7 +540,7 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
   for (int idx = tid; idx < rows; idx += PD_PCR_THREADS) {
     const int q = idx / kpb, ks = idx - q * kpb;
     const int kk = kk0 + ks;
-    if (kk >= sp.K) continue;
+    if (kk >= sp.kend) continue;
     const int slot = ks * n + q;
     Rw[((int64_t)q * 2) * K + kk] = s_rp[slot];
     Rw[((int64_t)q * 2 + 1) * K + kk] = s_rm[slot];
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(PD_KB)
 pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp, SlabPtrs sl) {
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
-  const int kk = blockIdx.x * PD_KB + tid;
-  const bool valid = kk < sp.K;
-  const int kc_idx = valid ? kk : sp.K - 1;
+  const int kk = sp.koff + blockIdx.x * PD_KB + tid;
+  const bool valid = kk < sp.kend;
+  const int kc_idx = valid ? kk : sp.kend - 1;
   const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   cplx* wu = w + kc_idx;
@@ -867,6 +868,8 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   }
   sp.h = h->h; sp.dt2 = h->dt * h->dt; sp.c = h->c;
   sp.plane = (int64_t)h->n * sp.K;
+  sp.koff = 0;
+  sp.kend = sp.K;
   sp.nlev = pl->nlev;
   sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
   sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
@@ -879,8 +882,9 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
 // levels 1..top: reduce, PCR on the top system, back-substitute; leaves the level-1 solution in R[1]
 static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, cudaStream_t st) {
   const int top = sp.nlev;
+  const int ncol = sp.kend - sp.koff;
   for (int lev = 1; lev < top; ++lev) {
-    pd_solve_level_reduce_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    pd_solve_level_reduce_kernel<<<stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
     PD_CHECK_LAUNCH();
     h->launches++;
   }
@@ -888,16 +892,16 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   int kpb = (PD_PCR_THREADS * PD_PCR_MAXROWS) / n;
   if (kpb > 32) kpb = 32;
   // keep at least ~2 CTAs per SM when the frequency count allows it
-  while (kpb > 4 && (sp.K + kpb - 1) / kpb < 2 * h->num_sms) kpb >>= 1;
+  while (kpb > 4 && (ncol + kpb - 1) / kpb < 2 * h->num_sms) kpb >>= 1;
   if (kpb < 1) kpb = 1;
   const size_t smem = (size_t)n * kpb * 64;
-  const int nblk = (sp.K + kpb - 1) / kpb;
+  const int nblk = (ncol + kpb - 1) / kpb;
   PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
   PD_CHECK_LAUNCH();
   h->launches++;
   for (int lev = top - 1; lev >= 1; --lev) {
-    pd_solve_level_back_kernel<<<stream_grid(h, sp.K, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    pd_solve_level_back_kernel<<<stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
     PD_CHECK_LAUNCH();
     h->launches++;
   }
@@ -988,16 +992,18 @@ int pd_solve_plan(pd_handle* h) {
   return PD_OK;
 }
 
-int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int half_spectrum) {
-  SolveParams sp; Levels lv; SlabPtrs sl;
-  fill_params(h, sp, lv, sl, half_spectrum);
-  const int top = sp.nlev;
-  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
-  if (top >= 1) {
+// one column range [koff, kend) through pass A, the interface levels and pass B on stream st
+static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, const SlabPtrs& sl, int koff, int kend,
+                       cudaStream_t st, cudaEvent_t* ev, cudaEvent_t after_passA = nullptr) {
+  sp.koff = koff;
+  sp.kend = kend;
+  const dim3 grid0 = stream_grid(h, kend - koff, sp.rows[1] + 1);
+  if (sp.nlev >= 1) {
     pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
+    if (after_passA) cudaEventRecord(after_passA, st);
     int rc = run_interface(h, sp, lv, st);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], st);
@@ -1009,6 +1015,15 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
+}
+
+int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int half_spectrum) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl, half_spectrum);
+  // (Splitting the columns over two streams to hide the latency-bound interface kernels under the
+  // streaming passes of the other half was tried and does not help: pass A / pass B occupy the whole
+  // register file of every SM, so nothing else becomes resident until they drain.)
+  return solve_range(h, w, sp, lv, sl, 0, sp.K, st, ev);
 }
 
 // slab mode, first half: pass A, interface levels, slab functionals -> out[6][K]
