@@ -62,21 +62,15 @@ __device__ __forceinline__ T ld_or_zero(const T* __restrict__ v, int f, int j, i
   return v[(int64_t)jl * op.N_t + i];
 }
 
+#define PD_MV_TJ 16  // nodes per thread: rows j-1, j, j+1 slide through registers, each row is loaded once per tile
+
 template <class T>
 __global__ void __launch_bounds__(256)
 pd_matvec_kernel(const T* __restrict__ x, T* __restrict__ y, OpParams op) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jl = blockIdx.y;
-  const int j = op.j0 + jl;  // global node
   if (i >= op.N_t) return;
   const T* u = x;
   const T* p = x + op.plane;
-  const int64_t o = (int64_t)jl * op.N_t + i;
-  if (j == 0 || j == op.n - 1) {
-    y[o] = u[o];
-    y[op.plane + o] = p[o];
-    return;
-  }
   const double m_off = op.h / 6.0, m_dia = 2.0 * op.h / 3.0;
   const double ih = 1.0 / op.h;
   const double d_i = (i == 0 && !op.circulant) ? 0.5 : 1.0;               // :117
@@ -89,32 +83,50 @@ pd_matvec_kernel(const T* __restrict__ x, T* __restrict__ y, OpParams op) {
   // differences of neighbouring values -- exact in floating point (Sterbenz) -- before any scaling:
   //   time:   D2 v = (v_i - v_{i-1}) - (v_{i-1} - v_{i-2})        per node, then M in space
   //   space:  K v  = ((v_C - v_L) + (v_C - v_R)) / h               per time level, then summed
+  const int jl0 = blockIdx.y * PD_MV_TJ;
+  const int jl1 = min(jl0 + PD_MV_TJ, op.nloc);
   T uv[3][3], pv[3][3];  // [node L,C,R][time level 0,1,2]: u at i-t, p at i+t
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
+  for (int s = 0; s < 2; ++s)
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      uv[s][t] = ld_or_zero<T>(u, 0, j - 1 + s, i - t, op);
-      pv[s][t] = ld_or_zero<T>(p, 1, j - 1 + s, i + t, op);
+      uv[s + 1][t] = ld_or_zero<T>(u, 0, op.j0 + jl0 - 1 + s, i - t, op);
+      pv[s + 1][t] = ld_or_zero<T>(p, 1, op.j0 + jl0 - 1 + s, i + t, op);
     }
-  T d2u[3], d2p[3];
+  for (int jl = jl0; jl < jl1; ++jl) {
+    const int j = op.j0 + jl;  // global node
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    d2u[s] = vsub(vsub(uv[s][0], uv[s][1]), vsub(uv[s][1], uv[s][2]));
-    d2p[s] = vsub(vsub(pv[s][0], pv[s][1]), vsub(pv[s][1], pv[s][2]));
+    for (int t = 0; t < 3; ++t) {
+      uv[0][t] = uv[1][t]; uv[1][t] = uv[2][t];
+      pv[0][t] = pv[1][t]; pv[1][t] = pv[2][t];
+      uv[2][t] = ld_or_zero<T>(u, 0, j + 1, i - t, op);
+      pv[2][t] = ld_or_zero<T>(p, 1, j + 1, i + t, op);
+    }
+    const int64_t o = (int64_t)jl * op.N_t + i;
+    if (j == 0 || j == op.n - 1) {  // Dirichlet rows: identity (the centre value bypasses the column mask)
+      y[o] = u[o];
+      y[op.plane + o] = p[o];
+      continue;
+    }
+    T d2u[3], d2p[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      d2u[s] = vsub(vsub(uv[s][0], uv[s][1]), vsub(uv[s][1], uv[s][2]));
+      d2p[s] = vsub(vsub(pv[s][0], pv[s][1]), vsub(pv[s][1], pv[s][2]));
+    }
+    const T Ku0 = vscale(vadd(vsub(uv[1][0], uv[0][0]), vsub(uv[1][0], uv[2][0])), ih);
+    const T Ku2 = vscale(vadd(vsub(uv[1][2], uv[0][2]), vsub(uv[1][2], uv[2][2])), ih);
+    const T Kp0 = vscale(vadd(vsub(pv[1][0], pv[0][0]), vsub(pv[1][0], pv[2][0])), ih);
+    const T Kp2 = vscale(vadd(vsub(pv[1][2], pv[0][2]), vsub(pv[1][2], pv[2][2])), ih);
+    const T Md2u = vlin3(d2u[0], d2u[1], d2u[2], m_off, m_dia);
+    const T Md2p = vlin3(d2p[0], d2p[1], d2p[2], m_off, m_dia);
+    const T Mu0 = vlin3(uv[0][0], uv[1][0], uv[2][0], m_off, m_dia);
+    const T Mp0 = vlin3(pv[0][0], pv[1][0], pv[2][0], m_off, m_dia);
+    // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
+    y[o] = vcomb(Md2u, q_i * op.dt2h, vadd(Ku0, Ku2), d_i * op.c, Mp0);
+    // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
+    y[op.plane + o] = vcomb(Md2p, op.dt2h, vadd(Kp0, Kp2), -e_i * op.c, Mu0);
   }
-  const T Ku0 = vscale(vadd(vsub(uv[1][0], uv[0][0]), vsub(uv[1][0], uv[2][0])), ih);
-  const T Ku2 = vscale(vadd(vsub(uv[1][2], uv[0][2]), vsub(uv[1][2], uv[2][2])), ih);
-  const T Kp0 = vscale(vadd(vsub(pv[1][0], pv[0][0]), vsub(pv[1][0], pv[2][0])), ih);
-  const T Kp2 = vscale(vadd(vsub(pv[1][2], pv[0][2]), vsub(pv[1][2], pv[2][2])), ih);
-  const T Md2u = vlin3(d2u[0], d2u[1], d2u[2], m_off, m_dia);
-  const T Md2p = vlin3(d2p[0], d2p[1], d2p[2], m_off, m_dia);
-  const T Mu0 = vlin3(uv[0][0], uv[1][0], uv[2][0], m_off, m_dia);
-  const T Mp0 = vlin3(pv[0][0], pv[1][0], pv[2][0], m_off, m_dia);
-  // state row: M(u_i - 2u_{i-1} + u_{i-2}) + q dt^2/2 K(u_i + u_{i-2}) - d c M p_i
-  y[o] = vcomb(Md2u, q_i * op.dt2h, vadd(Ku0, Ku2), d_i * op.c, Mp0);
-  // adjoint row: e c M u_i + M(p_i - 2p_{i+1} + p_{i+2}) + dt^2/2 K(p_i + p_{i+2})
-  y[op.plane + o] = vcomb(Md2p, op.dt2h, vadd(Kp0, Kp2), -e_i * op.c, Mu0);
 }
 
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
@@ -129,7 +141,7 @@ int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int 
     pd_set_error("matvec in slab mode needs the neighbour rows (halo_lo / halo_hi)");
     return PD_ERR_INVALID;
   }
-  dim3 grid((op.N_t + 255) / 256, h->n);
+  dim3 grid((op.N_t + 255) / 256, (h->n + PD_MV_TJ - 1) / PD_MV_TJ);
   if (real_vectors)
     pd_matvec_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(x), reinterpret_cast<double*>(y), op);
   else
