@@ -31,7 +31,7 @@
 //            (Toeplitz except its last diagonal entry -- a structure the reduction
 //            preserves, so its coefficients too are regenerated, never stored).
 //            While it has more than PD_PCR_MAX rows it is reduced again the same way
-//            with chunks of PD_LG = 16 rows (generic kernels, ~6 % of the data).
+//            with chunks of PD_LG = 8 rows (generic kernels, ~6 % of the data).
 //   top      the last interface system (<= 32 rows per k) is solved by parallel
 //            cyclic reduction held in shared memory, up to 32 frequencies per CTA.
 //   back     the generic levels are back-substituted, then pass B (1 read + 1 write
@@ -44,8 +44,9 @@
 #include "pd_common.cuh"
 
 #define PD_L 16            // level-0 chunk length (rows held in registers)
-#define PD_LG 16           // chunk length of the generic interface levels
+#define PD_LG 8            // chunk length of the generic interface levels
 #define PD_KB 128          // frequencies per CTA in the streaming passes
+#define PD_AG 4            // rows per software-pipeline group in pass A
 #define PD_PCR_MAX 32      // largest interface system handed to the PCR kernel (many frequencies)
 #define PD_PCR_MAX_SMALLK 128  // ... when there are few frequencies (launch-bound sizes: fewer kernels win)
 #define PD_PCR_THREADS 256
@@ -253,7 +254,7 @@ struct Levels {
 };
 
 // ------------------------------------------------------------------- pass A
-__global__ void __launch_bounds__(PD_KB)
+__global__ void __launch_bounds__(PD_KB, 4)
 pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
                       SolveParams sp, cplx* __restrict__ lastl) {
   __shared__ cplx mtab[PD_L][PD_KB];
@@ -270,39 +271,57 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
   for (int c = blockIdx.y; c <= P; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
-    // chunk rows and (c < P) the separator row that follows: index PD_L
-    cplx ru[PD_L + 1], rp_[PD_L + 1];
+    const int nrows = Lc + (c < P ? 1 : 0);  // chunk rows + the separator row that follows
+    // Software pipeline over groups of PD_AG rows: the next group's loads are in flight while the current
+    // group's recurrences run.  (Loading all 17 rows up front costs 254 registers = 2 CTAs per SM.)
+    cplx bu[2][PD_AG], bp[2][PD_AG];
 #pragma unroll
-    for (int i = 0; i < PD_L + 1; ++i) {
-      if (i < Lc || (i == PD_L && c < P)) {
-        ru[i] = wu[(int64_t)(j0 + i) * K];
-        rp_[i] = wp[(int64_t)(j0 + i) * K];
+    for (int r = 0; r < PD_AG; ++r)
+      if (r < nrows) {
+        bu[0][r] = wu[(int64_t)(j0 + r) * K];
+        bp[0][r] = wp[(int64_t)(j0 + r) * K];
       }
-    }
     cplx dP = cmake(0, 0), dM = cmake(0, 0), fP = cmake(0, 0), fM = cmake(0, 0);
-    cplx pi = cmake(1, 0);
+    cplx pi = cmake(1, 0), sP = cmake(0, 0), sM = cmake(0, 0);
+#pragma unroll 1
+    for (int g = 0; g < (PD_L + 1 + PD_AG - 1) / PD_AG; g += 2) {
 #pragma unroll
-    for (int i = 0; i < PD_L; ++i) {
-      if (i < Lc) {
-        cplx rP, rM;
-        rotate_in(kc, ru[i], rp_[i], rP, rM);
-        const cplx mi = mtab[i][tid];
-        if (i > 0) {
-          const cplx cp = cmul(kc.a, mtab[i - 1][tid]);  // c'_{i-1}
-          pi = cneg(cmul(pi, cp));
+      for (int half = 0; half < 2; ++half) {
+        const int base = (g + half) * PD_AG;
+        // prefetch the following group into the other buffer
+#pragma unroll
+        for (int r = 0; r < PD_AG; ++r) {
+          const int i = base + PD_AG + r;
+          if (i < nrows) {
+            bu[half ^ 1][r] = wu[(int64_t)(j0 + i) * K];
+            bp[half ^ 1][r] = wp[(int64_t)(j0 + i) * K];
+          }
         }
-        dP = cmul(cfms(kc.a, dP, rP), mi);
-        dM = cmul(cfms(kc.a, dM, rM), mi);
-        fP = cfma(pi, dP, fP);
-        fM = cfma(pi, dM, fM);
+#pragma unroll
+        for (int r = 0; r < PD_AG; ++r) {
+          const int i = base + r;
+          if (i < Lc) {
+            cplx rP, rM;
+            rotate_in(kc, bu[half][r], bp[half][r], rP, rM);
+            const cplx mi = mtab[i][tid];
+            if (i > 0) {
+              const cplx cp = cmul(kc.a, mtab[i - 1][tid]);  // c'_{i-1}
+              pi = cneg(cmul(pi, cp));
+            }
+            dP = cmul(cfms(kc.a, dP, rP), mi);
+            dM = cmul(cfms(kc.a, dM, rM), mi);
+            fP = cfma(pi, dP, fP);
+            fM = cfma(pi, dM, fM);
+          } else if (i == PD_L && c < P) {
+            rotate_in(kc, bu[half][r], bp[half][r], sP, sM);
+          }
+        }
       }
     }
     if (valid) {
       F0[((int64_t)c * 2) * K + kk] = fP;
       F0[((int64_t)c * 2 + 1) * K + kk] = fM;
       if (c < P) {
-        cplx sP, sM;
-        rotate_in(kc, ru[PD_L], rp_[PD_L], sP, sM);
         R1[((int64_t)c * 2) * K + kk] = cfms(kc.a, dP, sP);      // rho_sep - a l_c
         R1[((int64_t)c * 2 + 1) * K + kk] = cfms(kc.a, dM, sM);
       } else if (lastl) {
