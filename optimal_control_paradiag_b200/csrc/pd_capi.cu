@@ -28,6 +28,7 @@ extern "C" int pd_destroy(pd_handle* h) {
   pd_krylov_free(h);
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->twiddle_half) cudaFree(h->twiddle_half);
+  if (h->twiddle_quarter) cudaFree(h->twiddle_quarter);
   pd_solve_free(h);
 
   if (h->work) cudaFree(h->work);

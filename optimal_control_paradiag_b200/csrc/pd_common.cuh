@@ -81,7 +81,9 @@ struct pd_handle {
 
   // FFT plan
   cplx* twiddle;  // e^{-2 pi i j / N_t}, j < N_t
-  cplx* twiddle_half;  // same for N_t / 2 (only N_t = 16384)
+  cplx* twiddle_half;     // same for N_t / 2 (power-of-two N_t >= 128: real-input path)
+  cplx* twiddle_quarter;  // same for N_t / 4 (only N_t = 16384: the 4-CTA cluster kernel)
+  int fft16k_clusters;    // co-resident 4-CTA clusters (grid of the persistent 16k kernel)
   int fft_kind;   // 0 generic smem Stockham, 1 power-of-two register kernel
   int npass;
   int radix[PD_MAX_FFT_PASSES];

@@ -157,7 +157,37 @@ __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 //   LAST  : outputs go to global memory (or, with KEEP, stay in `io`)
 //   io    : 16 registers; input order io[u*R + q] <-> element (t + u T) + q N/R,
 //           output order io[u*R + r] <-> element base(t + u T) + r Ns
-template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false>
+// ---- thread-block-cluster plumbing of the N_t = 16384 kernel (sm_90+ PTX) ----
+// Two barrier phases per line, both on the hardware cluster barrier, split into arrive and wait:
+//   A "my shared memory may be overwritten": RELAXED -- it orders shared-memory reads that were issued before
+//     the __syncthreads preceding the arrive against the peers' later remote stores, so no fence is needed
+//     (arrive.release would stall every warp on a membar until its in-flight global stores are acknowledged);
+//   B "the exchange has landed": release / acquire, the remote stores must be visible to the reader.
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 32-bit shared::cluster address of `smem_ptr` in CTA `rank` of the cluster (keeps the 64-bit generic
+// pointers of cluster.map_shared_rank out of the register budget)
+__device__ __forceinline__ uint32_t cluster_map(const void* smem_ptr, uint32_t rank) {
+  uint32_t r;
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_store(uint32_t addr, cplx v) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
+template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false, bool CLARRIVE = false>
 __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
                                           cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
                                           int t, int T, double scale, bool live, cplx* io = nullptr) {
@@ -199,6 +229,8 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
       }
     }
     __syncthreads();  // all reads of sm done before anyone overwrites it
+    // cluster kernels: this CTA's shared memory is free from here on (split-phase cluster barrier)
+    if (CLARRIVE) cluster_arrive_relaxed();
   }
 #pragma unroll
   for (int u = 0; u < NB; ++u) dft_pow2<R>(v[u]);
@@ -261,82 +293,124 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
   }
 }
 
-// N_t = 16384: a line is 256 KiB, more than one CTA's shared memory, so a 2-CTA thread-block cluster
-// transforms it as 2 x 8192: each CTA runs the 8192-point pipeline above entirely in its own shared
-// memory and ONE exchange through distributed shared memory performs the remaining radix-2 stage.
-//   TO_FREQ (time -> frequency, decimation in frequency): the radix-2 stage comes first,
-//       y0[n] = x[n] + x[n+N/2],  y1[n] = (x[n] - x[n+N/2]) W_N^n,  X[2c] = FFT(y0)[c], X[2c+1] = FFT(y1)[c];
-//       CTA 0 stores the even frequencies in the first half of the line, CTA 1 the odd ones in the second.
-//   !TO_FREQ (frequency -> time, decimation in time): input in that same even/odd order,
-//       y[i] = A[i] + W_N^i B[i],  y[i+N/2] = A[i] - W_N^i B[i]  with A, B the two half transforms.
-// The frequency axis of an N_t = 16384 problem is therefore stored as [even k | odd k]; the per-frequency
-// solves are independent and only need the index map (pd_freq_index), so no reordering pass exists.
+// N_t = 16384: a line is 256 KiB, more than one CTA's shared memory, so a 4-CTA thread-block cluster
+// transforms it as N = 4 x 4096.  Every CTA runs the 4096-point register pipeline above (256 threads, 68 KiB
+// of shared memory, two CTAs per SM so that one CTA's global traffic overlaps the other's arithmetic), and
+// the remaining radix-4 stage is an all-to-all between the four CTAs done with REMOTE STORES into
+// distributed shared memory (3/4 of a line crosses the SM-to-SM network once; stores are fire-and-forget, no
+// remote-load latency is exposed).  With Q = N/4, w = W_N:
+//   TO_FREQ (time -> frequency, decimation in frequency):
+//       y_q[j] = w^{jq} sum_m x[j + Q m] (-i)^{mq},   X[4k' + q] = FFT_Q(y_q)[k'].
+//       CTA c loads x[j + Q m] for its j-quarter [1024c, 1024c + 1024) and all m straight from global
+//       memory (four contiguous 16 KiB pieces), does the 4-point DFTs and twiddles in registers and stores
+//       y_q[j] into CTA q's shared memory; CTA q then transforms y_q and writes the frequencies k = q (mod 4)
+//       as the q-th quarter of the line.
+//   !TO_FREQ (frequency -> time, decimation in time), input in that [q][k'] order:
+//       Z_q = FFT_Q(Y_q),   x[n' + Q m] = sum_q (-i)^{mq} w^{n'q} Z_q[n'].
+//       CTA q transforms its quarter and stores Z_q[n'] into the shared memory of the CTA that owns n'
+//       (n'-quarters); that CTA twiddles, does the 4-point DFTs and writes four contiguous 16 KiB pieces of
+//       the time line.
+// The frequency axis of an N_t = 16384 problem is therefore stored as [k = 0 mod 4 | 1 mod 4 | 2 mod 4 |
+// 3 mod 4]; the per-frequency solves are independent and only need the index map (freq_of in pd_solve.cu),
+// so no reordering pass exists.  Measured alternatives (B200): a 2-CTA cluster of
+// 8192-point pipelines reading the peer's half through distributed shared memory (one CTA per SM) reached
+// 2.5 TB/s against 3.1-3.4 TB/s here; st.async + mbarrier instead of the release/acquire barrier, an L2
+// prefetch of the next line and three CTAs per SM (80 registers) each measured equal or slower.
 #define PD_BIGN 16384
 template <bool INV, bool TO_FREQ>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 2)
 pd_fft_16k_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
-                  const cplx* __restrict__ tw, const cplx* __restrict__ tw_half, double scale) {
-  constexpr int N = PD_BIGN, H = N / 2, T = H / 16;  // T = 512 threads per CTA
+                  const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale) {
+  constexpr int N = PD_BIGN, Q = N / 4, T = Q / 16, J = Q / 4;  // T = 256 threads, J = 1024 per j-quarter
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned c = cluster.block_rank();
+  const int c = (int)cluster.block_rank();
   cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw);
-  const cplx* peer = cluster.map_shared_rank(sm, c ^ 1u);
   const int t = threadIdx.x;
-  const int64_t ncl = gridDim.x / 2;
-  for (int64_t line = blockIdx.x / 2; line < nlines; line += ncl) {
-    const cplx* gsrc = in + line * N + (int64_t)c * H;
-    cplx* gdst = out + line * N + (int64_t)c * H;
-    cplx io[16];
+  const int64_t ncl = gridDim.x / 4;
+  // barrier phase A of a line: arrive right after the last local pass has read the shared memory (inside
+  // pow2_pass), wait just before the exchange stores -- the wait is hidden behind that pass's arithmetic and
+  // global stores and the next line's global loads.  Phase B brackets the exchange.
+  cluster_arrive_relaxed();  // A of the first line: nothing to protect yet
+  for (int64_t line = blockIdx.x / 4; line < nlines; line += ncl) {
     if (TO_FREQ) {
+      const cplx* g = in + line * N + c * J + t;
+      cplx v[4][4];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        cplx x = gsrc[t + T * q];
-        if (INV) x.y = -x.y;
-        io[q] = x;
-        sm[pad16(t + T * q)] = x;
-      }
-      cluster.sync();
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const cplx o = peer[pad16(t + T * q)];
-        io[q] = c == 0 ? cadd(io[q], o) : cmul(csub(o, io[q]), tw[t + T * q]);
+        for (int m = 0; m < 4; ++m) {
+          cplx x = g[T * u + Q * m];
+          if (INV) x.y = -x.y;
+          v[u][m] = x;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dft_pow2<4>(v[u]);  // v[u][q] = sum_m x[j + Q m] (-i)^{mq}
+        const cplx w1 = tw[c * J + T * u + t];
+        const cplx w2 = cmul(w1, w1);
+        v[u][1] = cmul(v[u][1], w1);
+        v[u][2] = cmul(v[u][2], w2);
+        v[u][3] = cmul(v[u][3], cmul(w2, w1));
       }
-      cluster.sync();  // the peer has read my half before the local passes overwrite it
-      pow2_pass<16, false, true, false, true, false>(gsrc, gdst, sm, tw_half, H, 1, t, T, scale, true, io);
-      pow2_pass<16, false, false, false>(gsrc, gdst, sm, tw_half, H, 16, t, T, scale, true);
-      pow2_pass<8, false, false, false>(gsrc, gdst, sm, tw_half, H, 256, t, T, scale, true);
-      pow2_pass<4, INV, false, true>(gsrc, gdst, sm, tw_half, H, 2048, t, T, scale, true);
+      cluster_wait();  // A: every CTA of the cluster is done with the previous line
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t dst = cluster_map(sm, q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cluster_store(dst + 16u * (uint32_t)pad16(c * J + T * u + t), v[u][q]);
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();  // B: y_c is complete in this CTA's shared memory
+      cplx io[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) io[q] = sm[pad16(t + T * q)];
       __syncthreads();
+      cplx* gdst = out + line * N + (int64_t)c * Q;
+      pow2_pass<16, false, true, false, true, false>(nullptr, gdst, sm, tw_q, Q, 1, t, T, scale, true, io);
+      pow2_pass<16, false, false, false>(nullptr, gdst, sm, tw_q, Q, 16, t, T, scale, true);
+      pow2_pass<16, INV, false, true, false, false, true>(nullptr, gdst, sm, tw_q, Q, 256, t, T, scale, true);
     } else {
-      pow2_pass<16, INV, true, false>(gsrc, gdst, sm, tw_half, H, 1, t, T, scale, true);
-      pow2_pass<16, false, false, false>(gsrc, gdst, sm, tw_half, H, 16, t, T, scale, true);
-      pow2_pass<8, false, false, false>(gsrc, gdst, sm, tw_half, H, 256, t, T, scale, true);
-      pow2_pass<4, false, false, true, false, true>(gsrc, gdst, sm, tw_half, H, 2048, t, T, scale, true, io);
-      // io[u*4 + r] <-> element t + 512 u + 2048 r of this CTA's half transform
-      __syncthreads();
+      const cplx* gsrc = in + line * N + (int64_t)c * Q;
+      cplx io[16];
+      pow2_pass<16, INV, true, false>(gsrc, nullptr, sm, tw_q, Q, 1, t, T, scale, true);
+      pow2_pass<16, false, false, false>(gsrc, nullptr, sm, tw_q, Q, 16, t, T, scale, true);
+      pow2_pass<16, false, false, true, false, true, true>(gsrc, nullptr, sm, tw_q, Q, 256, t, T, scale, true, io);
+      // io[r] <-> Z_c[n'], n' = t + 256 r (the twiddle w^{n'c} is applied by the CTA that owns n')
+      cluster_wait();  // A: every CTA of the cluster is done with its local passes
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int o = 0; o < 4; ++o) {
+        const uint32_t dst = cluster_map(sm, o);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = t + T * u + 2048 * r;
-          if (c == 1) io[u * 4 + r] = cmul(io[u * 4 + r], tw[i]);  // W_N^i B[i]
-          sm[pad16(i)] = io[u * 4 + r];
-        }
-      cluster.sync();
+        for (int u = 0; u < 4; ++u) cluster_store(dst + 16u * (uint32_t)pad16(c * J + t + T * u), io[4 * o + u]);
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();  // B: slot [q][s] of this CTA = Z_q[n'], n' = 1024 c + s
+      cplx* gdst = out + line * N + c * J + t;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u) {
+        cplx v[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = t + T * u + 2048 * r;
-          const cplx o = peer[pad16(i)];
-          cplx y = c == 0 ? cadd(io[u * 4 + r], o) : csub(o, io[u * 4 + r]);
+        for (int q = 0; q < 4; ++q) v[q] = sm[pad16(q * J + T * u + t)];
+        const cplx w1 = tw[c * J + T * u + t];  // W_N^{n'}
+        const cplx w2 = cmul(w1, w1);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], cmul(w2, w1));
+        dft_pow2<4>(v);  // v[m] = x[n' + Q m]
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          cplx y = v[m];
           if (INV) y.y = -y.y;
-          gdst[i] = cscale(y, scale);
+          gdst[T * u + Q * m] = cscale(y, scale);
         }
-      cluster.sync();
+      }
+      __syncthreads();  // the combine reads are done before the next line's first pass overwrites them
     }
   }
+  // balance the last A arrive; after it no peer stores into this CTA any more (its B wait of the last line
+  // has seen every store), so the CTA may leave
+  cluster_wait();
 }
 
 // ------------------------------------------------------------ real-input fast path
@@ -479,11 +553,40 @@ int pd_fft_plan(pd_handle* h) {
   h->ws_bytes += sizeof(cplx) * (size_t)N;
   pd_twiddle_kernel<<<(N + 255) / 256, 256>>>(h->twiddle, N);
   PD_CHECK_LAUNCH();
-  if (is_pow2(N) && N >= 128) {  // N/2 table: real-input fast path and the 2-CTA kernel's half transforms
+  if (is_pow2(N) && N >= 128) {  // N/2 table: real-input fast path
     PD_CUDA(cudaMalloc(&h->twiddle_half, sizeof(cplx) * (size_t)(N / 2)));
     h->ws_bytes += sizeof(cplx) * (size_t)(N / 2);
     pd_twiddle_kernel<<<(N / 2 + 255) / 256, 256>>>(h->twiddle_half, N / 2);
     PD_CHECK_LAUNCH();
+  }
+  if (N == PD_BIGN) {
+    PD_CUDA(cudaMalloc(&h->twiddle_quarter, sizeof(cplx) * (size_t)(N / 4)));
+    h->ws_bytes += sizeof(cplx) * (size_t)(N / 4);
+    pd_twiddle_kernel<<<(N / 4 + 255) / 256, 256>>>(h->twiddle_quarter, N / 4);
+    PD_CHECK_LAUNCH();
+    const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    // co-resident 4-CTA clusters (GPC boundaries keep this a little below num_sms * 2 / 4: 71 on B200)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(4 * (unsigned)h->num_sms, 1, 1);
+    lc.blockDim = dim3(256, 1, 1);
+    lc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, pd_fft_16k_kernel<true, true>, &lc) != cudaSuccess) {
+      cudaGetLastError();
+      ncl = 0;
+    }
+    h->fft16k_clusters = ncl;
   }
   PassList pl;
   factorize(N, pl);
@@ -530,19 +633,18 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
 }
 
 static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
-  const size_t smem = (size_t)(PD_BIGN / 2 + PD_BIGN / 32) * sizeof(cplx);
-  int64_t ncl = nlines < (int64_t)h->num_sms * 4 ? nlines : (int64_t)h->num_sms * 4;
   const double scale = inverse ? 1.0 / (double)PD_BIGN : 1.0;
-  // inverse (time -> frequency, :500-501) leaves the even/odd frequency order, forward (:547-548) consumes it
-  if (inverse) {
-    auto k = pd_fft_16k_kernel<true, true>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)(2 * ncl), 512, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half, scale);
-  } else {
-    auto k = pd_fft_16k_kernel<false, false>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)(2 * ncl), 512, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half, scale);
-  }
+  // inverse (time -> frequency, :500-501) leaves the permuted frequency order, forward (:547-548) consumes it.
+  // 4-CTA clusters, persistent over the lines: as many clusters as can be co-resident
+  const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
+  int64_t ncl = h->fft16k_clusters > 0 ? h->fft16k_clusters : h->num_sms / 2;
+  if (ncl > nlines) ncl = nlines;
+  if (inverse)
+    pd_fft_16k_kernel<true, true><<<(unsigned)(4 * ncl), 256, smem, st>>>(in, out, nlines, h->twiddle,
+                                                                         h->twiddle_quarter, scale);
+  else
+    pd_fft_16k_kernel<false, false><<<(unsigned)(4 * ncl), 256, smem, st>>>(in, out, nlines, h->twiddle,
+                                                                           h->twiddle_quarter, scale);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;

@@ -63,7 +63,7 @@ struct SolveParams {
   // Single-GPU: row 0 and row m+1 are the Dirichlet nodes.  Slab mode (x-slab r of G): row 0 is the
   // inter-slab separator (r > 0) and the last body row is followed by the next slab's separator (r < G-1).
   int first_dirichlet, last_dirichlet;
-  int freq_perm;  // 1: columns hold [even k | odd k] (the N_t = 16384 FFT kernel's frequency order)
+  int freq_perm;  // 1: columns hold [k mod 4 = 0 | 1 | 2 | 3] (the N_t = 16384 FFT kernel's frequency order)
   int koff, kend; // column range [koff, kend) this launch works on (row stride stays K)
 };
 
@@ -85,8 +85,8 @@ struct KCoef {
 __device__ __forceinline__ int freq_of(const SolveParams& sp, int kk) {
   const int col = sp.kbegin + kk;
   if (!sp.freq_perm) return col;
-  const int half = sp.N_t >> 1;
-  return col < half ? 2 * col : 2 * (col - half) + 1;
+  const int quarter = sp.N_t >> 2;
+  return 4 * (col & (quarter - 1)) + col / quarter;
 }
 
 __device__ __forceinline__ KCoef make_coef(int kglob, const SolveParams& sp) {

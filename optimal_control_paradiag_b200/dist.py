@@ -172,6 +172,25 @@ class DistributedDiagFFTPC:
         self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * self.n_r, False)     # :547-548
         return y_local
 
+    def apply_host(self, x_host, y_host):
+        """The same apply for node-slab blocks that live in HOST memory (what a PETSc ``Vec`` of a spatial
+        decomposition hands the PC, :493-497 / :552-553): H2D of this rank's block, apply, D2H.
+        ``x_host`` / ``y_host``: complex128 torch CPU tensors (pinned for full PCIe rate) or numpy arrays."""
+        t = self.torch
+        if isinstance(x_host, np.ndarray):
+            x_host = t.from_numpy(x_host)
+        if isinstance(y_host, np.ndarray):
+            y_host = t.from_numpy(y_host)
+        if getattr(self, "_xdev", None) is None:
+            self._xdev = t.empty(self.local_size, dtype=t.complex128, device=self.device)
+            self._ydev = t.empty(self.local_size, dtype=t.complex128, device=self.device)
+        self._xdev.copy_(x_host.reshape(-1), non_blocking=True)
+        self.apply(self._xdev, self._ydev)
+        y_host.reshape(-1).copy_(self._ydev, non_blocking=True)
+        if self.device.type == "cuda":
+            t.cuda.current_stream(self.device).synchronize()
+        return y_host
+
     # ------------------------------------------------------------------ distributed Krylov solve
     def build_rhs(self):
         """This rank's block of the manufactured right-hand side (Build_f/g/IC, :48-83)."""

@@ -170,6 +170,10 @@ def _worker(rank, world, port, N_x, N_t, gamma, ret, mode="alltoall"):
         yg = dpc.gather_to_global(y_local).numpy()
         ref = DiagFFTPCFast(N_x, N_t, 2.0, gamma).apply(xg)
         err = np.linalg.norm(yg - ref) / np.linalg.norm(ref)
+        # host-buffer entry point (numpy blocks in, numpy blocks out): same result
+        yh = np.empty(dpc.local_size, dtype=complex)
+        dpc.apply_host(x_local.numpy().copy(), yh)
+        err = max(err, float(np.abs(yh - y_local.numpy()).max()))
         d = dpc.describe()
         ok = err < 1e-11 and sum(d["node_slabs"]) == N_x + 1 and (mode == "slab" or sum(d["freq_slabs"]) == N_t)
         ret[rank] = (bool(ok), float(err))

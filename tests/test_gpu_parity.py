@@ -46,8 +46,9 @@ def test_fft_matches_scipy(N_t):
         xt = torch.tensor(x, device=DEV).reshape(-1)
         yt = torch.empty_like(xt)
         if N_t == 16384:
-            # 2-CTA kernel: time -> frequency leaves [even k | odd k]; frequency -> time consumes it
-            perm = np.concatenate([np.arange(0, N_t, 2), np.arange(1, N_t, 2)])
+            # 4-CTA cluster kernel: time -> frequency leaves [k = 0 mod 4 | 1 | 2 | 3]; frequency -> time
+            # consumes that order
+            perm = np.concatenate([np.arange(q, N_t, 4) for q in range(4)])
             h.stage_fft(xt, yt, nl, True)
             assert rel(yt.cpu().numpy().reshape(nl, N_t), sfft.ifft(x, axis=1)[:, perm]) < 5e-15
             xp = torch.tensor(np.ascontiguousarray(x[:, perm]), device=DEV).reshape(-1)
