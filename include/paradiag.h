@@ -55,8 +55,13 @@ typedef struct pd_config {
   double T;            /* final time (:335)                                      */
   double gamma;        /* regulariser (:339); the sqrt(gamma) scaling of the
                           pc=True formulation is built in (:56-57, :78-80, :87)  */
-  double alpha;        /* alpha-circulant weight; 1.0 = the upstream operator.
-                          Other values are an extension with no upstream pin.   */
+  double alpha;        /* alpha-circulant weight in (0, 1]; 1.0 = the upstream operator.
+                          Other values are an EXTENSION with no upstream pin (the
+                          reference has no alpha): Gamma_alpha time weights around
+                          the FFTs and alpha-shifted symbols in the per-frequency
+                          stage, defined in oracle/pc_alpha.py.  Single-GPU complex
+                          apply / GMRES only; sharded handles, the real-input path
+                          and pd_pc_matvec return PD_ERR_UNSUPPORTED.            */
   int32_t device;      /* CUDA device ordinal                                    */
   /* Frequency shard solved by this handle in pd_stage_solve (multi-GPU):
    * global frequencies [k_begin, k_begin + k_count).  k_count = 0 means all.   */
@@ -123,6 +128,10 @@ int pd_pc_apply_transpose(pd_handle* h, const void* x_dev, void* y_dev, void* st
  *                    :512), S rotation (:516-529) and 1/lambda_2 (:532-540).     */
 int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines,
                  int inverse, void* stream);
+/* alpha != 1 only: the Gamma_alpha time-weight scaling of `nlines` lines, out[l][j] = in[l][j] a^(+-j)
+ * with a = alpha^(1/N_t) (inverse == 0: Gamma before the inverse FFT; inverse != 0: Gamma^-1 after the
+ * forward FFT).  in == out ok.  With alpha = 1 it copies nothing and returns PD_OK.                   */
+int pd_stage_gamma(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int inverse, void* stream);
 int pd_stage_solve(pd_handle* h, void* w_dev, void* stream);
 
 /* Slab mode: the per-frequency solves with the x-direction distributed over `slab_count` ranks

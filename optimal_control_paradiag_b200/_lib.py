@@ -49,6 +49,7 @@ SYMBOLS = {
     "pd_pc_apply_profile": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_float), _I]),
     "pd_pc_apply_transpose": (_I, [_VP, _VP, _VP, _VP]),
     "pd_stage_fft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
+    "pd_stage_gamma": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "pd_stage_solve": (_I, [_VP, _VP, _VP]),
     "pd_slab_reduce": (_I, [_VP, _VP, _VP, _VP]),
     "pd_slab_finish": (_I, [_VP, _VP, _VP, _VP]),

@@ -29,6 +29,7 @@ extern "C" int pd_destroy(pd_handle* h) {
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->twiddle_half) cudaFree(h->twiddle_half);
   if (h->twiddle_quarter) cudaFree(h->twiddle_quarter);
+  if (h->gamma_tab) cudaFree(h->gamma_tab);
   pd_solve_free(h);
 
   if (h->work) cudaFree(h->work);
@@ -58,9 +59,15 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
     pd_set_error("pd_create: T and gamma must be positive");
     return PD_ERR_INVALID;
   }
-  if (cfg->alpha != 1.0) {
-    pd_set_error("pd_create: alpha = %g is not supported; the upstream preconditioner is the alpha = 1 "
-                 "block circulant and has no alpha", cfg->alpha);
+  // alpha != 1 is an extension (the upstream preconditioner is the alpha = 1 block circulant and has no alpha;
+  // definition in oracle/pc_alpha.py): single-GPU complex apply / GMRES only
+  if (!(cfg->alpha > 0.0) || cfg->alpha > 1.0) {
+    pd_set_error("pd_create: alpha = %g outside (0, 1]", cfg->alpha);
+    return PD_ERR_INVALID;
+  }
+  if (cfg->alpha != 1.0 && (cfg->k_count > 0 || cfg->n_local > 0 || cfg->slab_count > 1)) {
+    pd_set_error("pd_create: alpha = %g on a sharded handle is not supported (alpha != 1 is single-GPU only)",
+                 cfg->alpha);
     return PD_ERR_UNSUPPORTED;
   }
   int ndev = 0;
@@ -147,6 +154,15 @@ extern "C" int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int
   return pd_fft_launch(h, (const cplx*)in_dev, (cplx*)out_dev, nlines, inverse, (cudaStream_t)stream);
 }
 
+extern "C" int pd_stage_gamma(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int inverse,
+                              void* stream) {
+  if (!h || !in_dev || !out_dev || nlines < 0) {
+    pd_set_error("pd_stage_gamma: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  return pd_gamma_launch(h, (const cplx*)in_dev, (cplx*)out_dev, nlines, inverse, (cudaStream_t)stream);
+}
+
 extern "C" int pd_stage_solve(pd_handle* h, void* w_dev, void* stream) {
   if (!h || !w_dev) {
     pd_set_error("pd_stage_solve: invalid argument");
@@ -184,6 +200,14 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
   int rc = ensure_work(h);
   if (rc) return rc;
   const int64_t nlines = 2 * (int64_t)h->n;
+  if (h->cfg.alpha != 1.0) {
+    // extension: Gamma, ifft, alpha-shifted per-frequency stage, fft, Gamma^-1 (two extra elementwise sweeps)
+    if ((rc = pd_gamma_launch(h, (const cplx*)x_dev, h->work, nlines, 0, st))) return rc;
+    if ((rc = pd_fft_launch(h, h->work, h->work, nlines, 1, st))) return rc;
+    if ((rc = pd_solve_launch(h, h->work, st))) return rc;
+    if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
+    return pd_gamma_launch(h, (const cplx*)y_dev, (cplx*)y_dev, nlines, 1, st);
+  }
   // :500-501 ifft along time, :445-540 per-frequency stage, :547-548 fft along time
   if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st))) return rc;
   if ((rc = pd_solve_launch(h, h->work, st))) return rc;
@@ -200,6 +224,10 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
   if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
     pd_set_error("pd_pc_apply_profile: handle is sharded");
     return PD_ERR_INVALID;
+  }
+  if (h->cfg.alpha != 1.0) {
+    pd_set_error("pd_pc_apply_profile: alpha != 1 is not covered by the per-stage profile");
+    return PD_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_work(h);
@@ -235,6 +263,10 @@ extern "C" int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream) {
     pd_set_error("pd_stage_solve_half: invalid argument or sharded handle");
     return PD_ERR_INVALID;
   }
+  if (h->cfg.alpha != 1.0) {
+    pd_set_error("pd_stage_solve_half: alpha != 1 is not supported on the real-input path");
+    return PD_ERR_UNSUPPORTED;
+  }
   return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream, nullptr, 1);
 }
 
@@ -246,6 +278,10 @@ extern "C" int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, vo
   if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
     pd_set_error("pd_pc_apply_real: handle is sharded; the real-input path is single-GPU");
     return PD_ERR_INVALID;
+  }
+  if (h->cfg.alpha != 1.0) {
+    pd_set_error("pd_pc_apply_real: alpha != 1 is not supported on the real-input path; use pd_pc_apply");
+    return PD_ERR_UNSUPPORTED;
   }
   if (!pd_rfft_supported(h)) {
     pd_set_error("pd_pc_apply_real: needs a power-of-two N_t in [128, 16384] (got %d); use pd_pc_apply", h->cfg.N_t);
@@ -319,6 +355,10 @@ extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* 
   if (!h || !x_dev || !y_dev || x_dev == y_dev) {
     pd_set_error("pd_pc_matvec: invalid argument (x and y must be distinct device vectors)");
     return PD_ERR_INVALID;
+  }
+  if (h->cfg.alpha != 1.0) {
+    pd_set_error("pd_pc_matvec: only the alpha = 1 block circulant has a matvec kernel");
+    return PD_ERR_UNSUPPORTED;
   }
   return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 1);
 }

@@ -84,6 +84,7 @@ struct pd_handle {
   cplx* twiddle_half;     // same for N_t / 2 (power-of-two N_t >= 128: real-input path)
   cplx* twiddle_quarter;  // same for N_t / 4 (only N_t = 16384: the 4-CTA cluster kernel)
   int fft16k_clusters;    // co-resident 4-CTA clusters (grid of the persistent 16k kernel)
+  double* gamma_tab;      // alpha != 1 only: a^j (N_t entries) followed by a^-j, a = alpha^(1/N_t)
   int fft_kind;   // 0 generic smem Stockham, 1 power-of-two register kernel
   int npass;
   int radix[PD_MAX_FFT_PASSES];
@@ -119,6 +120,7 @@ struct pd_handle {
 int pd_fft_plan(pd_handle* h);
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
                   cudaStream_t st);
+int pd_gamma_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st);
 bool pd_rfft_supported(const pd_handle* h);
 int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st);
 int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st);

@@ -28,6 +28,26 @@ __global__ void pd_twiddle_kernel(cplx* tw, int N) {
   }
 }
 
+// ---------------------------------------------------- Gamma_alpha time weights (alpha != 1, an extension)
+// The upstream operator has no alpha; with pd_config.alpha != 1 the apply becomes
+// Gamma^-1 fft_t [ per-frequency solves with alpha-shifted symbols ] ifft_t Gamma,  Gamma = diag(a^j),
+// a = alpha^(1/N_t) (oracle/pc_alpha.py).  gam[0][j] = a^j, gam[1][j] = a^-j.
+__global__ void pd_gamma_table_kernel(double* gam, int N, double lna) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) {
+    gam[j] = exp(lna * (double)j);
+    gam[N + j] = exp(-lna * (double)j);
+  }
+}
+// out[line][j] = in[line][j] * g[j]; one thread per element, lines are contiguous (in == out allowed)
+__global__ void __launch_bounds__(256)
+pd_gamma_scale_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t total, int N,
+                      const double* __restrict__ g) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    out[i] = cscale(in[i], g[(int)(i % N)]);
+}
+
 struct PassList {
   int n;
   int r[PD_MAX_FFT_PASSES];
@@ -315,7 +335,10 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
 // so no reordering pass exists.  Measured alternatives (B200): a 2-CTA cluster of
 // 8192-point pipelines reading the peer's half through distributed shared memory (one CTA per SM) reached
 // 2.5 TB/s against 3.1-3.4 TB/s here; st.async + mbarrier instead of the release/acquire barrier, an L2
-// prefetch of the next line and three CTAs per SM (80 registers) each measured equal or slower.
+// prefetch of the next line, three CTAs per SM (80 registers) and 512-thread CTAs with radix-8 passes (32 warps
+// per SM, one more exchange) each measured equal or slower.  Without the exchange and the barriers the same
+// pipeline streams at 4.9 TB/s: the cluster coupling, not a saturated unit, is what is left (ncu: no pipe above
+// 50 %).
 #define PD_BIGN 16384
 template <bool INV, bool TO_FREQ>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 2)
@@ -588,6 +611,12 @@ int pd_fft_plan(pd_handle* h) {
     }
     h->fft16k_clusters = ncl;
   }
+  if (h->cfg.alpha != 1.0) {
+    PD_CUDA(cudaMalloc(&h->gamma_tab, sizeof(double) * 2 * (size_t)N));
+    h->ws_bytes += sizeof(double) * 2 * (size_t)N;
+    pd_gamma_table_kernel<<<(N + 255) / 256, 256>>>(h->gamma_tab, N, log(h->cfg.alpha) / (double)N);
+    PD_CHECK_LAUNCH();
+  }
   PassList pl;
   factorize(N, pl);
   h->npass = pl.n;
@@ -844,6 +873,20 @@ int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int 
   }
   pd_set_error("pd_rfft_launch: unsupported N_t %d", h->cfg.N_t);
   return PD_ERR_UNSUPPORTED;
+}
+
+// Gamma (inverse = 0) or Gamma^-1 (inverse = 1) on `nlines` time lines
+int pd_gamma_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
+  if (nlines <= 0 || !h->gamma_tab) return PD_OK;
+  const int N = h->cfg.N_t;
+  const int64_t total = nlines * N;
+  int64_t nblk = (total + 255) / 256;
+  const int64_t cap = (int64_t)h->num_sms * 32;
+  if (nblk > cap) nblk = cap;
+  pd_gamma_scale_kernel<<<(unsigned)nblk, 256, 0, st>>>(in, out, total, N, h->gamma_tab + (inverse ? N : 0));
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
 }
 
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,

@@ -65,6 +65,8 @@ struct SolveParams {
   int first_dirichlet, last_dirichlet;
   int freq_perm;  // 1: columns hold [k mod 4 = 0 | 1 | 2 | 3] (the N_t = 16384 FFT kernel's frequency order)
   int koff, kend; // column range [koff, kend) this launch works on (row stride stays K)
+  int al;         // 1: alpha != 1 (extension, see make_coef<true>); 0: the upstream operator
+  double lna;     // ln(alpha) / N_t
 };
 
 // Slab-mode extras (device pointers; all null in single-GPU mode)
@@ -77,8 +79,14 @@ struct SlabPtrs {
 struct KCoef {
   cplx a;        // off-diagonal of Tt (the diagonal is b = sh - 2a)
   cplx sh;       // s h = b + 2a: the detuning from the discrete resonance, cancellation-free
+  // rotation, alpha = 1 (the upstream operator)
   cplx zc;       // conj(z) = e^{-i theta}
   double sigma;  // sign(cos theta)
+  // rotation, alpha != 1 (general 2x2 eigen-decomposition, see make_coef<true>)
+  double gp, gm;    // g_+- = (d +- beta) / (2 d)
+  cplx e;           // i c e^{i phi} / (2 d)
+  cplx eic;         // e^{-i phi}
+  double bmd, bpd;  // (beta -+ d) / c
 };
 
 // frequency index of column `kk` of this handle's frequency block
@@ -89,35 +97,82 @@ __device__ __forceinline__ int freq_of(const SolveParams& sp, int kk) {
   return 4 * (col & (quarter - 1)) + col / quarter;
 }
 
+// AL = false: the upstream (alpha = 1) operator, division-free closed forms.
+// AL = true : the alpha extension (oracle/pc_alpha.py; no upstream counterpart).  With a = alpha^(1/N_t),
+//   l1 = (1 - a z)^2,  l2 = 1 + a^2 z^2 = |l2| e^{i phi},  mu = l1 e^{-i phi},  beta = Im mu,  d = sqrt(beta^2 + c^2):
+//   Tt = s M + kap K,  s = Re mu + i d,  kap = dt^2/2 |l2|   (conj(Tt) serves the second eigenvalue)
+//   rho_+ = g_+ uh + e ph,  rho_- = g_- uh - e ph;  wh_u = e^{-i phi}(zeta_+ + zeta_-),
+//   wh_p = i [(beta - d) zeta_+ + (beta + d) zeta_-] / c.     |l2| >= 1 - a^2 > 0 for alpha < 1.
+// Unused members are dead code in each instantiation (everything is inlined).
+template <bool AL>
 __device__ __forceinline__ KCoef make_coef(int kglob, const SolveParams& sp) {
   KCoef kc;
   double st, ct, sh, chh;
   sincospi(2.0 * (double)kglob / (double)sp.N_t, &st, &ct);
   sincospi((double)kglob / (double)sp.N_t, &sh, &chh);
-  kc.sigma = ct >= 0.0 ? 1.0 : -1.0;
-  const double sre = -4.0 * sh * sh;
-  const double sim = sp.c * kc.sigma;
-  const double kap = sp.dt2 * ct;
-  kc.a = cmake(sre * (sp.h / 6.0) - kap / sp.h, sim * (sp.h / 6.0));
-  kc.sh = cmake(sre * sp.h, sim * sp.h);  // b + 2a = s (2h/3 + 2 h/6): the stiffness parts cancel exactly
-  kc.zc = cmake(ct, -st);
+  if (!AL) {
+    kc.sigma = ct >= 0.0 ? 1.0 : -1.0;
+    const double sre = -4.0 * sh * sh;
+    const double sim = sp.c * kc.sigma;
+    const double kap = sp.dt2 * ct;
+    kc.a = cmake(sre * (sp.h / 6.0) - kap / sp.h, sim * (sp.h / 6.0));
+    kc.sh = cmake(sre * sp.h, sim * sp.h);  // b + 2a = s (2h/3 + 2 h/6): the stiffness parts cancel exactly
+    kc.zc = cmake(ct, -st);
+  } else {
+    const double a = exp(sp.lna), oma = -expm1(sp.lna), oma2 = -expm1(2.0 * sp.lna);  // a, 1 - a, 1 - a^2
+    const cplx q = cmake(oma + 2.0 * a * sh * sh, -a * st);                              // 1 - a z
+    const cplx l1 = cmul(q, q);
+    const cplx l2 = cmake(oma2 + 2.0 * a * a * ct * ct, 2.0 * a * a * st * ct);
+    const double al2 = sqrt(l2.x * l2.x + l2.y * l2.y);
+    const cplx eiphi = cmake(l2.x / al2, l2.y / al2);
+    const cplx mu = cmulc(l1, eiphi);  // l1 e^{-i phi}
+    const double beta = mu.y, d = sqrt(beta * beta + sp.c * sp.c);
+    const double kap = 0.5 * sp.dt2 * al2;
+    kc.a = cmake(mu.x * (sp.h / 6.0) - kap / sp.h, d * (sp.h / 6.0));
+    kc.sh = cmake(mu.x * sp.h, d * sp.h);
+    const double i2d = 0.5 / d;
+    kc.gp = (d + beta) * i2d;
+    kc.gm = (d - beta) * i2d;
+    kc.e = cmake(-sp.c * eiphi.y * i2d, sp.c * eiphi.x * i2d);  // i c e^{i phi} / (2 d)
+    kc.eic = cconj(eiphi);
+    kc.bmd = (beta - d) / sp.c;
+    kc.bpd = (beta + d) / sp.c;
+  }
   return kc;
+}
+// kernels that only need (a, sh): one run-time switch
+__device__ __forceinline__ KCoef make_coef(int kglob, const SolveParams& sp) {
+  return sp.al ? make_coef<true>(kglob, sp) : make_coef<false>(kglob, sp);
 }
 
 // rho_+ and conj(rho_-) from (u-hat, p-hat)
+template <bool AL>
 __device__ __forceinline__ void rotate_in(const KCoef& kc, cplx u, cplx p, cplx& rp, cplx& rm) {
-  cplx uz = cmul(u, kc.zc);
-  cplx ip = cmake(-p.y * kc.sigma, p.x * kc.sigma);  // i sigma p
-  rp = cmake(0.5 * (uz.x + ip.x), 0.5 * (uz.y + ip.y));
-  rm = cmake(0.5 * (uz.x - ip.x), -0.5 * (uz.y - ip.y));  // conjugated
+  if (!AL) {
+    cplx uz = cmul(u, kc.zc);
+    cplx ip = cmake(-p.y * kc.sigma, p.x * kc.sigma);  // i sigma p
+    rp = cmake(0.5 * (uz.x + ip.x), 0.5 * (uz.y + ip.y));
+    rm = cmake(0.5 * (uz.x - ip.x), -0.5 * (uz.y - ip.y));  // conjugated
+  } else {
+    const cplx ep = cmul(kc.e, p);
+    rp = cmake(kc.gp * u.x + ep.x, kc.gp * u.y + ep.y);
+    rm = cmake(kc.gm * u.x - ep.x, -(kc.gm * u.y - ep.y));  // conjugated
+  }
 }
 // (w_u, w_p) from zeta_+ and conj(zeta_-)
+template <bool AL>
 __device__ __forceinline__ void rotate_out(const KCoef& kc, cplx zp, cplx zmc, cplx& wu, cplx& wp) {
   cplx zm = cconj(zmc);
-  wu = cadd(zp, zm);
-  cplx d = csub(zp, zm);
-  cplx t = cmulc(d, kc.zc);                         // d * z
-  wp = cmake(t.y * kc.sigma, -t.x * kc.sigma);      // -i sigma (d z)
+  if (!AL) {
+    wu = cadd(zp, zm);
+    cplx d = csub(zp, zm);
+    cplx t = cmulc(d, kc.zc);                         // d * z
+    wp = cmake(t.y * kc.sigma, -t.x * kc.sigma);      // -i sigma (d z)
+  } else {
+    wu = cmul(kc.eic, cadd(zp, zm));
+    const cplx t = cmake(kc.bmd * zp.x + kc.bpd * zm.x, kc.bmd * zp.y + kc.bpd * zm.y);
+    wp = cmake(-t.y, t.x);                            // i t
+  }
 }
 
 // A level system: tridiag(off, d, off) with n rows, d = dmain except the last row (dlast).
@@ -254,6 +309,7 @@ struct Levels {
 };
 
 // ------------------------------------------------------------------- pass A
+template <bool AL>
 __global__ void __launch_bounds__(PD_KB, 4)
 pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
                       SolveParams sp, cplx* __restrict__ lastl) {
@@ -262,7 +318,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
   const bool valid = kk < sp.kend;
   const int kc_idx = valid ? kk : sp.kend - 1;
-  const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
+  const KCoef kc = make_coef<AL>(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   const cplx* wu = w + kc_idx;
   const cplx* wp = w + sp.plane + kc_idx;
@@ -302,7 +358,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
           const int i = base + r;
           if (i < Lc) {
             cplx rP, rM;
-            rotate_in(kc, bu[half][r], bp[half][r], rP, rM);
+            rotate_in<AL>(kc, bu[half][r], bp[half][r], rP, rM);
             const cplx mi = mtab[i][tid];
             if (i > 0) {
               const cplx cp = cmul(kc.a, mtab[i - 1][tid]);  // c'_{i-1}
@@ -313,7 +369,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
             fP = cfma(pi, dP, fP);
             fM = cfma(pi, dM, fM);
           } else if (i == PD_L && c < P) {
-            rotate_in(kc, bu[half][r], bp[half][r], sP, sM);
+            rotate_in<AL>(kc, bu[half][r], bp[half][r], sP, sM);
           }
         }
       }
@@ -567,7 +623,7 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
 }
 
 // ------------------------------------------------------------------- pass B
-template <bool SLAB>
+template <bool SLAB, bool AL>
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp, SlabPtrs sl) {
   __shared__ cplx mtab[PD_L][PD_KB];
@@ -575,7 +631,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
   const bool valid = kk < sp.kend;
   const int kc_idx = valid ? kk : sp.kend - 1;
-  const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
+  const KCoef kc = make_coef<AL>(freq_of(sp, kc_idx), sp);
   fill_pivots(kc, mtab, tid);
   cplx* wu = w + kc_idx;
   cplx* wp = w + sp.plane + kc_idx;
@@ -642,7 +698,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
     for (int i = 0; i < PD_L; ++i) {
       if (i < Lc) {
         cplx rP, rM;
-        rotate_in(kc, dP[i], dM[i], rP, rM);
+        rotate_in<AL>(kc, dP[i], dM[i], rP, rM);
         if (i == Lc - 1) {
           rP = cfms(kc.a, zrP, rP);
           rM = cfms(kc.a, zrM, rM);
@@ -668,7 +724,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
           nM = dM[i];
         }
         cplx ou, op;
-        rotate_out(kc, nP, nM, ou, op);
+        rotate_out<AL>(kc, nP, nM, ou, op);
         if (valid) {
           wu[(int64_t)(j0 + i) * sp.K] = ou;
           wp[(int64_t)(j0 + i) * sp.K] = op;
@@ -677,7 +733,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
     }
     if (valid && c < P) {  // the separator row that follows this chunk
       cplx ou, op;
-      rotate_out(kc, zrP, zrM, ou, op);
+      rotate_out<AL>(kc, zrP, zrM, ou, op);
       wu[(int64_t)(j0 + PD_L) * sp.K] = ou;
       wp[(int64_t)(j0 + PD_L) * sp.K] = op;
     }
@@ -685,7 +741,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
     // inter-slab separator this rank owns
     if (valid && c == 0) {
       cplx ou = zero, op = zero;
-      if (SLAB && !sp.first_dirichlet) rotate_out(kc, oLP, oLM, ou, op);
+      if (SLAB && !sp.first_dirichlet) rotate_out<AL>(kc, oLP, oLM, ou, op);
       wu[0] = ou;
       wp[0] = op;
     }
@@ -741,7 +797,7 @@ pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp
     }
   }
   cplx sP = cmake(0, 0), sM = cmake(0, 0);
-  if (!sp.first_dirichlet) rotate_in(kc, w[kk], w[sp.plane + kk], sP, sM);
+  if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
   out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
   out[4 * K + kk] = sP; out[5 * K + kk] = sM;
 }
@@ -893,6 +949,8 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
   sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
   sp.freq_perm = h->cfg.N_t == 16384 && !half_spectrum;
+  sp.al = h->cfg.alpha != 1.0;
+  sp.lna = log(h->cfg.alpha) / (double)h->cfg.N_t;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = pl->green; sl.zout = pl->zout;
@@ -1018,7 +1076,10 @@ static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, 
   sp.kend = kend;
   const dim3 grid0 = stream_grid(h, kend - koff, sp.rows[1] + 1);
   if (sp.nlev >= 1) {
-    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+    if (sp.al)
+      pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+    else
+      pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
@@ -1030,7 +1091,10 @@ static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, 
     cudaEventRecord(ev[0], st);
     cudaEventRecord(ev[1], st);
   }
-  pd_solve_passB_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  if (sp.al)
+    pd_solve_passB_kernel<false, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  else
+    pd_solve_passB_kernel<false, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1053,7 +1117,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st) {
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
   SolvePlan* pl = plan_of(h);
   if (sp.nlev >= 1) {
-    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+    pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
     int rc = run_interface(h, sp, lv, st);
@@ -1062,7 +1126,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st) {
     // a single chunk: its first / last entries come from one forward sweep; reuse pass A with a
     // private F buffer (zout is free at this point: 4K entries >= 2K)
     lv.F[0] = pl->zout;
-    pd_solve_passA_kernel<<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+    pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
   }
@@ -1081,7 +1145,7 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
   pd_slab_global_kernel<<<kblocks, PD_KB, 0, st>>>(gathered, sp, pl->sg, pl->slabcoef, pl->zout);
   PD_CHECK_LAUNCH();
-  pd_solve_passB_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches += 2;
   return PD_OK;

@@ -143,6 +143,13 @@ class ParaDiagHandle:
                                     self._stream()))
         return dst
 
+    def stage_gamma(self, src, dst, nlines, inverse):
+        """Gamma_alpha (inverse False) / Gamma_alpha^-1 (inverse True) time weights; alpha != 1 only."""
+        check(self.lib.pd_stage_gamma(self._h, self._ptr(src, nlines * self.N_t, "src"),
+                                      self._ptr(dst, nlines * self.N_t, "dst"), int(nlines), int(bool(inverse)),
+                                      self._stream()))
+        return dst
+
     def stage_solve(self, w):
         check(self.lib.pd_stage_solve(self._h, self._ptr(w, 2 * self.n * self.k_count, "w"), self._stream()))
         return w

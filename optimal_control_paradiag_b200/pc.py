@@ -13,7 +13,8 @@ problem description (N_x, N_t, T, gamma) is looked up, in this order:
 1. a Firedrake ``appctx`` (``get_appctx(pc)``) with key ``"paradiag"`` (a dict) or the keys
    ``N_x, N_t, T, gamma`` directly, when Firedrake's ``PCBase`` is the base class;
 2. PC-local options under the prefix PETSc hands the PC (``pc.getOptionsPrefix()``):
-   ``<prefix>diagfft_nx``, ``..._nt``, ``..._T``, ``..._gamma``, ``..._device``;
+   ``<prefix>diagfft_nx``, ``..._nt``, ``..._T``, ``..._gamma``, ``..._device``, ``..._alpha``
+   (alpha != 1 is an extension with no upstream counterpart, see oracle/pc_alpha.py);
 3. ``DiagFFTPC.configure(...)`` class-level defaults;
 4. the globals ``N_x, N_t, T, gamma`` of ``__main__`` (how the upstream script itself is laid out).
 
@@ -101,7 +102,7 @@ class DiagFFTPC(PCBase):
     def configure(cls, **kw):
         """Class-level problem description (replaces the module globals :362-368)."""
         for k in kw:
-            if k not in _KEYS + ("device", "node_order", "bug138"):
+            if k not in _KEYS + ("device", "node_order", "bug138", "alpha"):
                 raise TypeError(f"unknown DiagFFTPC option {k!r}")
         cls._defaults = dict(cls._defaults, **kw)
 
@@ -119,12 +120,15 @@ class DiagFFTPC(PCBase):
         dev = _options_lookup(pc, "diagfft_device", int)
         if dev is not None:
             cfg["device"] = dev
+        al = _options_lookup(pc, "diagfft_alpha", float)
+        if al is not None:
+            cfg["alpha"] = al
         try:                                                         # 1. appctx
             ctx = self.get_appctx(pc) or {}
         except Exception:
             ctx = {}
         sub = ctx.get("paradiag", {}) if hasattr(ctx, "get") else {}
-        for k in _KEYS + ("device", "node_order", "bug138"):
+        for k in _KEYS + ("device", "node_order", "bug138", "alpha"):
             if k in sub:
                 cfg[k] = sub[k]
             elif hasattr(ctx, "get") and k in ctx:
@@ -150,7 +154,9 @@ class DiagFFTPC(PCBase):
             if sorted(self.node_order.tolist()) != list(range(self.n)):
                 raise ValueError("node_order must be a permutation of range(N_x + 1)")
             self._inv_order = np.argsort(self.node_order)
-        self.handle = ParaDiagHandle(self.N_x, self.N_t, T=self.T, gamma=self.gamma,
+        # alpha: extension (the upstream PC is the alpha = 1 block circulant); 1.0 unless asked for
+        self.alpha = float(cfg.get("alpha", 1.0))
+        self.handle = ParaDiagHandle(self.N_x, self.N_t, T=self.T, gamma=self.gamma, alpha=self.alpha,
                                      bug138=cfg.get("bug138", True), device=int(cfg.get("device", 0)))
         self.initialized = True
 
@@ -171,6 +177,7 @@ class DiagFFTPC(PCBase):
                 raise NotImplementedError("node_order is only supported on the host-Vec path")
             if x.dtype == torch.float64:
                 # real vectors (what GMRES feeds the PC in this problem): half-spectrum fast path
+                # (alpha = 1 only; the library answers PD_ERR_UNSUPPORTED otherwise)
                 self.handle.pc_apply_real(x.reshape(-1), y.reshape(-1))
             else:
                 self.handle.pc_apply(x.reshape(-1), y.reshape(-1))
