@@ -545,6 +545,18 @@ pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nl
 }
 
 // --------------------------------------------------------------- host side
+// cudaFuncSetAttribute once per kernel instantiation and device instead of on every launch (the launch-bound
+// small configurations pay for every host call)
+#define PD_SET_SMEM_ONCE(kernel, bytes)                                                                  \
+  do {                                                                                                   \
+    static unsigned long long pd_done_mask = 0;                                                          \
+    const int pd_dev = h->cfg.device & 63;                                                               \
+    if (!(pd_done_mask >> pd_dev & 1ull)) {                                                              \
+      PD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      pd_done_mask |= 1ull << pd_dev;                                                                    \
+    }                                                                                                    \
+  } while (0)
+
 static void factorize(int N, PassList& pl) {
   pl.n = 0;
   int rem = N;
@@ -629,10 +641,12 @@ int pd_fft_plan(pd_handle* h) {
                    smem);
       return PD_ERR_INVALID;
     }
+    // the limit is a property of the kernel, shared by every handle of the process: always the maximum, so
+    // that a later handle with a smaller N_t cannot lower it under an earlier one
     PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+                                 227 * 1024));
     PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+                                 227 * 1024));
   }
   return PD_OK;
 }
@@ -649,11 +663,11 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   double scale = inverse ? 1.0 / (double)N : 1.0;
   if (inverse) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
   } else {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
   }
   PD_CHECK_LAUNCH();
@@ -803,11 +817,11 @@ static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nno
   int64_t nblk = (nnodes + lpb - 1) / lpb;
   if (to_freq) {
     auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, true>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
   } else {
     auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, false>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
   }
   PD_CHECK_LAUNCH();
@@ -841,11 +855,11 @@ static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, 
   int64_t nblk = (nlines + lpb - 1) / lpb;
   if (to_freq) {
     auto k = pd_rfft_kernel<R0, R1, R2, R3, true>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
   } else {
     auto k = pd_rfft_kernel<R0, R1, R2, R3, false>;
-    PD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
   }
   PD_CHECK_LAUNCH();

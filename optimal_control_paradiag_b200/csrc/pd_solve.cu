@@ -973,7 +973,6 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   if (kpb < 1) kpb = 1;
   const size_t smem = (size_t)n * kpb * 64;
   const int nblk = (ncol + kpb - 1) / kpb;
-  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
   PD_CHECK_LAUNCH();
   h->launches++;
@@ -986,6 +985,9 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
 }
 
 int pd_solve_plan(pd_handle* h) {
+  // largest dynamic shared memory the PCR kernel is ever launched with (set once, not per launch)
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               PD_PCR_THREADS * PD_PCR_MAXROWS * 64));
   SolvePlan* pl = new SolvePlan();
   memset(pl, 0, sizeof(*pl));
   h->solve_plan = pl;
