@@ -13,6 +13,7 @@
 //           Stockham with direct (O(R) per output) passes ping-ponging between
 //           two shared-memory buffers; prime factors of any size are accepted.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "pd_common.cuh"
 
@@ -179,9 +180,9 @@ __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 //           output order io[u*R + r] <-> element base(t + u T) + r Ns
 // ---- thread-block-cluster plumbing of the N_t = 16384 kernel (sm_90+ PTX) ----
 // Two barrier phases per line, both on the hardware cluster barrier, split into arrive and wait:
-//   A "my shared memory may be overwritten": RELAXED -- it orders shared-memory reads that were issued before
-//     the __syncthreads preceding the arrive against the peers' later remote stores, so no fence is needed
-//     (arrive.release would stall every warp on a membar until its in-flight global stores are acknowledged);
+//   A "my shared memory may be overwritten": RELAXED arrive behind a block-scope fence -- it orders this
+//     CTA's completed shared-memory reads against the peers' later remote stores (arrive.release would
+//     stall every warp on a membar until its in-flight global stores are acknowledged device-wide);
 //   B "the exchange has landed": release / acquire, the remote stores must be visible to the reader.
 __device__ __forceinline__ void cluster_arrive_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -249,8 +250,14 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
       }
     }
     __syncthreads();  // all reads of sm done before anyone overwrites it
-    // cluster kernels: this CTA's shared memory is free from here on (split-phase cluster barrier)
-    if (CLARRIVE) cluster_arrive_relaxed();
+    // cluster kernels: this CTA's shared memory is free from here on (split-phase cluster barrier).  The
+    // block-scope fence makes sure the shared-memory loads above have been PERFORMED, not merely issued: the
+    // untwiddled element v[u][0] is first used after this point, and a peer's remote store (which does not
+    // queue behind this SM's own shared-memory pipeline) overtook such a load about once in 5000 lines.
+    if (CLARRIVE) {
+      __threadfence_block();
+      cluster_arrive_relaxed();
+    }
   }
 #pragma unroll
   for (int u = 0; u < NB; ++u) dft_pow2<R>(v[u]);
@@ -313,32 +320,32 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
   }
 }
 
-// N_t = 16384: a line is 256 KiB, more than one CTA's shared memory, so a 4-CTA thread-block cluster
-// transforms it as N = 4 x 4096.  Every CTA runs the 4096-point register pipeline above (256 threads, 68 KiB
-// of shared memory, two CTAs per SM so that one CTA's global traffic overlaps the other's arithmetic), and
-// the remaining radix-4 stage is an all-to-all between the four CTAs done with REMOTE STORES into
-// distributed shared memory (3/4 of a line crosses the SM-to-SM network once; stores are fire-and-forget, no
-// remote-load latency is exposed).  With Q = N/4, w = W_N:
+// N_t = 16384: a line is 256 KiB, more than one CTA's shared memory.  Two kernels exist; both leave the
+// frequency axis as [k = 0 mod 4 | 1 mod 4 | 2 mod 4 | 3 mod 4] (N = 4 x 4096, Q = N/4, w = W_N):
 //   TO_FREQ (time -> frequency, decimation in frequency):
-//       y_q[j] = w^{jq} sum_m x[j + Q m] (-i)^{mq},   X[4k' + q] = FFT_Q(y_q)[k'].
-//       CTA c loads x[j + Q m] for its j-quarter [1024c, 1024c + 1024) and all m straight from global
-//       memory (four contiguous 16 KiB pieces), does the 4-point DFTs and twiddles in registers and stores
-//       y_q[j] into CTA q's shared memory; CTA q then transforms y_q and writes the frequencies k = q (mod 4)
-//       as the q-th quarter of the line.
+//       y_q[j] = w^{jq} sum_m x[j + Q m] (-i)^{mq},   X[4k' + q] = FFT_Q(y_q)[k']
 //   !TO_FREQ (frequency -> time, decimation in time), input in that [q][k'] order:
 //       Z_q = FFT_Q(Y_q),   x[n' + Q m] = sum_q (-i)^{mq} w^{n'q} Z_q[n'].
-//       CTA q transforms its quarter and stores Z_q[n'] into the shared memory of the CTA that owns n'
-//       (n'-quarters); that CTA twiddles, does the 4-point DFTs and writes four contiguous 16 KiB pieces of
-//       the time line.
-// The frequency axis of an N_t = 16384 problem is therefore stored as [k = 0 mod 4 | 1 mod 4 | 2 mod 4 |
-// 3 mod 4]; the per-frequency solves are independent and only need the index map (freq_of in pd_solve.cu),
-// so no reordering pass exists.  Measured alternatives (B200): a 2-CTA cluster of
-// 8192-point pipelines reading the peer's half through distributed shared memory (one CTA per SM) reached
-// 2.5 TB/s against 3.1-3.4 TB/s here; st.async + mbarrier instead of the release/acquire barrier, an L2
-// prefetch of the next line, three CTAs per SM (80 registers) and 512-thread CTAs with radix-8 passes (32 warps
-// per SM, one more exchange) each measured equal or slower.  Without the exchange and the barriers the same
-// pipeline streams at 4.9 TB/s: the cluster coupling, not a saturated unit, is what is left (ncu: no pipe above
-// 50 %).
+// The per-frequency solves are independent and only need the index map (freq_of in pd_solve.cu), so no
+// reordering pass exists.
+//
+// (1) pd_fft_16k_l2_kernel (default, further down): one CTA per line, the radix-4 stage is an in-place pass
+//     over the line in global memory that L2 absorbs (eviction-priority hints).  4.2 TB/s on B200.
+// (2) pd_fft_16k_kernel (PD_FFT16K=cluster): a 4-CTA thread-block cluster per line.  Every CTA runs the
+//     4096-point register pipeline (256 threads, 68 KiB of shared memory, two CTAs per SM) and the radix-4
+//     stage is an all-to-all between the four CTAs done with REMOTE STORES into distributed shared memory
+//     (3/4 of a line crosses the SM-to-SM network once; stores are fire-and-forget, no remote-load latency is
+//     exposed).  TO_FREQ: CTA c loads x[j + Q m] for its j-quarter and all m straight from global memory,
+//     does the 4-point DFTs and twiddles in registers and stores y_q[j] into CTA q's shared memory; CTA q
+//     transforms y_q and writes the q-th quarter of the line.  !TO_FREQ: CTA q transforms its quarter and
+//     stores Z_q[n'] into the shared memory of the CTA that owns n'; that CTA twiddles, does the 4-point DFTs
+//     and writes four contiguous 16 KiB pieces of the time line.  3.1-3.4 TB/s: the barrier coupling of four
+//     CTAs that each share their SM with a CTA of another cluster costs more than the L2 round trip of (1)
+//     (without the exchange and the barriers the same pipeline streams at 4.9 TB/s; ncu shows no pipe above
+//     50 %).  Measured alternatives for (2): a 2-CTA cluster of 8192-point pipelines reading the peer's half
+//     through distributed shared memory (one CTA per SM) 2.5 TB/s; st.async + mbarrier instead of the
+//     release/acquire barrier, an L2 prefetch of the next line, three CTAs per SM (80 registers) and
+//     512-thread CTAs with radix-8 passes each equal or slower.
 #define PD_BIGN 16384
 template <bool INV, bool TO_FREQ>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256, 2)
@@ -434,6 +441,142 @@ pd_fft_16k_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t n
   // balance the last A arrive; after it no peer stores into this CTA any more (its B wait of the last line
   // has seen every store), so the CTA may leave
   cluster_wait();
+}
+
+// L2 eviction-priority hints (createpolicy / .L2::cache_hint): the cluster-free 16k kernel parks a 256 KiB
+// intermediate line in L2 for a few microseconds; "evict_last" on it and "evict_first" on the streaming
+// input keep the intermediates of all resident CTAs (148 x 2 x 256 KiB = 76 MB of the 126 MB L2) from being
+// written back to HBM and fetched again.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// L1-bypassing load / store of one complex number with an L2 cache policy
+__device__ __forceinline__ cplx ld_cg_hint(const cplx* p, uint64_t pol) {
+  cplx v;
+  asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_hint(cplx* p, cplx v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
+// N_t = 16384 WITHOUT a cluster (the default; PD_FFT16K=cluster selects the kernel above): one 256-thread CTA
+// owns a whole line and does the radix-4 stage as an in-place pass over the line in GLOBAL memory -- the
+// 256 KiB line it has just written (or is about to re-read) sits in L2, so HBM still sees one read and one
+// write of the line while no CTA ever waits for another one.  Same [k mod 4] frequency order.
+//   TO_FREQ : butterflies (reads `in`, writes y_q[j] to out[q Q + j]), then four 4096-point pipelines in place;
+//   !TO_FREQ: four 4096-point pipelines (in -> out), then the butterflies in place on out.
+// Every global access is explicit here (L1-bypassing, with an L2 policy): the local pipelines run with their
+// first pass fed from registers and their last pass kept in registers.  Measured (B200, ncu): without the
+// policies 1.57 + 1.70 GB of DRAM traffic per 1.07 GB sweep and 3.7-3.9 TB/s; with them 1.08 + 1.06 GB and
+// 4.2 TB/s (an L2 prefetch of the next input piece and a persistent grid changed nothing).
+template <bool INV, bool TO_FREQ>
+__global__ void __launch_bounds__(256, 2)
+pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
+                     const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale) {
+  constexpr int N = PD_BIGN, Q = N / 4, T = Q / 16, J = Q / 4;
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw);
+  const int t = threadIdx.x;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  auto ld_in = [&](const cplx* p) { return ld_cg_hint(p, pol_stream); };     // streaming input
+  auto ld_mid = [&](const cplx* p) { return ld_cg_hint(p, pol_keep); };      // parked intermediate line
+  auto st_mid = [&](cplx* p, cplx v) { st_hint(p, v, pol_keep); };
+  auto st_out = [&](cplx* p, cplx v) { st_hint(p, v, pol_stream); };         // streaming output
+  for (int64_t line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const cplx* src = in + line * N;
+    cplx* dst = out + line * N;
+    if (TO_FREQ) {
+#pragma unroll 1
+      for (int jq = 0; jq < 4; ++jq) {
+        cplx v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            cplx x = ld_in(src + jq * J + T * u + t + Q * m);
+            if (INV) x.y = -x.y;
+            v[u][m] = x;
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dft_pow2<4>(v[u]);
+          const cplx w1 = tw[jq * J + T * u + t];
+          const cplx w2 = cmul(w1, w1);
+          v[u][1] = cmul(v[u][1], w1);
+          v[u][2] = cmul(v[u][2], w2);
+          v[u][3] = cmul(v[u][3], cmul(w2, w1));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st_mid(dst + q * Q + jq * J + T * u + t, v[u][q]);
+        }
+      }
+      __syncthreads();  // the line of y is visible to the whole CTA (read back through L2 below)
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        cplx io[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) io[r] = ld_mid(dst + q * Q + t + T * r);
+        pow2_pass<16, false, true, false, true, false>(nullptr, nullptr, sm, tw_q, Q, 1, t, T, scale, true, io);
+        pow2_pass<16, false, false, false>(nullptr, nullptr, sm, tw_q, Q, 16, t, T, scale, true);
+        pow2_pass<16, false, false, true, false, true>(nullptr, nullptr, sm, tw_q, Q, 256, t, T, scale, true, io);
+        // io[r] <-> X[4 (t + 256 r) + q]
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          cplx y = io[r];
+          if (INV) y.y = -y.y;
+          st_out(dst + q * Q + t + T * r, cscale(y, scale));
+        }
+        __syncthreads();  // the last pass's shared-memory reads are done before the next quarter's first pass
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        cplx io[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          cplx x = ld_in(src + q * Q + t + T * r);
+          if (INV) x.y = -x.y;
+          io[r] = x;
+        }
+        pow2_pass<16, false, true, false, true, false>(nullptr, nullptr, sm, tw_q, Q, 1, t, T, 1.0, true, io);
+        pow2_pass<16, false, false, false>(nullptr, nullptr, sm, tw_q, Q, 16, t, T, 1.0, true);
+        pow2_pass<16, false, false, true, false, true>(nullptr, nullptr, sm, tw_q, Q, 256, t, T, 1.0, true, io);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) st_mid(dst + q * Q + t + T * r, io[r]);   // Z_q[t + 256 r]
+        __syncthreads();
+      }
+      // (the __syncthreads above also makes the four quarter transforms visible to the whole CTA)
+#pragma unroll 1
+      for (int jq = 0; jq < 4; ++jq) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = jq * J + T * u + t;
+          cplx v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = ld_mid(dst + q * Q + n);
+          const cplx w1 = tw[n];
+          const cplx w2 = cmul(w1, w1);
+          v[1] = cmul(v[1], w1);
+          v[2] = cmul(v[2], w2);
+          v[3] = cmul(v[3], cmul(w2, w1));
+          dft_pow2<4>(v);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            cplx y = v[m];
+            if (INV) y.y = -y.y;
+            st_out(dst + m * Q + n, cscale(y, scale));
+          }
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------ real-input fast path
@@ -604,6 +747,14 @@ int pd_fft_plan(pd_handle* h) {
                                  (int)smem));
     PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    {
+      const char* env = getenv("PD_FFT16K");
+      h->fft16k_l2 = !(env && env[0] == 'c');  // default: the cluster-free kernel; PD_FFT16K=cluster selects the other
+    }
     // co-resident 4-CTA clusters (GPC boundaries keep this a little below num_sms * 2 / 4: 71 on B200)
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(4 * (unsigned)h->num_sms, 1, 1);
@@ -678,8 +829,19 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
 static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
   const double scale = inverse ? 1.0 / (double)PD_BIGN : 1.0;
   // inverse (time -> frequency, :500-501) leaves the permuted frequency order, forward (:547-548) consumes it.
-  // 4-CTA clusters, persistent over the lines: as many clusters as can be co-resident
   const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
+  if (h->fft16k_l2) {
+    const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
+    if (inverse)
+      pd_fft_16k_l2_kernel<true, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter, scale);
+    else
+      pd_fft_16k_l2_kernel<false, false><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
+                                                                 scale);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+    return PD_OK;
+  }
+  // 4-CTA clusters, persistent over the lines: as many clusters as can be co-resident
   int64_t ncl = h->fft16k_clusters > 0 ? h->fft16k_clusters : h->num_sms / 2;
   if (ncl > nlines) ncl = nlines;
   if (inverse)

@@ -37,6 +37,33 @@ def rand_x(size, seed=0, real=False):
 
 
 # ---------------------------------------------------------------------------- time-axis FFT
+@pytest.mark.parametrize("variant", ["l2", "cluster"])
+def test_fft_16384_both_kernels_many_lines(variant, monkeypatch):
+    # both N_t = 16384 kernels (cluster-free default, 4-CTA cluster), enough lines for every persistent CTA to
+    # loop: out of place and in place.  (A remote store overtaking a not-yet-performed shared-memory load in
+    # the cluster kernel corrupted about one line in 5000 before the block-scope fence went in.)
+    import scipy.fft as sfft
+    monkeypatch.setenv("PD_FFT16K", variant)
+    N_t, nl = 16384, 1500
+    perm = np.concatenate([np.arange(q, N_t, 4) for q in range(4)])
+    x = rand_x(nl * N_t).reshape(nl, N_t)
+    with ParaDiagHandle(8, N_t) as h:
+        xt = torch.tensor(x, device=DEV).reshape(-1)
+        yt, zt = torch.empty_like(xt), torch.empty_like(xt)
+        for rep in range(3):
+            h.stage_fft(xt, yt, nl, True)
+            if rep == 0:
+                assert rel(yt.cpu().numpy().reshape(nl, N_t), sfft.ifft(x, axis=1)[:, perm]) < 5e-15
+            h.stage_fft(yt, zt, nl, False)
+            assert np.abs(zt.cpu().numpy().reshape(nl, N_t) - x).max() < 1e-12
+            h.stage_fft(yt, yt, nl, False)
+            assert np.abs(yt.cpu().numpy().reshape(nl, N_t) - x).max() < 1e-12
+            zt.copy_(xt)
+            h.stage_fft(zt, zt, nl, True)
+            h.stage_fft(zt, zt, nl, False)
+            assert np.abs(zt.cpu().numpy().reshape(nl, N_t) - x).max() < 1e-12
+
+
 @pytest.mark.parametrize("N_t", [3, 5, 13, 64, 81, 96, 97, 100, 128, 256, 512, 625, 1024, 2048, 4096, 8192, 16384])
 def test_fft_matches_scipy(N_t):
     import scipy.fft as sfft
@@ -46,7 +73,7 @@ def test_fft_matches_scipy(N_t):
         xt = torch.tensor(x, device=DEV).reshape(-1)
         yt = torch.empty_like(xt)
         if N_t == 16384:
-            # 4-CTA cluster kernel: time -> frequency leaves [k = 0 mod 4 | 1 | 2 | 3]; frequency -> time
+            # N_t = 16384 kernels: time -> frequency leaves [k = 0 mod 4 | 1 | 2 | 3]; frequency -> time
             # consumes that order
             perm = np.concatenate([np.arange(q, N_t, 4) for q in range(4)])
             h.stage_fft(xt, yt, nl, True)
