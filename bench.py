@@ -298,19 +298,19 @@ def run_ours(args):
         # the solve pass is pass A + PCR + pass B, of which pass B carries the read+write sweep
         dom = max(prof, key=prof.get)
         alg = {"ifft": 2 * S, "fft": 2 * S, "passB": 2 * S, "passA": S, "pcr": 0.3 * S}[dom]
-        fftk = "pd_fft_16k_kernel" if N_t == 16384 else ("pd_fft_pow2_kernel" if (N_t & (N_t - 1)) == 0 and N_t >= 64
+        fftk = "pd_fft_16k_l2_kernel" if N_t == 16384 else ("pd_fft_pow2_kernel" if (N_t & (N_t - 1)) == 0 and N_t >= 64
                                                          else "pd_fft_generic_kernel")
         names = {"ifft": fftk + "<inv>", "fft": fftk + "<fwd>", "passA": "pd_solve_passA_kernel",
                  "pcr": "pd_solve_pcr_kernel", "passB": "pd_solve_passB_kernel"}
         ach = alg / (prof[dom] * 1e-3) / 1e9
         # DRAM traffic of that kernel per launch, from the committed `ncu --set full` capture of this
-        # command (profiles/r01_ncu_full_final.txt; cfg3 only)
+        # command (profiles/r01_ncu_full_cfg3.txt; cfg3 only)
         traffic = None
         try:
             if args.workload == "cfg3":
                 key = {"ifft": "pd_fft_pow2_kernel<16, 16, 16, 1, 1>", "fft": "pd_fft_pow2_kernel<16, 16, 16, 1, 0>",
                        "passA": "pd_solve_passA_kernel", "passB": "pd_solve_passB_kernel", "pcr": "pd_solve_pcr_kernel"}[dom]
-                blocks = open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.txt")).read().split("== ")
+                blocks = open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg3.txt")).read().split("== ")
                 for blk in blocks:
                     if blk.strip() and key in blk.splitlines()[0]:
                         dram = 0.0
@@ -421,7 +421,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))

@@ -43,7 +43,7 @@ def _worker(rank, world, port, N_x, N_t, gamma, ret, mode):
 
 
 @pytest.mark.parametrize("mode", ["alltoall", "slab"])
-@pytest.mark.parametrize("N_x,N_t", [(80, 81), (255, 128), (1024, 1024), (37, 16), (4096, 64)])
+@pytest.mark.parametrize("N_x,N_t", [(80, 81), (255, 128), (1024, 1024), (37, 16), (4096, 64), (20, 16384)])
 def test_sharded_apply_equals_single_gpu_apply(N_x, N_t, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
