@@ -247,7 +247,8 @@ def run_ours(args):
         del xh, yh
 
     gmres_dist = None
-    if world > 1 and args.dist_mode == "slab" and not args.no_gmres:
+    # (a restart-300 Krylov basis of multi-GB local vectors does not fit: skip the solve leg there)
+    if world > 1 and args.dist_mode == "slab" and not args.no_gmres and handle.local_size * 16 <= (4 << 30):
         # GMRES time-to-solution on the reference's manufactured problem, all ranks (collective)
         try:
             b = handle.build_rhs()

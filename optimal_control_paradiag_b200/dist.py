@@ -230,7 +230,7 @@ class DistributedDiagFFTPC:
         tmp = t.empty(ln, dtype=c128, device=self.device)
         # Krylov basis in blocks of BS vectors, allocated as the iteration proceeds (a cfg3 vector is
         # 2.1 GB / G per rank: the restart length of 300 cannot be pre-allocated)
-        BS = 8
+        BS = max(1, min(8, (2 << 30) // (16 * ln)))      # ~2 GB per block
         blocks = [t.empty((BS, ln), dtype=c128, device=self.device)]
 
         def vec(j):
