@@ -15,6 +15,7 @@ class FakeHandle:
         self.N_x, self.N_t, self.T, self.gamma, self.device = N_x, N_t, T, gamma, device
         self.n = N_x + 1
         self.size = 2 * self.n * N_t
+        self.alpha = kw.get("alpha", 1.0)
         self.calls = []
         FakeHandle.created.append(self)
 
@@ -74,6 +75,26 @@ def test_options_prefix_overrides_configure():
     pc.setUp()
     h = FakeHandle.created[-1]
     assert (h.N_x, h.N_t, h.gamma, h.T) == (8, 5, 0.01, 2.0)
+
+
+def test_alpha_defaults_to_the_upstream_operator_and_follows_the_option_chain():
+    # the reference has no alpha: 1.0 unless explicitly asked for (configure < options prefix)
+    pkg.DiagFFTPC.configure(N_x=4, N_t=3, T=2.0, gamma=0.5)
+    pc = petsc_shim.PC()
+    pc.setPythonContext(pkg.DiagFFTPC())
+    pc.setUp()
+    assert FakeHandle.created[-1].alpha == 1.0
+    pkg.DiagFFTPC.configure(alpha=0.25)
+    pc = petsc_shim.PC()
+    pc.setPythonContext(pkg.DiagFFTPC())
+    pc.setUp()
+    assert FakeHandle.created[-1].alpha == 0.25
+    pc = petsc_shim.PC(prefix="p_", options=petsc_shim.Options({"p_diagfft_alpha": "1e-3"}))
+    pc.setPythonContext(pkg.DiagFFTPC())
+    pc.setUp()
+    assert FakeHandle.created[-1].alpha == 1e-3
+    with pytest.raises(TypeError):
+        pkg.DiagFFTPC.configure(beta=1.0)
 
 
 def test_appctx_has_highest_priority(monkeypatch):
