@@ -121,6 +121,17 @@ class AllAtOnce:
             A[:, j] = self.matvec(I[:, j])
         return A
 
+    def direct_solve(self, b=None):
+        """The reference's ``pc=False`` baseline (:186, :573-577: ``ksp_type preonly``, ``pc_type lu``, MUMPS):
+        a direct LU solve of the all-at-once system, here SuperLU on the explicit matrix (small sizes)."""
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        b = self.rhs() if b is None else np.asarray(b)
+        lu = spla.splu(sp.csc_matrix(self.dense()))
+        if np.iscomplexobj(b):
+            return lu.solve(b.real) + 1j * lu.solve(b.imag)
+        return lu.solve(b)
+
     def analytic(self):
         """Nodal values of the analytic state/adjoint the data were manufactured
         from (write(), :299-300), at the times the unknowns live on:

@@ -85,6 +85,10 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_product_package_never_imports_the_oracle():
     pkgdir = os.path.join(ROOT, "optimal_control_paradiag_b200")
+    for f in os.listdir(os.path.join(ROOT, "tools")):            # dev tools outside tests/ stay oracle-free too
+        if f.endswith((".py", ".sh")):
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(ROOT, "tools", f)).read(),
+                                 flags=re.M), f
     for dirpath, _, files in os.walk(pkgdir):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -404,3 +404,13 @@ def test_errors_are_status_codes_not_aborts():
         with pytest.raises(ParaDiagError):
             h.matvec(x, x)                                # aliasing is rejected
         assert h.launch_count >= 0 and h.workspace_bytes > 0
+
+
+def test_gmres_solution_equals_the_direct_lu_baseline():
+    # the reference's pc=False branch (:573-577, direct MUMPS) restated by the oracle, against the device solve
+    N_x, N_t = 24, 32
+    direct = AllAtOnce(N_x, N_t).direct_solve()
+    with ParaDiagHandle(N_x, N_t) as h:
+        x, its, hist, reason = h.gmres(h.build_rhs(), rtol=1e-12)
+        assert reason == "CONVERGED_RTOL"
+        assert rel(x.cpu().numpy(), direct + 0j) < 1e-9

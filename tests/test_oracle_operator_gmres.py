@@ -99,3 +99,18 @@ def test_gmres_golden(path):
     x, its, hist, _ = gmres(op.matvec, DiagFFTPCFast(N_x, N_t, float(g["T"]), gamma).apply, g["b"], rtol=1e-7)
     assert its == int(g["its"])
     assert np.allclose(np.array(hist)[:-1], g["hist"][:-1], rtol=1e-6)
+
+
+def test_gmres_with_pc_reproduces_the_direct_lu_baseline():
+    # upstream's own end-to-end check: the pc=True run (GMRES + DiagFFTPC, :567) against the pc=False direct
+    # MUMPS solve (:573-577) of the same problem
+    from oracle.gmres import gmres
+    from oracle.operator import AllAtOnce
+    from oracle.pc_fast import DiagFFTPCFast
+    N_x, N_t = 16, 24
+    op = AllAtOnce(N_x, N_t)
+    direct = op.direct_solve()
+    x, its, _, reason = gmres(op.matvec, DiagFFTPCFast(N_x, N_t).apply, op.rhs() + 0j, rtol=1e-12)
+    assert reason == "CONVERGED_RTOL"
+    assert np.linalg.norm(x - direct) / np.linalg.norm(direct) < 1e-9
+    assert np.linalg.norm(op.matvec(direct) - op.rhs()) / np.linalg.norm(op.rhs()) < 1e-12

@@ -1,6 +1,6 @@
 """Developer probe: where does the PC-apply error on SMOOTH vectors come from? (vs 80-bit oracle)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, scipy.fft as sfft
 from optimal_control_paradiag_b200 import ParaDiagHandle
 from oracle.pc_fast import DiagFFTPCFast

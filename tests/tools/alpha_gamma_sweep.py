@@ -7,7 +7,7 @@ defined in oracle/pc_alpha.py (no upstream behaviour exists for it: parity unpin
 Writes one JSON object per line to stdout.
 """
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from optimal_control_paradiag_b200 import ParaDiagHandle
 from oracle.pc_alpha import DiagFFTPCAlpha

@@ -1,6 +1,6 @@
 """N_t = 16384 FFT kernel on the GPU box: parity against scipy and the oracle, then timing."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import scipy.fft as sfft
 from optimal_control_paradiag_b200 import ParaDiagHandle

@@ -1,6 +1,6 @@
 """Developer probe: GMRES residual histories at large sizes, GPU vs CPU oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from optimal_control_paradiag_b200 import ParaDiagHandle
 from oracle.pc_fast import DiagFFTPCFast
