@@ -246,6 +246,29 @@ def run_ours(args):
                     "api": "DistributedDiagFFTPC.apply_host(x, y): every rank's node-slab block in pinned host memory"}
         del xh, yh
 
+    real_dist = None
+    if world > 1 and args.dist_mode == "slab":
+        # the same apply on float64 blocks (the real problem): half spectrum through the slab-distributed solve
+        try:
+            xr = torch.randn(handle.local_size, dtype=torch.float64, device=dev)
+            yr = torch.empty_like(xr)
+            for _ in range(3):
+                handle.apply_real(xr, yr)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                handle.apply_real(xr, yr)
+            e1.record()
+            barrier()
+            tr = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            real_dist = {"ms_per_step": float(tr.item()), "applies_per_sec": 1e3 / float(tr.item()),
+                         "note": "DistributedDiagFFTPC.apply_real on float64 node-slab blocks (half spectrum)"}
+            del xr, yr
+        except Exception as ex:  # unsupported N_t
+            real_dist = {"error": str(ex)}
+
     gmres_dist = None
     # (a restart-300 Krylov basis of multi-GB local vectors does not fit: skip the solve leg there)
     if world > 1 and args.dist_mode == "slab" and not args.no_gmres and handle.local_size * 16 <= (4 << 30):
@@ -414,6 +437,7 @@ def run_ours(args):
         line["e2e"] = e2e_dist
         line["dist"] = handle.describe()
         line["gmres"] = gmres_dist
+        line["real_input_apply"] = real_dist
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -145,6 +145,14 @@ int pd_stage_solve(pd_handle* h, void* w_dev, void* stream);
  * Together they replace pd_stage_solve (i.e. :445-540) for a distributed x-axis.                  */
 int pd_slab_reduce(pd_handle* h, void* w_dev, void* out_dev, void* stream);
 int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream);
+/* Slab mode on the real-input path (float64 vectors, half spectrum k = 0..N_t/2, rows padded to Kp complex
+ * numbers): pd_stage_rfft_pair transforms both fields of `nnodes` node lines, (2, nnodes, N_t) float64 <->
+ * (2, nnodes, Kp) complex; pd_slab_reduce_half / pd_slab_finish_half are pd_slab_reduce / pd_slab_finish on
+ * w = (2, n_r, Kp) with out (6, Kp) and gathered (G, 6, Kp).  No upstream counterpart (the reference has no
+ * parallel decomposition).  Power-of-two N_t in [128, 16384]; PD_ERR_UNSUPPORTED otherwise.             */
+int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_dev, int64_t nnodes, int to_freq, void* stream);
+int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, void* stream);
+int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream);
 
 /* Matrix-free action of the Jacobian of Build_L (:86-179, pc=True branches):
  * y = A x with Dirichlet rows as identity.  x and y must not alias.             */

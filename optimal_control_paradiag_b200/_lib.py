@@ -53,6 +53,9 @@ SYMBOLS = {
     "pd_stage_solve": (_I, [_VP, _VP, _VP]),
     "pd_slab_reduce": (_I, [_VP, _VP, _VP, _VP]),
     "pd_slab_finish": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_stage_rfft_pair": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
+    "pd_slab_reduce_half": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_slab_finish_half": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec_slab": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),

@@ -187,6 +187,48 @@ extern "C" int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_de
   return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream);
 }
 
+// slab mode on the half spectrum of the real-input path: w = (2, n_r, Kp), out (6, Kp), gathered (G, 6, Kp)
+extern "C" int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, void* stream) {
+  if (!h || !w_dev || !out_dev || h->slab_count <= 1) {
+    pd_set_error("pd_slab_reduce_half: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  if (!pd_slab_half_supported(h)) {
+    pd_set_error("pd_slab_reduce_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  return pd_slab_reduce_launch(h, (cplx*)w_dev, (cplx*)out_dev, (cudaStream_t)stream, 1);
+}
+
+extern "C" int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream) {
+  if (!h || !w_dev || !gathered_dev || h->slab_count <= 1) {
+    pd_set_error("pd_slab_finish_half: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  if (!pd_slab_half_supported(h)) {
+    pd_set_error("pd_slab_finish_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream, 1);
+}
+
+// both fields of `nnodes` node lines at once: (2, nnodes, N_t) float64 <-> (2, nnodes, Kp) complex half spectra
+// (one complex N_t-point transform per node where the pair kernel covers N_t, else the per-line kernel)
+extern "C" int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_dev, int64_t nnodes, int to_freq,
+                                  void* stream) {
+  if (!h || !in_dev || !out_dev || nnodes < 0) {
+    pd_set_error("pd_stage_rfft_pair: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  if (!pd_rfft_supported(h)) {
+    pd_set_error("pd_stage_rfft_pair: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  int rc = pd_rfft_pair_launch(h, in_dev, out_dev, nnodes, to_freq, (cudaStream_t)stream);
+  if (rc == -100) rc = pd_rfft_launch(h, in_dev, out_dev, 2 * nnodes, to_freq, (cudaStream_t)stream);
+  return rc;
+}
+
 extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
   if (!h || !x_dev || !y_dev) {
     pd_set_error("pd_pc_apply: invalid argument");

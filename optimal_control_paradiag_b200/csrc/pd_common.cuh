@@ -127,8 +127,9 @@ int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int 
 int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st);
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr, int half_spectrum = 0);
-int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st);
-int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st);
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0);
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0);
+bool pd_slab_half_supported(const pd_handle* h);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
                      const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr, int real_vectors = 0);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors = 0);

@@ -903,6 +903,8 @@ struct SolvePlan {
   cplx* green;
   cplx* zout;
   cplx* slabcoef;
+  cplx* green_h;     // the same two plan-time tables for the half spectrum of the real-input path
+  cplx* slabcoef_h;  //   (columns 0 .. N_t/2 in natural order, row stride Kp)
   SlabGeom sg;
 };
 
@@ -915,6 +917,8 @@ void pd_solve_free(pd_handle* h) {
     if (pl->R[l]) cudaFree(pl->R[l]);
     if (pl->F[l]) cudaFree(pl->F[l]);
   }
+  if (pl->green_h) cudaFree(pl->green_h);
+  if (pl->slabcoef_h) cudaFree(pl->slabcoef_h);
   if (pl->lastl) cudaFree(pl->lastl);
   if (pl->green) cudaFree(pl->green);
   if (pl->zout) cudaFree(pl->zout);
@@ -953,7 +957,7 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   sp.lna = log(h->cfg.alpha) / (double)h->cfg.N_t;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
-  sl.lastl = pl->lastl; sl.green = pl->green; sl.zout = pl->zout;
+  sl.lastl = pl->lastl; sl.green = half_spectrum ? pl->green_h : pl->green; sl.zout = pl->zout;
 }
 
 // levels 1..top: reduce, PCR on the top system, back-substitute; leaves the level-1 solution in R[1]
@@ -1043,29 +1047,34 @@ int pd_solve_plan(pd_handle* h) {
     PD_CUDA(cudaMalloc(&pl->zout, sizeof(cplx) * 4 * K));
     PD_CUDA(cudaMemset(pl->lastl, 0, sizeof(cplx) * 2 * K));
     PD_CUDA(cudaMemset(pl->zout, 0, sizeof(cplx) * 4 * K));
-    PD_CUDA(cudaMalloc(&pl->slabcoef, sizeof(cplx) * (size_t)G * 2 * K));
-    h->ws_bytes += sizeof(cplx) * (6 + (size_t)G * 2) * K;
-    {
+    h->ws_bytes += sizeof(cplx) * 6 * K;
+    // plan-time tables (per-slab Green's coefficients, interface Green's vectors), for the full spectrum and,
+    // when the real-input path exists for this N_t, for its half spectrum
+    const bool want_half = pd_rfft_supported(h);
+    for (int half = 0; half <= (want_half ? 1 : 0); ++half) {
       SolveParams sp; Levels lv; SlabPtrs sl;
-      fill_params(h, sp, lv, sl);
-      pd_slab_coef_kernel<<<dim3((unsigned)((K + PD_KB - 1) / PD_KB), G), PD_KB>>>(sp, pl->sg, pl->slabcoef);
+      fill_params(h, sp, lv, sl, half);
+      const size_t Kt = (size_t)sp.K;
+      cplx** coef = half ? &pl->slabcoef_h : &pl->slabcoef;
+      cplx** green = half ? &pl->green_h : &pl->green;
+      PD_CUDA(cudaMalloc(coef, sizeof(cplx) * (size_t)G * 2 * Kt));
+      h->ws_bytes += sizeof(cplx) * (size_t)G * 2 * Kt;
+      pd_slab_coef_kernel<<<dim3((unsigned)((Kt + PD_KB - 1) / PD_KB), G), PD_KB>>>(sp, pl->sg, *coef);
       PD_CHECK_LAUNCH();
-    }
-    if (pl->nlev >= 1) {
-      // interface Green's vectors: one run of the interface levels on unit right-hand sides
-      const int P = pl->rows[1];
-      size_t bytes = sizeof(cplx) * (size_t)P * 2 * K;
-      PD_CUDA(cudaMalloc(&pl->green, bytes));
-      h->ws_bytes += bytes;
-      SolveParams sp; Levels lv; SlabPtrs sl;
-      fill_params(h, sp, lv, sl);
-      PD_CUDA(cudaMemset(pl->F[0], 0, sizeof(cplx) * (size_t)(P + 1) * 2 * K));
-      const int64_t tot = (int64_t)P * 2 * K;
-      pd_slab_unit_rhs_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(pl->R[1], P, (int64_t)K);
-      PD_CHECK_LAUNCH();
-      int rc = run_interface(h, sp, lv, 0);
-      if (rc) return rc;
-      PD_CUDA(cudaMemcpy(pl->green, pl->R[1], bytes, cudaMemcpyDeviceToDevice));
+      if (pl->nlev >= 1) {
+        // interface Green's vectors: one run of the interface levels on unit right-hand sides
+        const int P = pl->rows[1];
+        const size_t bytes = sizeof(cplx) * (size_t)P * 2 * Kt;
+        PD_CUDA(cudaMalloc(green, bytes));
+        h->ws_bytes += bytes;
+        PD_CUDA(cudaMemset(pl->F[0], 0, sizeof(cplx) * (size_t)(P + 1) * 2 * Kt));
+        const int64_t tot = (int64_t)P * 2 * Kt;
+        pd_slab_unit_rhs_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(pl->R[1], P, (int64_t)Kt);
+        PD_CHECK_LAUNCH();
+        int rc = run_interface(h, sp, lv, 0);
+        if (rc) return rc;
+        PD_CUDA(cudaMemcpy(*green, pl->R[1], bytes, cudaMemcpyDeviceToDevice));
+      }
     }
   }
   return PD_OK;
@@ -1111,10 +1120,15 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int
   return solve_range(h, w, sp, lv, sl, 0, sp.K, st, ev);
 }
 
+bool pd_slab_half_supported(const pd_handle* h) {
+  const SolvePlan* pl = reinterpret_cast<const SolvePlan*>(h->solve_plan);
+  return pl && pl->slabcoef_h != nullptr;
+}
+
 // slab mode, first half: pass A, interface levels, slab functionals -> out[6][K]
-int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st) {
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum) {
   SolveParams sp; Levels lv; SlabPtrs sl;
-  fill_params(h, sp, lv, sl);
+  fill_params(h, sp, lv, sl, half_spectrum);
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
   SolvePlan* pl = plan_of(h);
@@ -1139,13 +1153,14 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st) {
 }
 
 // slab mode, second half: global separator solve from the gathered functionals, then pass B
-int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st) {
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum) {
   SolveParams sp; Levels lv; SlabPtrs sl;
-  fill_params(h, sp, lv, sl);
+  fill_params(h, sp, lv, sl, half_spectrum);
   SolvePlan* pl = plan_of(h);
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
-  pd_slab_global_kernel<<<kblocks, PD_KB, 0, st>>>(gathered, sp, pl->sg, pl->slabcoef, pl->zout);
+  pd_slab_global_kernel<<<kblocks, PD_KB, 0, st>>>(gathered, sp, pl->sg, half_spectrum ? pl->slabcoef_h : pl->slabcoef,
+                                                   pl->zout);
   PD_CHECK_LAUNCH();
   pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();

@@ -172,6 +172,29 @@ class DistributedDiagFFTPC:
         self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * self.n_r, False)     # :547-548
         return y_local
 
+    def apply_real(self, x_local, y_local=None):
+        """The same apply for REAL node-slab blocks (float64, (2, n_r, N_t)): what GMRES feeds the PC in this
+        real problem.  Half spectrum (k <= N_t/2) in every stage: half the bytes of ``apply``, and the
+        all-gather shrinks to 6 (N_t/2 + 1) values per rank.  Slab mode, power-of-two N_t in [128, 16384]."""
+        t = self.torch
+        if self.mode != "slab":
+            raise NotImplementedError("the real-input distributed apply uses the slab decomposition")
+        if y_local is None:
+            y_local = t.empty_like(x_local)
+        if getattr(self, "_w_half", None) is None:
+            Kp = self.backend.half_cols
+            c128 = t.complex128
+            self._w_half = t.empty(2 * self.n_r * Kp, dtype=c128, device=self.device)
+            self._fl_half = t.empty(6 * Kp, dtype=c128, device=self.device)
+            self._gath_half = t.empty(self.world * 6 * Kp, dtype=c128, device=self.device)
+        self.backend.stage_rfft_pair(x_local.reshape(-1), self._w_half, self.n_r, True)
+        self.backend.slab_reduce_half(self._w_half, self._fl_half)
+        self.dist.all_gather_into_tensor(t.view_as_real(self._gath_half).reshape(-1),
+                                         t.view_as_real(self._fl_half).reshape(-1), group=self.group)
+        self.backend.slab_finish_half(self._w_half, self._gath_half)
+        self.backend.stage_rfft_pair(self._w_half, y_local.reshape(-1), self.n_r, False)
+        return y_local
+
     def apply_host(self, x_host, y_host):
         """The same apply for node-slab blocks that live in HOST memory (what a PETSc ``Vec`` of a spatial
         decomposition hands the PC, :493-497 / :552-553): H2D of this rank's block, apply, D2H.

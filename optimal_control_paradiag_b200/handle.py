@@ -166,6 +166,28 @@ class ParaDiagHandle:
                                       self._stream()))
         return w
 
+    # ---- slab mode on the half spectrum of the real-input path
+    @property
+    def half_cols(self):
+        """Row length Kp of a half spectrum: N_t/2 + 1 rounded up to a multiple of 8 complex numbers."""
+        return (self.N_t // 2 + 1 + 7) & ~7
+
+    def stage_rfft_pair(self, src, dst, nnodes, to_freq):
+        """(2, nnodes, N_t) float64 <-> (2, nnodes, Kp) complex half spectra (pd_stage_rfft_pair)."""
+        check(self.lib.pd_stage_rfft_pair(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                          int(nnodes), int(bool(to_freq)), self._stream()))
+        return dst
+
+    def slab_reduce_half(self, w, out):
+        check(self.lib.pd_slab_reduce_half(self._h, self._ptr(w, None, "w"), self._ptr(out, 6 * self.half_cols, "out"),
+                                           self._stream()))
+        return out
+
+    def slab_finish_half(self, w, gathered):
+        check(self.lib.pd_slab_finish_half(self._h, self._ptr(w, None, "w"), self._ptr(gathered, None, "gathered"),
+                                           self._stream()))
+        return w
+
     def matvec(self, x, y=None):
         """y = A x, the Jacobian action of Build_L (Control_Wave_PC.py:86-179)."""
         if y is None:

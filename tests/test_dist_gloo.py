@@ -32,27 +32,56 @@ class OracleStageBackend:
             self.body = [c - 1 - (1 if s == slab_count - 1 else 0) for s, c in enumerate(counts)]
 
     # ---- slab mode, restated with dense little solves (SPIKE): independent of the CUDA algorithm
-    def _rot_in(self, W):
+    def _rot_in(self, W, kidx=None):
         pc = self.pc
-        uz = W[0] * np.conj(pc.z)
-        ip = (1j * pc.sigma) * W[1]
+        kidx = np.arange(self.N_t) if kidx is None else kidx
+        uz = W[0] * np.conj(pc.z[kidx])
+        ip = (1j * pc.sigma[kidx]) * W[1]
         return (uz + ip) / 2, np.conj((uz - ip) / 2)          # slot +, conj slot -
 
     def _T(self, m, k):
         a, b = self.pc.a[k], self.pc.b[k]
         return (np.diag(np.full(m, b)) + np.diag(np.full(m - 1, a), 1) + np.diag(np.full(m - 1, a), -1))
 
-    def slab_reduce(self, w, out):
-        W = w.numpy().reshape(2, self.n_r, self.N_t)
-        rP, rM = self._rot_in(W)
+    def slab_reduce(self, w, out, kidx=None):
+        kidx = np.arange(self.N_t) if kidx is None else kidx       # column -> frequency
+        K = len(kidx)
+        W = w.numpy().reshape(2, self.n_r, K)
+        rP, rM = self._rot_in(W, kidx)
         m = self.body[self.r]
-        o = out.numpy().reshape(6, self.N_t)
-        for k in range(self.N_t):
+        o = out.numpy().reshape(6, K)
+        for col, k in enumerate(kidx):
             T = self._T(m, k)
-            yP = np.linalg.solve(T, rP[1:1 + m, k])
-            yM = np.linalg.solve(T, rM[1:1 + m, k])
-            o[0, k], o[1, k], o[2, k], o[3, k] = yP[0], yM[0], yP[-1], yM[-1]
-            o[4, k], o[5, k] = (rP[0, k], rM[0, k]) if self.r > 0 else (0, 0)
+            yP = np.linalg.solve(T, rP[1:1 + m, col])
+            yM = np.linalg.solve(T, rM[1:1 + m, col])
+            o[0, col], o[1, col], o[2, col], o[3, col] = yP[0], yM[0], yP[-1], yM[-1]
+            o[4, col], o[5, col] = (rP[0, col], rM[0, col]) if self.r > 0 else (0, 0)
+
+    # ---- real-input path: half spectrum, rows padded to Kp columns (padding columns hold zeros)
+    @property
+    def half_cols(self):
+        return (self.N_t // 2 + 1 + 7) & ~7
+
+    def _half_kidx(self):
+        return np.minimum(np.arange(self.half_cols), self.N_t // 2)
+
+    def stage_rfft_pair(self, src, dst, nnodes, to_freq):
+        N, Kp, H = self.N_t, self.half_cols, self.N_t // 2
+        if to_freq:
+            x = src.numpy().reshape(2, nnodes, N)
+            out = np.zeros((2, nnodes, Kp), complex)
+            out[..., :H + 1] = np.fft.ifft(x, axis=2)[..., :H + 1]
+            dst.copy_(torch.from_numpy(out.reshape(-1)))
+        else:
+            Y = src.numpy().reshape(2, nnodes, Kp)[..., :H + 1]
+            y = N * np.fft.irfft(np.conj(Y), n=N, axis=2)            # fft of the Hermitian extension
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(y).reshape(-1)))
+
+    def slab_reduce_half(self, w, out):
+        self.slab_reduce(w, out, self._half_kidx())
+
+    def slab_finish_half(self, w, gathered):
+        self.slab_finish(w, gathered, self._half_kidx())
 
     # ---- Krylov pieces (numpy), same contracts as ParaDiagHandle
     def _op(self):
@@ -91,13 +120,15 @@ class OracleStageBackend:
             norm2_out[0] = float(np.vdot(wn, wn).real)
         return w
 
-    def slab_finish(self, w, gathered):
+    def slab_finish(self, w, gathered, kidx=None):
         pc, G, r = self.pc, self.G, self.r
-        W = w.numpy().reshape(2, self.n_r, self.N_t)
-        g = gathered.numpy().reshape(G, 6, self.N_t)
-        rP, rM = self._rot_in(W)
+        kidx = np.arange(self.N_t) if kidx is None else kidx
+        K = len(kidx)
+        W = w.numpy().reshape(2, self.n_r, K)
+        g = gathered.numpy().reshape(G, 6, K)
+        rP, rM = self._rot_in(W, kidx)
         m = self.body[r]
-        for k in range(self.N_t):
+        for col, k in enumerate(kidx):
             a, b = pc.a[k], pc.b[k]
             inv = [np.linalg.inv(self._T(ms, k)) for ms in self.body]
             A = np.zeros((G - 1, G - 1), complex)
@@ -108,14 +139,14 @@ class OracleStageBackend:
                     A[s - 1, s - 2] = -a * a * inv[s - 1][-1, 0]
                 if s < G - 1:
                     A[s - 1, s] = -a * a * inv[s][0, -1]
-                rhs[s - 1, 0] = g[s, 4, k] - a * (g[s - 1, 2, k] + g[s, 0, k])
-                rhs[s - 1, 1] = g[s, 5, k] - a * (g[s - 1, 3, k] + g[s, 1, k])
+                rhs[s - 1, 0] = g[s, 4, col] - a * (g[s - 1, 2, col] + g[s, 0, col])
+                rhs[s - 1, 1] = g[s, 5, col] - a * (g[s - 1, 3, col] + g[s, 1, col])
             zs = np.linalg.solve(A, rhs)
             zl = zs[r - 1] if r > 0 else np.zeros(2)
             zr = zs[r] if r < G - 1 else np.zeros(2)
             out = []
             for slot, rr in ((0, rP), (1, rM)):
-                v = rr[1:1 + m, k].copy()
+                v = rr[1:1 + m, col].copy()
                 v[0] -= a * zl[slot]
                 v[-1] -= a * zr[slot]
                 out.append(np.linalg.solve(self._T(m, k), v))
@@ -123,8 +154,8 @@ class OracleStageBackend:
             zM = np.zeros(self.n_r, complex)
             zP[1:1 + m], zM[1:1 + m] = out[0], np.conj(out[1])
             zP[0], zM[0] = zl[0], np.conj(zl[1])
-            W[0, :, k] = zP + zM
-            W[1, :, k] = (-1j * pc.sigma[k] * pc.z[k]) * (zP - zM)
+            W[0, :, col] = zP + zM
+            W[1, :, col] = (-1j * pc.sigma[k] * pc.z[k]) * (zP - zM)
 
     def stage_fft(self, src, dst, nlines, inverse):
         import scipy.fft as sfft
@@ -190,6 +221,34 @@ def test_distributed_apply_matches_single_process_oracle(world, N_x, N_t):
     for r in range(world):
         ok, err = ret[r]
         assert ok, (r, err)
+
+
+def _real_worker(rank, world, port, N_x, N_t, gamma, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pc_fast import DiagFFTPCFast
+        factory = lambda **kw: OracleStageBackend(N_x, N_t, 2.0, gamma, **kw)
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=gamma, backend_factory=factory, mode="slab")
+        xg = np.random.default_rng(0).standard_normal(2 * (N_x + 1) * N_t)
+        x_local = dpc.scatter_from_global(torch.from_numpy(xg))               # float64 block
+        y_local = dpc.apply_real(x_local)
+        assert y_local.dtype == torch.float64
+        yg = dpc.gather_to_global(y_local.to(torch.complex128)).numpy()
+        ref = DiagFFTPCFast(N_x, N_t, 2.0, gamma).apply(xg + 0j)
+        ret[rank] = float(np.linalg.norm(yg - ref.real) / np.linalg.norm(ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N_x,N_t", [(2, 16, 8), (3, 22, 16)])
+def test_slab_mode_real_input_apply_matches_single_process_oracle(world, N_x, N_t):
+    # host logic of DistributedDiagFFTPC.apply_real (half spectrum through the slab-distributed solve)
+    ret = mp.Manager().dict()
+    mp.spawn(_real_worker, args=(world, _free_port(), N_x, N_t, 0.5, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] < 1e-11, (r, ret[r])
 
 
 @pytest.mark.parametrize("world,N_x,N_t", [(2, 16, 6), (3, 22, 5)])

@@ -91,3 +91,43 @@ def test_distributed_gmres_equals_single_gpu(N_x, N_t):
     for r in range(world):
         its, its_s, reason, err, mv_err = ret[r]
         assert reason == "CONVERGED_RTOL" and abs(its - its_s) <= 1 and err < 1e-6 and mv_err == 0.0, ret[r]
+
+
+def _real_worker(rank, world, port, cases, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from optimal_control_paradiag_b200 import ParaDiagHandle
+        from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
+        errs = []
+        for (N_x, N_t) in cases:
+            dpc = DistributedDiagFFTPC(N_x, N_t, device=rank, mode="slab")
+            xg = torch.randn(2 * (N_x + 1) * N_t, dtype=torch.float64, device=f"cuda:{rank}",
+                             generator=torch.Generator(device=f"cuda:{rank}").manual_seed(7))
+            y_local = dpc.apply_real(dpc.scatter_from_global(xg))
+            yg = dpc.gather_to_global(y_local.to(torch.complex128)).real
+            with ParaDiagHandle(N_x, N_t, device=rank) as h:
+                ref = h.pc_apply_real(xg)                       # single-GPU half-spectrum path
+                refc = h.pc_apply(xg.to(torch.complex128)).real  # and the complex path
+            errs.append((float(torch.linalg.norm(yg - ref) / torch.linalg.norm(ref)),
+                         float(torch.linalg.norm(yg - refc) / torch.linalg.norm(refc))))
+            dpc.backend.close()
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_real_input_apply_equals_single_gpu():
+    # DistributedDiagFFTPC.apply_real: half spectrum through the slab-distributed solve (all cases in one
+    # process group: N_t covered by the two-for-one kernel, by the per-line kernel (16384), several depths)
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cases = [(255, 128), (1024, 1024), (4096, 256), (20, 16384), (37, 512)]
+    ret = mp.Manager().dict()
+    mp.spawn(_real_worker, args=(world, _free_port(), cases, ret), nprocs=world, join=True)
+    for r in range(world):
+        for (e_half, e_cplx), case in zip(ret[r], cases):
+            assert e_half < 1e-10 and e_cplx < 1e-10, (r, case, e_half, e_cplx)
