@@ -566,7 +566,10 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
   bool converged = false, first = true;
   PD_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * (size_t)len, st));
 
-  std::vector<hcplx> H((size_t)(restart + 1) * restart), g(restart + 1), cs(restart), sn(restart), yk(restart);
+  // Hessenberg matrix, column-major with stride restart + 1; columns are appended as the iteration proceeds
+  // (restart = 300 would otherwise cost a 1.4 MB zero-fill per solve, as much as a whole 5-iteration solve of
+  // the small configurations)
+  std::vector<hcplx> H, g(restart + 1), cs(restart), sn(restart), yk(restart);
   auto Hat = [&](int i, int j) -> hcplx& { return H[(size_t)j * (restart + 1) + i]; };
 
   while (!converged && (its < max_it || first)) {
@@ -620,6 +623,7 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
       if ((rc = maxpy_list(h, kc->V.data(), j + 1, hdev, -1.0, w, len, hdev + (j + 1), st))) return rc;
       PD_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(cplx) * (size_t)(j + 2), cudaMemcpyDeviceToHost, st));
       PD_CUDA(cudaStreamSynchronize(st));
+      if (H.size() < (size_t)(j + 1) * (restart + 1)) H.resize((size_t)(j + 1) * (restart + 1));
       for (int i = 0; i <= j; ++i) Hat(i, j) = hhost[i];
       const double hn = sqrt(fmax(hhost[j + 1].re, 0.0));
       Hat(j + 1, j) = {hn, 0};
