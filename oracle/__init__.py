@@ -23,13 +23,25 @@ What it restates (all citations are into the read-only upstream checkout,
 * ``operator``     the all-at-once matrix of ``Build_L`` :86-179 and the
                    manufactured right-hand side of ``Build_f/g/IC`` :48-83.
 * ``gmres``        PETSc-KSPGMRES semantics selected by the options :347-359.
+* ``pc_alpha``     the alpha EXTENSION (no upstream counterpart): explicit P_alpha,
+                   per-frequency block LU, decoupled closed form.
 
-PARITY UNPINNED.  The upstream repository holds no golden vectors, fixtures or
-recorded logs for PC-apply outputs or GMRES iteration counts, and none of
-Firedrake / petsc4py / MUMPS is installable in this image, so the upstream
-code itself cannot be run.  The only known-answer checks upstream are the
-numpy identities of ``Code/mat_test.ipynb`` (FFT convention, circulant
-eigenvalues, 2x2 diagonalisation); the oracle is pinned against those
-(``tests/test_oracle_notebook.py``) and, beyond them, only against itself
-(three independent routes agreeing to ~1e-13 at small sizes).
+PARITY UNPINNED, with one exception.  The upstream repository holds no golden
+vectors, fixtures or recorded logs for PC-apply outputs or GMRES iteration
+counts, and none of Firedrake / petsc4py / MUMPS is installable in this image,
+so ``DiagFFTPC.apply`` and the Krylov solve themselves cannot be run.  Pinned:
+
+* the eigen-set-up stage: the upstream lines :387-436 (Lambda_1, Lambda_2, the
+  per-frequency ``eig`` / ``inv`` loop) are plain numpy and ARE executed,
+  unmodified, by ``tests/golden/make_reference_setup_golden.py``; ``eigs``
+  reproduces their output bit for bit and every route agrees with the
+  line-by-line route driven by those arrays
+  (``tests/test_reference_setup_golden.py``);
+* the numpy identities of ``Code/mat_test.ipynb`` (FFT convention, circulant
+  eigenvalues, 2x2 diagonalisation; ``tests/test_oracle_notebook.py``).
+
+Unpinned (restated from the source, checked only against itself -- three
+independent routes agreeing to ~1e-13 at small sizes): the P1 mass / stiffness
+assembly, the shifted solves with Dirichlet rows, the operator / right-hand
+side of ``Build_L`` / ``Build_f/g/IC`` and PETSc's GMRES semantics.
 """
