@@ -414,3 +414,22 @@ def test_gmres_solution_equals_the_direct_lu_baseline():
         x, its, hist, reason = h.gmres(h.build_rhs(), rtol=1e-12)
         assert reason == "CONVERGED_RTOL"
         assert rel(x.cpu().numpy(), direct + 0j) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["refsetup_81_1.npz", "refsetup_64_0.0001.npz", "refsetup_5_1.npz"])
+def test_pc_apply_against_the_route_driven_by_executed_upstream_setup(name):
+    # S, S^-1, Sigma, Lambda_2 as computed by the EXECUTED upstream lines :387-436 (tests/golden/
+    # make_reference_setup_golden.py) drive the line-by-line route; the CUDA path regenerates all of it in-kernel
+    from oracle.pc_ref_route import DiagFFTPCRefRoute
+    g = np.load(os.path.join(GOLDEN, name))
+    N_t, T, gamma = int(g["N_t"]), float(g["T"]), float(g["gamma"])
+    N_x = 40
+    pc = DiagFFTPCRefRoute(N_x, N_t, T, gamma)
+    assert np.array_equal(pc.Sigma, np.stack([g["Sigma_1"], g["Sigma_2"]], -1))
+    pc.Lambda_1, pc.Lambda_2 = g["Lambda_1"], g["Lambda_2"]
+    pc.S = np.stack([np.stack([g["S11"], g["S12"]], -1), np.stack([g["S21"], g["S22"]], -1)], -2)
+    pc.SI = np.stack([np.stack([g["SI11"], g["SI12"]], -1), np.stack([g["SI21"], g["SI22"]], -1)], -2)
+    with ParaDiagHandle(N_x, N_t, T=T, gamma=gamma) as h:
+        x = rand_x(h.size)
+        y = h.pc_apply(torch.tensor(x, device=DEV)).cpu().numpy()
+        assert rel(y, pc.apply(x)) < PC_TOL
