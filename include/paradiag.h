@@ -154,6 +154,37 @@ int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_dev, int64_t 
 int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, void* stream);
 int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream);
 
+/* Slab mode with the PEER-STORE EXCHANGE: the whole distributed apply behind one call, no host-launched
+ * collective on the data path.  Every rank owns a small "symmetric" buffer that all ranks map (cudaIpc between
+ * processes, plain peer access inside one process).  The kernel that produces a slab's functionals stores them
+ * straight into slot [rank] of every rank's buffer over NVLink and publishes a per-frequency-block flag; the
+ * separator-solve kernel waits (bounded) for the flags of its own frequency block.  Epochs and parities live in
+ * device memory, so the sequence is capturable in a CUDA graph.  Replaces, for a distributed x-axis, the same
+ * upstream lines as pd_pc_apply (:491-553); the reference has no parallel decomposition to mirror.
+ *   pd_slab_comm_create  : allocate this rank's buffer; ipc_handle_out (64 bytes, may be NULL) receives its
+ *                          cudaIpcMemHandle_t, *base_out (may be NULL) its device address.
+ *   pd_slab_comm_connect : mode 0: `peers` = slab_count x 64-byte IPC handles in rank order (other processes);
+ *                          mode 1: `peers` = void*[slab_count] device addresses valid in THIS process
+ *                          (peer_devices[r] = CUDA ordinal of rank r's buffer, NULL if all on this device).
+ *   pd_slab_apply        : y_local = P^-1 x on this rank's (2, n_r, N_t) complex128 block.  Collective in the
+ *                          sense that every rank must call it the same number of times.
+ *   pd_slab_apply_real   : the same on float64 blocks (half spectrum), power-of-two N_t in [128, 16384].
+ *   pd_slab_apply_begin / _end : the two halves (up to the peer stores / from the wait on), so that one process
+ *                          driving several ranks can issue all first halves before any second half (kernels that
+ *                          wait on one another must never be queued on ONE GPU in the wrong order).
+ *   pd_slab_apply_profile: one apply with CUDA events between its stages, ms[0..6] = {inverse FFT, pass A,
+ *                          interface levels, functionals + peer stores, wait + separator solve, pass B, FFT}.
+ *   pd_slab_comm_status  : *timed_out != 0 if a bounded wait expired since the last call (a peer never
+ *                          delivered); *epoch = applies completed.  Synchronises the device.               */
+int pd_slab_comm_create(pd_handle* h, void* ipc_handle_out, void** base_out);
+int pd_slab_comm_connect(pd_handle* h, const void* peers, int mode, const int* peer_devices);
+int pd_slab_comm_status(pd_handle* h, int* timed_out, uint64_t* epoch);
+int pd_slab_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+int pd_slab_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+int pd_slab_apply_begin(pd_handle* h, const void* x_dev, void* stream, int real_input);
+int pd_slab_apply_end(pd_handle* h, void* y_dev, void* stream, int real_input);
+int pd_slab_apply_profile(pd_handle* h, const void* x_dev, void* y_dev, void* stream, float* ms, int nms);
+
 /* Matrix-free action of the Jacobian of Build_L (:86-179, pc=True branches):
  * y = A x with Dirichlet rows as identity.  x and y must not alias.             */
 int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);

@@ -56,6 +56,14 @@ SYMBOLS = {
     "pd_stage_rfft_pair": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "pd_slab_reduce_half": (_I, [_VP, _VP, _VP, _VP]),
     "pd_slab_finish_half": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_slab_comm_create": (_I, [_VP, _VP, C.POINTER(_VP)]),
+    "pd_slab_comm_connect": (_I, [_VP, _VP, _I, C.POINTER(_I)]),
+    "pd_slab_comm_status": (_I, [_VP, C.POINTER(_I), C.POINTER(C.c_uint64)]),
+    "pd_slab_apply": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_slab_apply_real": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_slab_apply_begin": (_I, [_VP, _VP, _VP, _I]),
+    "pd_slab_apply_end": (_I, [_VP, _VP, _VP, _I]),
+    "pd_slab_apply_profile": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_float), _I]),
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec_slab": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),

@@ -24,7 +24,7 @@ extern "C" int64_t pd_launch_count(const pd_handle* h) { return h ? h->launches 
 
 extern "C" int pd_destroy(pd_handle* h) {
   if (!h) return PD_OK;
-  cudaSetDevice(h->cfg.device);
+  PD_ON_DEVICE(h);
   pd_krylov_free(h);
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->twiddle_half) cudaFree(h->twiddle_half);
@@ -81,7 +81,7 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
     pd_set_error("pd_create: device %d out of range (%d devices)", cfg->device, ndev);
     return PD_ERR_INVALID;
   }
-  PD_CUDA(cudaSetDevice(cfg->device));
+  PdDeviceGuard pd_device_guard_(cfg->device);  // the caller's current device is restored on return
   pd_handle* h = new pd_handle();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
@@ -151,6 +151,7 @@ extern "C" int pd_stage_fft(pd_handle* h, const void* in_dev, void* out_dev, int
     pd_set_error("pd_stage_fft: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_fft_launch(h, (const cplx*)in_dev, (cplx*)out_dev, nlines, inverse, (cudaStream_t)stream);
 }
 
@@ -160,6 +161,7 @@ extern "C" int pd_stage_gamma(pd_handle* h, const void* in_dev, void* out_dev, i
     pd_set_error("pd_stage_gamma: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_gamma_launch(h, (const cplx*)in_dev, (cplx*)out_dev, nlines, inverse, (cudaStream_t)stream);
 }
 
@@ -168,6 +170,7 @@ extern "C" int pd_stage_solve(pd_handle* h, void* w_dev, void* stream) {
     pd_set_error("pd_stage_solve: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream);
 }
 
@@ -176,6 +179,7 @@ extern "C" int pd_slab_reduce(pd_handle* h, void* w_dev, void* out_dev, void* st
     pd_set_error("pd_slab_reduce: invalid argument or handle not in slab mode");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_slab_reduce_launch(h, (cplx*)w_dev, (cplx*)out_dev, (cudaStream_t)stream);
 }
 
@@ -184,6 +188,7 @@ extern "C" int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_de
     pd_set_error("pd_slab_finish: invalid argument or handle not in slab mode");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream);
 }
 
@@ -193,6 +198,7 @@ extern "C" int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, voi
     pd_set_error("pd_slab_reduce_half: invalid argument or handle not in slab mode");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (!pd_slab_half_supported(h)) {
     pd_set_error("pd_slab_reduce_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
@@ -205,11 +211,148 @@ extern "C" int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gather
     pd_set_error("pd_slab_finish_half: invalid argument or handle not in slab mode");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (!pd_slab_half_supported(h)) {
     pd_set_error("pd_slab_finish_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream, 1);
+}
+
+// ---- slab mode with the peer-store exchange: the whole distributed apply behind one call
+extern "C" int pd_slab_comm_create(pd_handle* h, void* ipc_handle_out, void** base_out) {
+  if (!h || h->slab_count <= 1) {
+    pd_set_error("pd_slab_comm_create: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  return pd_slab_comm_create_impl(h, ipc_handle_out, base_out);
+}
+
+extern "C" int pd_slab_comm_connect(pd_handle* h, const void* peers, int mode, const int* peer_devices) {
+  if (!h || !peers || h->slab_count <= 1 || (mode != 0 && mode != 1)) {
+    pd_set_error("pd_slab_comm_connect: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  return pd_slab_comm_connect_impl(h, peers, mode, peer_devices);
+}
+
+extern "C" int pd_slab_comm_status(pd_handle* h, int* timed_out, uint64_t* epoch) {
+  if (!h || h->slab_count <= 1) {
+    pd_set_error("pd_slab_comm_status: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  unsigned long long ep = 0;
+  int rc = pd_slab_comm_status_impl(h, timed_out, &ep);
+  if (epoch) *epoch = ep;
+  return rc;
+}
+
+static int slab_apply_check(pd_handle* h, const void* p, const char* who, int real_input) {
+  if (!h || !p || h->slab_count <= 1) {
+    pd_set_error("%s: invalid argument or handle not in slab mode", who);
+    return PD_ERR_INVALID;
+  }
+  if (!pd_slab_comm_ready(h)) {
+    pd_set_error("%s: the peer-store exchange is not connected (pd_slab_comm_create / pd_slab_comm_connect)", who);
+    return PD_ERR_INVALID;
+  }
+  if (real_input && !pd_slab_half_supported(h)) {
+    pd_set_error("%s: the real-input path needs a power-of-two N_t in [128, 16384] (got %d)", who, h->cfg.N_t);
+    return PD_ERR_UNSUPPORTED;
+  }
+  return PD_OK;
+}
+
+// first half: time transform of this rank's lines, local elimination, functionals pushed to every rank
+static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_input, cudaEvent_t* ev) {
+  int rc = ensure_work(h);
+  if (rc) return rc;
+  if (real_input)
+    rc = pd_stage_rfft_pair(h, x, h->work, h->n, 1, st);
+  else
+    rc = pd_fft_launch(h, (const cplx*)x, h->work, 2 * (int64_t)h->n, 1, st);
+  if (rc) return rc;
+  if (ev) cudaEventRecord(ev[0], st);
+  return pd_slab_reduce_launch(h, h->work, nullptr, st, real_input, ev ? ev + 1 : nullptr);
+}
+
+// second half: wait for the peers' functionals, separator solve, back-substitution, time transform
+static int slab_end(pd_handle* h, void* y, cudaStream_t st, int real_input, cudaEvent_t* ev) {
+  int rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev);
+  if (rc) return rc;
+  if (ev) cudaEventRecord(ev[1], st);
+  if (real_input) return pd_stage_rfft_pair(h, h->work, y, h->n, 0, st);
+  return pd_fft_launch(h, h->work, (cplx*)y, 2 * (int64_t)h->n, 0, st);
+}
+
+extern "C" int pd_slab_apply_begin(pd_handle* h, const void* x_dev, void* stream, int real_input) {
+  int rc = slab_apply_check(h, x_dev, "pd_slab_apply_begin", real_input);
+  if (rc) return rc;
+  PD_ON_DEVICE(h);
+  return slab_begin(h, x_dev, (cudaStream_t)stream, real_input, nullptr);
+}
+
+extern "C" int pd_slab_apply_end(pd_handle* h, void* y_dev, void* stream, int real_input) {
+  int rc = slab_apply_check(h, y_dev, "pd_slab_apply_end", real_input);
+  if (rc) return rc;
+  PD_ON_DEVICE(h);
+  return slab_end(h, y_dev, (cudaStream_t)stream, real_input, nullptr);
+}
+
+extern "C" int pd_slab_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  int rc = slab_apply_check(h, x_dev, "pd_slab_apply", 0);
+  if (rc) return rc;
+  if (!y_dev) {
+    pd_set_error("pd_slab_apply: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 0, nullptr))) return rc;
+  return slab_end(h, y_dev, (cudaStream_t)stream, 0, nullptr);
+}
+
+extern "C" int pd_slab_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
+  int rc = slab_apply_check(h, x_dev, "pd_slab_apply_real", 1);
+  if (rc) return rc;
+  if (!y_dev) {
+    pd_set_error("pd_slab_apply_real: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 1, nullptr))) return rc;
+  return slab_end(h, y_dev, (cudaStream_t)stream, 1, nullptr);
+}
+
+// one distributed apply with CUDA events between its stages: ms[0..6] = {inverse FFT, pass A, interface levels,
+// functionals + peer stores, wait for the peers + separator solve, pass B, forward FFT}.  Synchronises.
+extern "C" int pd_slab_apply_profile(pd_handle* h, const void* x_dev, void* y_dev, void* stream, float* ms, int nms) {
+  int rc = slab_apply_check(h, x_dev, "pd_slab_apply_profile", 0);
+  if (rc) return rc;
+  if (!y_dev || !ms || nms < 7) {
+    pd_set_error("pd_slab_apply_profile: invalid argument (need ms[7])");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  struct Events {
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Events() {
+      for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
+    }
+  } E;
+  for (int i = 0; i < 8; ++i) PD_CUDA(cudaEventCreate(&E.ev[i]));
+  PD_CUDA(cudaEventRecord(E.ev[0], st));
+  if ((rc = slab_begin(h, x_dev, st, 0, &E.ev[1]))) return rc;   // ev[1] ifft, ev[2] pass A, ev[3] interface
+  PD_CUDA(cudaEventRecord(E.ev[4], st));                          // functionals + peer stores
+  if ((rc = slab_end(h, y_dev, st, 0, &E.ev[5]))) return rc;      // ev[5] separator solve, ev[6] pass B
+  PD_CUDA(cudaEventRecord(E.ev[7], st));
+  PD_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 7; ++i) PD_CUDA(cudaEventElapsedTime(&ms[i], E.ev[i], E.ev[i + 1]));
+  return PD_OK;
 }
 
 // both fields of `nnodes` node lines at once: (2, nnodes, N_t) float64 <-> (2, nnodes, Kp) complex half spectra
@@ -220,6 +363,7 @@ extern "C" int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_de
     pd_set_error("pd_stage_rfft_pair: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (!pd_rfft_supported(h)) {
     pd_set_error("pd_stage_rfft_pair: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
@@ -234,6 +378,7 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
     pd_set_error("pd_pc_apply: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
     pd_set_error("pd_pc_apply: handle is sharded (k_count/n_local/slab set); use the stage API");
     return PD_ERR_INVALID;
@@ -263,7 +408,8 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
     pd_set_error("pd_pc_apply_profile: invalid argument (need ms[5])");
     return PD_ERR_INVALID;
   }
-  if (h->kcount != h->cfg.N_t || h->nloc != h->n) {
+  PD_ON_DEVICE(h);
+  if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
     pd_set_error("pd_pc_apply_profile: handle is sharded");
     return PD_ERR_INVALID;
   }
@@ -274,7 +420,15 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_work(h);
   if (rc) return rc;
-  cudaEvent_t ev[6];
+  // events are destroyed on every path out of this function
+  struct Events {
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Events() {
+      for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
+    }
+  } E;
+  cudaEvent_t* ev = E.ev;
   for (int i = 0; i < 6; ++i) PD_CUDA(cudaEventCreate(&ev[i]));
   const int64_t nlines = 2 * (int64_t)h->n;
   PD_CUDA(cudaEventRecord(ev[0], st));
@@ -287,7 +441,6 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
   PD_CUDA(cudaStreamSynchronize(st));
   if (!rc)
     for (int i = 0; i < 5; ++i) PD_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-  for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
 
@@ -297,6 +450,7 @@ extern "C" int pd_stage_rfft(pd_handle* h, const void* in_dev, void* out_dev, in
     pd_set_error("pd_stage_rfft: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_rfft_launch(h, in_dev, out_dev, nlines, to_freq, (cudaStream_t)stream);
 }
 
@@ -305,8 +459,13 @@ extern "C" int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream) {
     pd_set_error("pd_stage_solve_half: invalid argument or sharded handle");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (h->cfg.alpha != 1.0) {
     pd_set_error("pd_stage_solve_half: alpha != 1 is not supported on the real-input path");
+    return PD_ERR_UNSUPPORTED;
+  }
+  if (!pd_rfft_supported(h)) {  // the interface workspaces are sized for N_t columns; Kp > N_t for N_t < 8
+    pd_set_error("pd_stage_solve_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream, nullptr, 1);
@@ -317,6 +476,7 @@ extern "C" int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, vo
     pd_set_error("pd_pc_apply_real: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (h->kcount != h->cfg.N_t || h->nloc != h->n || h->slab_count > 1) {
     pd_set_error("pd_pc_apply_real: handle is sharded; the real-input path is single-GPU");
     return PD_ERR_INVALID;
@@ -355,7 +515,7 @@ extern "C" int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host) 
     pd_set_error("pd_pc_apply_host: invalid argument");
     return PD_ERR_INVALID;
   }
-  PD_CUDA(cudaSetDevice(h->cfg.device));
+  PD_ON_DEVICE(h);
   const size_t bytes = sizeof(cplx) * 2 * (size_t)h->n * h->cfg.N_t;
   if (!h->stage_x) {
     PD_CUDA(cudaMalloc(&h->stage_x, bytes));
@@ -376,6 +536,7 @@ extern "C" int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* str
     pd_set_error("pd_matvec: invalid argument (x and y must be distinct device vectors)");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (h->slab_count > 1) {
     pd_set_error("pd_matvec: handle is in slab mode; use pd_matvec_slab");
     return PD_ERR_INVALID;
@@ -389,6 +550,7 @@ extern "C" int pd_matvec_slab(pd_handle* h, const void* x_dev, const void* halo_
     pd_set_error("pd_matvec_slab: invalid argument or handle not in slab mode");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0, (const cplx*)halo_lo_dev,
                           (const cplx*)halo_hi_dev);
 }
@@ -398,6 +560,7 @@ extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* 
     pd_set_error("pd_pc_matvec: invalid argument (x and y must be distinct device vectors)");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   if (h->cfg.alpha != 1.0) {
     pd_set_error("pd_pc_matvec: only the alpha = 1 block circulant has a matvec kernel");
     return PD_ERR_UNSUPPORTED;
@@ -410,6 +573,7 @@ extern "C" int pd_matvec_real(pd_handle* h, const void* x_dev, void* y_dev, void
     pd_set_error("pd_matvec_real: invalid argument (distinct float64 device vectors, unsharded handle)");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0, nullptr, nullptr, 1);
 }
 
@@ -418,6 +582,7 @@ extern "C" int pd_build_rhs_real(pd_handle* h, void* b_dev, void* stream) {
     pd_set_error("pd_build_rhs_real: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_rhs_launch(h, (cplx*)b_dev, (cudaStream_t)stream, 1);
 }
 
@@ -426,5 +591,6 @@ extern "C" int pd_build_rhs(pd_handle* h, void* b_dev, void* stream) {
     pd_set_error("pd_build_rhs: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   return pd_rhs_launch(h, (cplx*)b_dev, (cudaStream_t)stream);
 }

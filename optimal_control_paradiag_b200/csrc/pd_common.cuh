@@ -62,6 +62,22 @@ void pd_set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+// Every extern "C" entry point that takes a handle runs on the handle's device and leaves the caller's
+// current device as it found it (one process may hold handles on several GPUs).
+struct PdDeviceGuard {
+  int prev, dev;
+  explicit PdDeviceGuard(int device) : prev(-1), dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~PdDeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  PdDeviceGuard(const PdDeviceGuard&) = delete;
+  PdDeviceGuard& operator=(const PdDeviceGuard&) = delete;
+};
+#define PD_ON_DEVICE(h) PdDeviceGuard pd_device_guard_((h)->cfg.device)
+
 // ------------------------------------------------------------------ the handle
 static const int PD_MAX_FFT_PASSES = 16;
 
@@ -127,9 +143,15 @@ int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int 
 int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st);
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr, int half_spectrum = 0);
-int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0);
-int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0);
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0,
+                          cudaEvent_t* ev = nullptr);
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0,
+                          cudaEvent_t* ev = nullptr);
 bool pd_slab_half_supported(const pd_handle* h);
+int pd_slab_comm_create_impl(pd_handle* h, void* ipc_handle_out, void** base_out);
+int pd_slab_comm_connect_impl(pd_handle* h, const void* peers, int mode, const int* peer_devices);
+int pd_slab_comm_status_impl(pd_handle* h, int* timed_out, unsigned long long* epoch);
+bool pd_slab_comm_ready(const pd_handle* h);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
                      const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr, int real_vectors = 0);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors = 0);

@@ -15,6 +15,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "pd_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -690,13 +692,15 @@ pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nl
 // --------------------------------------------------------------- host side
 // cudaFuncSetAttribute once per kernel instantiation and device instead of on every launch (the launch-bound
 // small configurations pay for every host call)
+// (the mask is atomic: handles may be used from several host threads; a racing second call of
+// cudaFuncSetAttribute with the same value is harmless)
 #define PD_SET_SMEM_ONCE(kernel, bytes)                                                                  \
   do {                                                                                                   \
-    static unsigned long long pd_done_mask = 0;                                                          \
+    static std::atomic<unsigned long long> pd_done_mask{0};                                              \
     const int pd_dev = h->cfg.device & 63;                                                               \
-    if (!(pd_done_mask >> pd_dev & 1ull)) {                                                              \
+    if (!(pd_done_mask.load(std::memory_order_acquire) >> pd_dev & 1ull)) {                              \
       PD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
-      pd_done_mask |= 1ull << pd_dev;                                                                    \
+      pd_done_mask.fetch_or(1ull << pd_dev, std::memory_order_release);                                  \
     }                                                                                                    \
   } while (0)
 

@@ -440,6 +440,7 @@ extern "C" int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, cons
     pd_set_error("pd_mdot: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   std::vector<const cplx*> vs(nv);
   for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
   h->kry_real = 0;
@@ -453,6 +454,7 @@ extern "C" int pd_maxpy(pd_handle* h, const void* V_dev, int64_t ld, int nv, con
     pd_set_error("pd_maxpy: invalid argument");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   std::vector<const cplx*> vs(nv);
   for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
   return maxpy_list(h, vs.data(), nv, (const cplx*)coef_dev, sign, (cplx*)w_dev, len, (cplx*)norm2_out_dev,
@@ -523,6 +525,7 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
     pd_set_error("pd_gmres: handle is sharded (k_count/n_local set); use the stage API");
     return PD_ERR_INVALID;
   }
+  PD_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   // real vectors: 2 n N_t doubles, handled by the BLAS-1 kernels as n N_t complex pairs (the real part of
   // a pair-wise conj(v) w sum is the real inner product; imaginary parts are zeroed in the reduction)

@@ -52,6 +52,7 @@
 #define PD_PCR_THREADS 256
 #define PD_PCR_MAXROWS 4   // rows per thread in the PCR kernel
 #define PD_MAX_LEVELS 8
+#define PD_MAX_SLABS 16
 
 struct SolveParams {
   int n, m, K, kbegin, N_t;
@@ -74,6 +75,7 @@ struct SlabPtrs {
   cplx* lastl;        // [2][K]     last entry of the last chunk's local solve (pass A)
   const cplx* green;  // [P][2][K]  interface Green's vectors T_1^-1 e_0 (slot 0), T_1^-1 e_{P-1} (slot 1)
   const cplx* zout;   // [4][K]     outer separator values: left (+, -), right (+, -)
+  unsigned long long* epoch_bump;  // peer-store exchange: pass B marks the apply complete (else null)
 };
 
 struct KCoef {
@@ -750,6 +752,9 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       wp[(int64_t)(sp.m + 1) * sp.K] = zero;
     }
   }
+  // peer-store exchange: this apply's functionals and separator kernels are complete (stream order), the next
+  // apply's have not started
+  if (SLAB && sl.epoch_bump && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *sl.epoch_bump += 1ull;
 }
 
 // ------------------------------------------------------------ slab-mode kernels
@@ -760,12 +765,44 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
 // with rv_s = 1/V_{m_s}, dvv_s = (V_{m_s} - V_{m_s - 1}) / V_{m_s} (cancellation-free, see Sys) and
 // f_s / l_s the first / last entry of the slab-local solve with zero neighbours.
 
+// ---- peer-store exchange of the slab functionals (the fused compute + collective step of slab mode)
+// Every rank owns one "symmetric" buffer, mapped into all ranks (cudaIpc between processes, plain peer access
+// inside one process):   gathered[2 parities][G ranks][6][kmax] complex  +  flags[2][G][nflag] (uint64 epochs).
+// The kernel that produces a slab's six functionals per frequency STORES them straight into slot [rank] of
+// every rank's buffer (NVLink peer stores, fire and forget), fences, and publishes one flag per (rank, block of
+// PD_KB frequencies) = the apply's epoch.  The kernel that consumes them (separator solve) waits at its head for
+// the G flags of ITS frequency block only.  No host-launched collective, no extra kernel, no barrier:
+//   * parity = epoch & 1 double-buffers the slots: a rank can be at most one apply ahead of a peer (its
+//     epoch e+1 separator solve needs the peer's e+1 functionals, which the peer issues after finishing e);
+//   * epochs live in device memory (bumped by pass B), so the whole apply is capturable in a CUDA graph;
+//   * the wait is bounded (PD_SLAB_SPIN_LIMIT clock ticks): on expiry the kernel raises err[0] and goes on,
+//     the host reports it (pd_slab_comm_status) -- a dead peer can never hang the GPU.
+#define PD_SLAB_SPIN_LIMIT (8ll * 1000 * 1000 * 1000)
+struct SlabCommDev {
+  cplx* peer_gath[PD_MAX_SLABS];                  // every rank's gathered buffer (own included)
+  unsigned long long* peer_flag[PD_MAX_SLABS];    // every rank's flag array
+  const unsigned long long* epoch;                // completed applies of THIS rank
+  int* err;
+  int64_t kmax;
+  int nflag, G, rank;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // out[6][K] = (f+, f-, l+, l-, rho_sep+, rho_sep-) of this slab
+template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
-                           cplx* __restrict__ out) {
+                           cplx* __restrict__ out, SlabCommDev cm) {
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
-  if (kk >= sp.K) return;
+  if (kk < sp.K) {
   const int64_t K = sp.K;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
@@ -798,11 +835,32 @@ pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp
   }
   cplx sP = cmake(0, 0), sM = cmake(0, 0);
   if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
-  out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
-  out[4 * K + kk] = sP; out[5 * K + kk] = sM;
+  if (!PUSH) {
+    out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
+    out[4 * K + kk] = sP; out[5 * K + kk] = sM;
+  } else {
+    // slot [parity][rank] of EVERY rank's buffer (peer stores over NVLink; the own copy is a local store)
+    const unsigned long long ep = *cm.epoch + 1ull;
+    const int64_t slot = (((int64_t)(ep & 1ull) * cm.G + cm.rank) * 6) * cm.kmax + kk;
+    for (int p = 0; p < cm.G; ++p) {
+      cplx* g = cm.peer_gath[p] + slot;
+      g[0] = fP; g[cm.kmax] = fM; g[2 * cm.kmax] = lP; g[3 * cm.kmax] = lM;
+      g[4 * cm.kmax] = sP; g[5 * cm.kmax] = sM;
+    }
+  }
+  }  // kk < sp.K
+  if (PUSH) {
+    // publish: every thread's stores are ordered before the flag at system scope
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < cm.G) {
+      const unsigned long long ep = *cm.epoch + 1ull;
+      unsigned long long* f = cm.peer_flag[threadIdx.x] + ((int64_t)(ep & 1ull) * cm.G + cm.rank) * cm.nflag + blockIdx.x;
+      st_release_sys(f, ep);
+    }
+  }
 }
 
-#define PD_MAX_SLABS 16
 struct SlabGeom {
   int G, rank;
   int body[PD_MAX_SLABS];  // m_s of every slab
@@ -831,12 +889,31 @@ pd_slab_coef_kernel(SolveParams sp, SlabGeom sg, cplx* __restrict__ coef) {
 }
 
 // gathered[G][6][K] -> zout[4][K] (left+, left-, right+, right-) of this rank
+template <bool WAIT>
 __global__ void __launch_bounds__(PD_KB)
-pd_slab_global_kernel(const cplx* __restrict__ gathered, SolveParams sp, SlabGeom sg,
-                      const cplx* __restrict__ coef, cplx* __restrict__ zout) {
+pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveParams sp, SlabGeom sg,
+                      const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm) {
+  if (WAIT) {
+    // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
+    const unsigned long long ep = *cm.epoch + 1ull;
+    if (threadIdx.x < cm.G) {
+      const unsigned long long* f = cm.peer_flag[cm.rank] + ((int64_t)(ep & 1ull) * cm.G + threadIdx.x) * cm.nflag + blockIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < ep) {
+        if (clock64() - t0 > PD_SLAB_SPIN_LIMIT) {
+          atomicExch(cm.err, 1);
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    gathered = cm.peer_gath[cm.rank] + (int64_t)(ep & 1ull) * cm.G * 6 * cm.kmax;
+  }
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const int64_t K = sp.K;
+  const int64_t GS = gstride;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const int G = sg.G;
   cplx rv[PD_MAX_SLABS], dvv[PD_MAX_SLABS];
@@ -852,8 +929,8 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, SolveParams sp, SlabGeo
   cplx cp[PD_MAX_SLABS], dP[PD_MAX_SLABS], dM[PD_MAX_SLABS];
   cplx prevc = cmake(0, 0), pP = cmake(0, 0), pM = cmake(0, 0);
   for (int r = 1; r < G; ++r) {
-    const cplx* gl = gathered + ((int64_t)(r - 1) * 6) * K + kk;  // slab left of separator r
-    const cplx* gr = gathered + ((int64_t)r * 6) * K + kk;        // slab right of it (owns the separator)
+    const cplx* gl = gathered + ((int64_t)(r - 1) * 6) * GS + kk;  // slab left of separator r
+    const cplx* gr = gathered + ((int64_t)r * 6) * GS + kk;        // slab right of it (owns the separator)
     cplx di, lo, up;
     if (t.diag) {
       di = cmake(kc.sh.x - 2.0 * kc.a.x, kc.sh.y - 2.0 * kc.a.y);
@@ -863,8 +940,9 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, SolveParams sp, SlabGeo
       lo = r > 1 ? cmul(kc.a, rv[r - 1]) : cmake(0, 0);
       up = r < G - 1 ? cmul(kc.a, rv[r]) : cmake(0, 0);
     }
-    cplx rP = cfms(kc.a, cadd(gl[2 * K], gr[0]), gr[4 * K]);
-    cplx rM = cfms(kc.a, cadd(gl[3 * K], gr[K]), gr[5 * K]);
+    // (__ldcg: the peers' stores land in L2; never read these through L1)
+    cplx rP = cfms(kc.a, cadd(__ldcg(gl + 2 * GS), __ldcg(gr)), __ldcg(gr + 4 * GS));
+    cplx rM = cfms(kc.a, cadd(__ldcg(gl + 3 * GS), __ldcg(gr + GS)), __ldcg(gr + 5 * GS));
     const cplx inv = crcp(cfms(lo, prevc, di));
     prevc = cmul(up, inv);
     pP = cmul(cfms(lo, pP, rP), inv);
@@ -906,6 +984,16 @@ struct SolvePlan {
   cplx* green_h;     // the same two plan-time tables for the half spectrum of the real-input path
   cplx* slabcoef_h;  //   (columns 0 .. N_t/2 in natural order, row stride Kp)
   SlabGeom sg;
+  // peer-store exchange (pd_slab_comm_*): null / 0 until created
+  void* comm_base;                    // this rank's symmetric buffer (gathered + flags), one allocation
+  size_t comm_bytes;
+  int64_t comm_kmax;
+  int comm_nflag;
+  void* comm_peer[PD_MAX_SLABS];      // mapped base of every rank's buffer
+  bool comm_ipc[PD_MAX_SLABS];        // opened with cudaIpcOpenMemHandle (to be closed)
+  bool comm_connected;
+  unsigned long long* comm_epoch;     // device: completed applies
+  int* comm_err;                      // device: a bounded wait expired
 };
 
 static SolvePlan* plan_of(pd_handle* h) { return reinterpret_cast<SolvePlan*>(h->solve_plan); }
@@ -923,6 +1011,11 @@ void pd_solve_free(pd_handle* h) {
   if (pl->green) cudaFree(pl->green);
   if (pl->zout) cudaFree(pl->zout);
   if (pl->slabcoef) cudaFree(pl->slabcoef);
+  for (int r = 0; r < PD_MAX_SLABS; ++r)
+    if (pl->comm_ipc[r] && pl->comm_peer[r]) cudaIpcCloseMemHandle(pl->comm_peer[r]);
+  if (pl->comm_base) cudaFree(pl->comm_base);
+  if (pl->comm_epoch) cudaFree(pl->comm_epoch);
+  if (pl->comm_err) cudaFree(pl->comm_err);
   delete pl;
   h->solve_plan = nullptr;
 }
@@ -958,6 +1051,7 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = half_spectrum ? pl->green_h : pl->green; sl.zout = pl->zout;
+  sl.epoch_bump = nullptr;
 }
 
 // levels 1..top: reduce, PCR on the top system, back-substitute; leaves the level-1 solution in R[1]
@@ -1125,19 +1219,137 @@ bool pd_slab_half_supported(const pd_handle* h) {
   return pl && pl->slabcoef_h != nullptr;
 }
 
+// ---- peer-store exchange: set-up
+static size_t comm_gath_bytes(int G, int64_t kmax) { return sizeof(cplx) * 2 * (size_t)G * 6 * (size_t)kmax; }
+
+static SlabCommDev comm_dev_of(pd_handle* h) {
+  SolvePlan* pl = plan_of(h);
+  SlabCommDev cm;
+  memset(&cm, 0, sizeof(cm));
+  cm.G = pl->sg.G; cm.rank = pl->sg.rank; cm.kmax = pl->comm_kmax; cm.nflag = pl->comm_nflag;
+  cm.epoch = pl->comm_epoch; cm.err = pl->comm_err;
+  const size_t goff = comm_gath_bytes(cm.G, cm.kmax);
+  for (int r = 0; r < cm.G; ++r) {
+    cm.peer_gath[r] = reinterpret_cast<cplx*>(pl->comm_peer[r]);
+    cm.peer_flag[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(pl->comm_peer[r]) + goff);
+  }
+  return cm;
+}
+
+// allocates this rank's symmetric buffer; ipc_handle_out (64 bytes, optional) receives its cudaIpcMemHandle_t
+int pd_slab_comm_create_impl(pd_handle* h, void* ipc_handle_out, void** base_out) {
+  SolvePlan* pl = plan_of(h);
+  if (!pl->comm_base) {
+    const int G = pl->sg.G;
+    pl->comm_kmax = ((int64_t)h->cfg.N_t + 7) & ~7ll;  // covers the half spectrum's Kp as well (N_t >= 128)
+    if (pl->comm_kmax < 8) pl->comm_kmax = 8;
+    pl->comm_nflag = (int)((pl->comm_kmax + PD_KB - 1) / PD_KB);
+    pl->comm_bytes = comm_gath_bytes(G, pl->comm_kmax) + sizeof(unsigned long long) * 2 * (size_t)G * pl->comm_nflag;
+    PD_CUDA(cudaMalloc(&pl->comm_base, pl->comm_bytes));
+    PD_CUDA(cudaMemset(pl->comm_base, 0, pl->comm_bytes));
+    PD_CUDA(cudaMalloc(&pl->comm_epoch, sizeof(unsigned long long)));
+    PD_CUDA(cudaMemset(pl->comm_epoch, 0, sizeof(unsigned long long)));
+    PD_CUDA(cudaMalloc(&pl->comm_err, sizeof(int)));
+    PD_CUDA(cudaMemset(pl->comm_err, 0, sizeof(int)));
+    PD_CUDA(cudaDeviceSynchronize());
+    h->ws_bytes += pl->comm_bytes;
+  }
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t ih;
+    PD_CUDA(cudaIpcGetMemHandle(&ih, pl->comm_base));
+    static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &ih, sizeof(ih));
+  }
+  if (base_out) *base_out = pl->comm_base;
+  return PD_OK;
+}
+
+// mode 0: `peers` = G cudaIpcMemHandle_t (64 bytes each, rank order; the own entry is ignored)
+// mode 1: `peers` = G device pointers (void*[G]) already valid in this process (peer access is enabled here)
+int pd_slab_comm_connect_impl(pd_handle* h, const void* peers, int mode, const int* peer_devices) {
+  SolvePlan* pl = plan_of(h);
+  if (!pl->comm_base) {
+    pd_set_error("pd_slab_comm_connect: call pd_slab_comm_create first");
+    return PD_ERR_INVALID;
+  }
+  const int G = pl->sg.G, me = pl->sg.rank;
+  for (int r = 0; r < G; ++r) {
+    if (r == me) {
+      pl->comm_peer[r] = pl->comm_base;
+      continue;
+    }
+    if (mode == 0) {
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, reinterpret_cast<const char*>(peers) + 64 * (size_t)r, sizeof(ih));
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        pd_set_error("pd_slab_comm_connect: cudaIpcOpenMemHandle of rank %d failed: %s", r, cudaGetErrorString(e));
+        return PD_ERR_CUDA;
+      }
+      pl->comm_peer[r] = ptr;
+      pl->comm_ipc[r] = true;
+    } else {
+      pl->comm_peer[r] = reinterpret_cast<void* const*>(peers)[r];
+      if (peer_devices && peer_devices[r] != h->cfg.device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_devices[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          pd_set_error("pd_slab_comm_connect: no peer access from device %d to %d: %s", h->cfg.device,
+                       peer_devices[r], cudaGetErrorString(e));
+          return PD_ERR_CUDA;
+        }
+        cudaGetLastError();
+      }
+    }
+  }
+  pl->comm_connected = true;
+  return PD_OK;
+}
+
+bool pd_slab_comm_ready(const pd_handle* h) {
+  const SolvePlan* pl = reinterpret_cast<const SolvePlan*>(h->solve_plan);
+  return pl && pl->comm_connected;
+}
+
+// reads (and clears) the "a bounded wait expired" flag and the epoch; synchronises the device
+int pd_slab_comm_status_impl(pd_handle* h, int* timed_out, unsigned long long* epoch) {
+  SolvePlan* pl = plan_of(h);
+  if (!pl->comm_base) {
+    pd_set_error("pd_slab_comm_status: no exchange buffer");
+    return PD_ERR_INVALID;
+  }
+  int e = 0;
+  unsigned long long ep = 0;
+  PD_CUDA(cudaMemcpy(&e, pl->comm_err, sizeof(int), cudaMemcpyDeviceToHost));
+  PD_CUDA(cudaMemcpy(&ep, pl->comm_epoch, sizeof(ep), cudaMemcpyDeviceToHost));
+  if (e) PD_CUDA(cudaMemset(pl->comm_err, 0, sizeof(int)));
+  if (timed_out) *timed_out = e;
+  if (epoch) *epoch = ep;
+  return PD_OK;
+}
+
 // slab mode, first half: pass A, interface levels, slab functionals -> out[6][K]
-int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum) {
+// (out == nullptr: pushed to every rank's exchange buffer instead, see SlabCommDev)
+int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum, cudaEvent_t* ev) {
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, half_spectrum);
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
   SolvePlan* pl = plan_of(h);
+  if (!out && !pl->comm_connected) {
+    pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
+    return PD_ERR_INVALID;
+  }
   if (sp.nlev >= 1) {
     pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
+    if (ev) cudaEventRecord(ev[0], st);
     int rc = run_interface(h, sp, lv, st);
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[1], st);
   } else {
     // a single chunk: its first / last entries come from one forward sweep; reuse pass A with a
     // private F buffer (zout is free at this point: 4K entries >= 2K)
@@ -1145,23 +1357,44 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
     pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
+    if (ev) { cudaEventRecord(ev[0], st); cudaEventRecord(ev[1], st); }
   }
-  pd_slab_functionals_kernel<<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, out);
+  if (out) {
+    SlabCommDev none;
+    memset(&none, 0, sizeof(none));
+    pd_slab_functionals_kernel<false><<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, out, none);
+  } else {
+    pd_slab_functionals_kernel<true><<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, nullptr, comm_dev_of(h));
+  }
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
 }
 
 // slab mode, second half: global separator solve from the gathered functionals, then pass B
-int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum) {
+// (gathered == nullptr: waits for the peers' stores into this rank's exchange buffer)
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum, cudaEvent_t* ev) {
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, half_spectrum);
   SolvePlan* pl = plan_of(h);
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
-  pd_slab_global_kernel<<<kblocks, PD_KB, 0, st>>>(gathered, sp, pl->sg, half_spectrum ? pl->slabcoef_h : pl->slabcoef,
-                                                   pl->zout);
+  const cplx* coef = half_spectrum ? pl->slabcoef_h : pl->slabcoef;
+  if (gathered) {
+    SlabCommDev none;
+    memset(&none, 0, sizeof(none));
+    pd_slab_global_kernel<false><<<kblocks, PD_KB, 0, st>>>(gathered, (int64_t)sp.K, sp, pl->sg, coef, pl->zout, none);
+  } else {
+    if (!pl->comm_connected) {
+      pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
+      return PD_ERR_INVALID;
+    }
+    pd_slab_global_kernel<true><<<kblocks, PD_KB, 0, st>>>(nullptr, pl->comm_kmax, sp, pl->sg, coef, pl->zout,
+                                                          comm_dev_of(h));
+    sl.epoch_bump = pl->comm_epoch;
+  }
   PD_CHECK_LAUNCH();
+  if (ev) cudaEventRecord(ev[0], st);
   pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches += 2;

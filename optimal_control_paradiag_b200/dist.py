@@ -26,6 +26,7 @@ and back-substitutes its slab (``pd_slab_finish``).  Communication drops from 2 
 per rank (NVLink-bound) to 96 N_t bytes per rank; no transposes, no pack/unpack.
 """
 import math
+import os
 
 import numpy as np
 
@@ -42,7 +43,7 @@ def slab_bounds(total, parts):
 
 class DistributedDiagFFTPC:
     def __init__(self, N_x, N_t, T=2.0, gamma=1.0, device=0, group=None, backend_factory=None,
-                 mode="alltoall"):
+                 mode="alltoall", transport=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -70,10 +71,17 @@ class DistributedDiagFFTPC:
         self.local_size = 2 * self.n_r * self.N_t
         if mode == "slab":
             self.backend = backend_factory(slab_rank=self.rank, slab_count=self.world)
-            self.w_time = torch.empty(self.local_size, dtype=c128, device=self.device)
-            self.fl_out = torch.empty(6 * self.N_t, dtype=c128, device=self.device)
-            self.gathered = torch.empty(self.world * 6 * self.N_t, dtype=c128, device=self.device)
             self.comm_bytes_per_apply = 16 * 6 * self.N_t
+            # transport of the slab functionals: "peer" = stores into every rank's IPC-mapped exchange buffer
+            # from inside the producing kernel (pd_slab_apply, no collective call on the data path);
+            # "nccl" = one all_gather_into_tensor between pd_slab_reduce and pd_slab_finish (also what the
+            # CPU test backends use)
+            self.transport = "nccl"
+            want = transport or os.environ.get("PD_SLAB_TRANSPORT", "peer")
+            if want == "peer" and hasattr(self.backend, "slab_comm_create") and self.device.type == "cuda":
+                self.transport = self._connect_peers()
+            if self.transport == "nccl":
+                self._alloc_nccl_buffers()
             return
         self.backend = backend_factory(k_begin=self.koff[self.rank], k_count=self.k_r, n_local=self.n_r)
         self.freq_size = 2 * self.n * self.k_r
@@ -87,6 +95,40 @@ class DistributedDiagFFTPC:
         self.a_recv = [2 * ns * self.k_r for ns in self.ncount]    # from rank s: (2, n_s, k_r)
         self.comm_bytes_per_apply = 16 * 2 * (sum(self.a_send) - self.a_send[self.rank])
 
+    def _alloc_nccl_buffers(self):
+        t, c128 = self.torch, self.torch.complex128
+        self.w_time = t.empty(self.local_size, dtype=c128, device=self.device)
+        self.fl_out = t.empty(6 * self.N_t, dtype=c128, device=self.device)
+        self.gathered = t.empty(self.world * 6 * self.N_t, dtype=c128, device=self.device)
+
+    def _connect_peers(self):
+        """Exchange the IPC handles of the ranks' exchange buffers and map them; "peer" on success on EVERY rank,
+        else "nccl" everywhere (the decision is collective)."""
+        ok, handles = 1, None
+        try:
+            mine, _ = self.backend.slab_comm_create()
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, mine, group=self.group)
+            self.backend.slab_comm_connect_ipc(handles)
+        except Exception as ex:  # no IPC in this environment: every rank falls back together
+            ok, self.transport_error = 0, str(ex)
+        flag = self.torch.tensor([ok], dtype=self.torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        return "peer" if int(flag.item()) == 1 else "nccl"
+
+    def check_exchange(self):
+        """Raises if a bounded wait of the peer-store exchange expired (a rank never delivered)."""
+        if getattr(self, "transport", None) == "peer":
+            timed_out, epoch = self.backend.slab_comm_status()
+            if timed_out:
+                raise RuntimeError(f"rank {self.rank}: the slab exchange timed out waiting for a peer (epoch {epoch})")
+
+    def apply_profile(self, x_local, y_local):
+        """Per-stage device times of one distributed apply (peer transport): dict of milliseconds."""
+        if getattr(self, "transport", None) != "peer":
+            raise NotImplementedError("per-stage timing needs the peer-store transport")
+        return self.backend.slab_apply_profile(x_local.reshape(-1), y_local.reshape(-1))
+
     # -------------------------------------------------------------------------------
     @property
     def launch_count(self):
@@ -94,9 +136,13 @@ class DistributedDiagFFTPC:
 
     def describe(self):
         if self.mode == "slab":
-            return {"world": self.world, "mode": "slab", "node_slabs": self.ncount,
-                    "allgather_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply,
-                    "collective": "one all_gather of 6 N_t complex values per rank (slab functionals)"}
+            return {"world": self.world, "mode": "slab", "node_slabs": self.ncount, "transport": self.transport,
+                    "exchange_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply * (
+                        self.world - 1 if self.transport == "peer" else 1),
+                    "collective": ("none on the data path: the functionals kernel stores 6 N_t complex values into "
+                                   "every peer's IPC-mapped buffer and the separator kernel waits on per-block flags")
+                    if self.transport == "peer" else
+                    "one all_gather of 6 N_t complex values per rank (slab functionals)"}
         return {"world": self.world, "mode": "alltoall", "node_slabs": self.ncount, "freq_slabs": self.kcount,
                 "alltoall_bytes_sent_per_rank_per_apply": self.comm_bytes_per_apply,
                 "collective": "all_to_all_single x2 (uneven splits), pack/unpack by strided copies"}
@@ -164,6 +210,8 @@ class DistributedDiagFFTPC:
 
     def _apply_slab(self, x_local, y_local):
         t = self.torch
+        if self.transport == "peer":
+            return self.backend.slab_apply(x_local.reshape(-1), y_local.reshape(-1))          # :491-553
         self.backend.stage_fft(x_local.reshape(-1), self.w_time, 2 * self.n_r, True)      # :500-501
         self.backend.slab_reduce(self.w_time, self.fl_out)
         self.dist.all_gather_into_tensor(t.view_as_real(self.gathered).reshape(-1),
@@ -181,7 +229,11 @@ class DistributedDiagFFTPC:
             raise NotImplementedError("the real-input distributed apply uses the slab decomposition")
         if y_local is None:
             y_local = t.empty_like(x_local)
+        if self.transport == "peer":
+            return self.backend.slab_apply(x_local.reshape(-1), y_local.reshape(-1), real=True)
         if getattr(self, "_w_half", None) is None:
+            if not hasattr(self, "w_time"):
+                self._alloc_nccl_buffers()
             Kp = self.backend.half_cols
             c128 = t.complex128
             self._w_half = t.empty(2 * self.n_r * Kp, dtype=c128, device=self.device)
@@ -357,3 +409,61 @@ class DistributedDiagFFTPC:
                 reals[s].copy_(mine)
             self.dist.broadcast(reals[s], src=self.dist.get_global_rank(self.group, s) if self.group else s,
                                 group=self.group)
+
+
+class LocalSlabGroup:
+    """``G`` x-slab handles driven by ONE process: the peer-store exchange of ``pd_slab_apply`` with plain device
+    pointers instead of IPC handles.  All slabs may sit on one GPU (how the distributed path is exercised where
+    only one GPU is leased: every first half ``pd_slab_apply_begin`` is issued before any second half, so no
+    kernel ever waits for one queued behind it) or on several GPUs with peer access (one per slab)."""
+
+    def __init__(self, N_x, N_t, G, T=2.0, gamma=1.0, devices=None):
+        import torch
+
+        from .handle import ParaDiagHandle
+        self.torch = torch
+        self.N_x, self.N_t, self.n, self.G = int(N_x), int(N_t), int(N_x) + 1, int(G)
+        self.devices = [0] * self.G if devices is None else [int(d) for d in devices]
+        self.ncount, self.noff = slab_bounds(self.n, self.G)
+        self.handles = [ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, device=self.devices[r], slab_rank=r, slab_count=G)
+                        for r in range(self.G)]
+        bases = [h.slab_comm_create()[1] for h in self.handles]
+        for h in self.handles:
+            h.slab_comm_connect_local(bases, self.devices)
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def scatter(self, x_global):
+        xg = x_global.reshape(2, self.n, self.N_t)
+        return [xg[:, self.noff[r]:self.noff[r + 1], :].reshape(-1).contiguous().to(f"cuda:{self.devices[r]}")
+                for r in range(self.G)]
+
+    def apply_blocks(self, xs, real=False):
+        """One distributed apply on the ranks' blocks; returns the output blocks (same devices)."""
+        t = self.torch
+        ys = [t.empty_like(x) for x in xs]
+        if len(set(self.devices)) > 1:                      # the producers' inputs must be complete device-side
+            for d in set(self.devices):
+                t.cuda.synchronize(d)
+        for h, x in zip(self.handles, xs):
+            h.slab_apply_begin(x, real=real)
+        for h, y in zip(self.handles, ys):
+            h.slab_apply_end(y, real=real)
+        return ys
+
+    def apply(self, x_global, real=False):
+        ys = self.apply_blocks(self.scatter(x_global), real=real)
+        dev = x_global.device
+        parts = [y.to(dev).view(2, self.ncount[r], self.N_t) for r, y in enumerate(ys)]
+        return self.torch.cat(parts, dim=1).reshape(-1)
+
+    def status(self):
+        return [h.slab_comm_status() for h in self.handles]

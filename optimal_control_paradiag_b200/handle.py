@@ -27,10 +27,17 @@ class ParaDiagHandle:
         self.N_x, self.N_t, self.T, self.gamma = int(N_x), int(N_t), float(T), float(gamma)
         self.n = self.N_x + 1
         self.device = int(device)
+        self.alpha = float(alpha)
         self.size = 2 * self.n * self.N_t
         self.k_count = int(k_count) if k_count else self.N_t
         self.k_begin = int(k_begin) if k_count else 0
         self.n_local = int(n_local) if n_local else self.n
+        # local node rows of an x-slab handle (balanced split, the first n % G slabs one node longer)
+        if slab_count and int(slab_count) > 1:
+            G, r = int(slab_count), int(slab_rank)
+            self.n_slab = self.n // G + (1 if r < self.n % G else 0)
+        else:
+            self.n_slab = self.n
         cfg = pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=self.N_x, N_t=self.N_t, bug138=int(bool(bug138)),
                         T=self.T, gamma=self.gamma, alpha=float(alpha), device=self.device,
                         k_begin=int(k_begin), k_count=int(k_count), n_local=int(n_local),
@@ -58,6 +65,12 @@ class ParaDiagHandle:
     @property
     def workspace_bytes(self):
         return int(self.lib.pd_workspace_bytes(self._h))
+
+    @property
+    def real_path_supported(self):
+        """True when pd_pc_apply_real exists for this handle: power-of-two N_t in [128, 16384], alpha = 1."""
+        N = self.N_t
+        return self.alpha == 1.0 and N >= 128 and N <= 16384 and (N & (N - 1)) == 0
 
     @property
     def launch_count(self):
@@ -165,6 +178,58 @@ class ParaDiagHandle:
         check(self.lib.pd_slab_finish(self._h, self._ptr(w, None, "w"), self._ptr(gathered, None, "gathered"),
                                       self._stream()))
         return w
+
+    # ---- slab mode with the peer-store exchange (the whole distributed apply behind one call)
+    def slab_comm_create(self):
+        """Allocate this rank's exchange buffer; returns (ipc_handle: 64 bytes, device address)."""
+        buf = (C.c_ubyte * 64)()
+        base = C.c_void_p()
+        check(self.lib.pd_slab_comm_create(self._h, buf, C.byref(base)))
+        return bytes(buf), int(base.value)
+
+    def slab_comm_connect_ipc(self, handles):
+        """``handles``: the 64-byte IPC handles of every rank (rank order), from other processes."""
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.lib.pd_slab_comm_connect(self._h, arr, 0, None))
+
+    def slab_comm_connect_local(self, bases, devices=None):
+        """``bases``: device addresses of every rank's buffer, valid in this process (one process, many handles)."""
+        ptrs = (C.c_void_p * len(bases))(*bases)
+        devs = (C.c_int * len(bases))(*devices) if devices is not None else None
+        check(self.lib.pd_slab_comm_connect(self._h, ptrs, 1, devs))
+
+    def slab_comm_status(self):
+        """(timed_out, epoch): a bounded wait expired since the last call / applies completed."""
+        to, ep = C.c_int(0), C.c_uint64(0)
+        check(self.lib.pd_slab_comm_status(self._h, C.byref(to), C.byref(ep)))
+        return bool(to.value), int(ep.value)
+
+    def _slab_ptr(self, t, real):
+        torch = _torch()
+        want = torch.float64 if real else torch.complex128
+        if t.dtype != want or not t.is_cuda or not t.is_contiguous() or t.numel() != 2 * self.n_slab * self.N_t:
+            raise ValueError(f"slab apply: need a contiguous {want} CUDA tensor with {2 * self.n_slab * self.N_t} entries")
+        return C.c_void_p(t.data_ptr())
+
+    def slab_apply(self, x, y, real=False):
+        fn = self.lib.pd_slab_apply_real if real else self.lib.pd_slab_apply
+        check(fn(self._h, self._slab_ptr(x, real), self._slab_ptr(y, real), self._stream()))
+        return y
+
+    def slab_apply_begin(self, x, real=False):
+        check(self.lib.pd_slab_apply_begin(self._h, self._slab_ptr(x, real), self._stream(), int(real)))
+
+    def slab_apply_end(self, y, real=False):
+        check(self.lib.pd_slab_apply_end(self._h, self._slab_ptr(y, real), self._stream(), int(real)))
+        return y
+
+    def slab_apply_profile(self, x, y):
+        ms = (C.c_float * 7)()
+        check(self.lib.pd_slab_apply_profile(self._h, self._slab_ptr(x, False), self._slab_ptr(y, False),
+                                             self._stream(), ms, 7))
+        return dict(zip(("ifft", "passA", "interface", "functionals_push", "wait_separators", "passB", "fft"),
+                        [float(v) for v in ms]))
 
     # ---- slab mode on the half spectrum of the real-input path
     @property

@@ -176,9 +176,14 @@ class DiagFFTPC(PCBase):
             if self.node_order is not None:
                 raise NotImplementedError("node_order is only supported on the host-Vec path")
             if x.dtype == torch.float64:
-                # real vectors (what GMRES feeds the PC in this problem): half-spectrum fast path
-                # (alpha = 1 only; the library answers PD_ERR_UNSUPPORTED otherwise)
-                self.handle.pc_apply_real(x.reshape(-1), y.reshape(-1))
+                # real vectors (what GMRES feeds the PC in this problem): half-spectrum fast path where the
+                # library has one (power-of-two N_t in [128, 16384], alpha = 1); every other size -- the
+                # upstream default N_t = 81 included -- goes through the complex apply like any other vector
+                if self.handle.real_path_supported:
+                    self.handle.pc_apply_real(x.reshape(-1), y.reshape(-1))
+                else:
+                    yc = self.handle.pc_apply(x.reshape(-1).to(torch.complex128))
+                    y.reshape(-1).copy_(yc.real)
             else:
                 self.handle.pc_apply(x.reshape(-1), y.reshape(-1))
             return

@@ -28,6 +28,8 @@ def load(build_if_missing=True):
         lib = C.CDLL(_SO)
         lib.oracle_thomas_toeplitz.restype = C.c_int
         lib.oracle_thomas_toeplitz.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.oracle_pc_stage.restype = C.c_int
+        lib.oracle_pc_stage.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_num_threads.restype = C.c_int
         lib.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = lib
@@ -53,3 +55,19 @@ def thomas_toeplitz_c(a, b, rhs, conj_mode=False):
     if rc:
         raise MemoryError("oracle_thomas_toeplitz")
     return out
+
+
+def pc_stage_c(a, b, z, sigma, xh):
+    """The whole per-frequency stage (rotation in, both Thomas solves, rotation out, Dirichlet rows), fused and
+    threaded, IN PLACE on xh = ifft_t(x) of shape (2, n, K) complex128 (Control_Wave_PC.py:445-540)."""
+    lib = load()
+    assert xh.dtype == np.complex128 and xh.flags.c_contiguous and xh.ndim == 3 and xh.shape[0] == 2
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    rc = lib.oracle_pc_stage(xh.shape[1], xh.shape[2], a.ctypes.data, b.ctypes.data, z.ctypes.data,
+                             sigma.ctypes.data, xh.ctypes.data)
+    if rc:
+        raise MemoryError(f"oracle_pc_stage: {rc}")
+    return xh

@@ -97,6 +97,30 @@ class DiagFFTPCFast:
         w[1] = (-1j * self.sigma * self.z) * (zp - zm)
         return sfft.fft(w, axis=2, workers=self.workers)
 
+    def stage_columns(self, ks, xh_cols):
+        """The per-frequency stage (:445-540) on a SAMPLE of frequencies: ``xh_cols`` = columns ``ks`` of
+        ifft_t(x), shape (2, n, len(ks)); returns the same columns of wh.  Frequencies decouple, so a handful of
+        columns can be solved in 80-bit arithmetic (``dtype=np.longdouble``) at any BASELINE size."""
+        ks = np.asarray(ks)
+        xh = np.asarray(xh_cols, dtype=self.ctype)
+        z, sg, a, b = self.z[ks], self.sigma[ks], self.a[ks], self.b[ks]
+        uz = xh[0] * np.conj(z)
+        ip = (1j * sg) * xh[1]
+        rp, rm = (uz + ip) / 2, (uz - ip) / 2
+        zp, zm = np.zeros_like(rp), np.zeros_like(rm)
+        zp[1:-1] = thomas_toeplitz(a, b, rp[1:-1])
+        zm[1:-1] = np.conj(thomas_toeplitz(a, b, np.conj(rm[1:-1])))
+        return np.stack([zp + zm, (-1j * sg * z) * (zp - zm)])
+
+    def apply_threaded(self, x):
+        """Same operator with every stage on all host threads: scipy.fft with ``workers`` and the fused C
+        stage of oracle/csrc/pc_solve.c (``oracle_pc_stage``).  The timed CPU baseline of bench.py; float64 only."""
+        from . import csolve
+        x = np.asarray(x, dtype=np.complex128).reshape(2, self.n, self.N_t)
+        xh = sfft.ifft(x, axis=2, workers=self.workers)
+        csolve.pc_stage_c(self.a, self.b, self.z, self.sigma, xh)
+        return sfft.fft(xh, axis=2, workers=self.workers, overwrite_x=True).reshape(-1)
+
     def apply(self, x):
         rp, rm = self.forward_stage(x)
         zp, zm = self.solve_stage(rp, rm)
