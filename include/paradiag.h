@@ -94,8 +94,12 @@ int64_t pd_launch_count(const pd_handle* h);
 
 /* DiagFFTPC.apply (:491-553): y = P^-1 x, device pointers.  x and y may alias.  */
 int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
-/* Same with host buffers (PETSc Vec arrays): H2D, apply, D2H, synchronises.     */
+/* Same with host buffers (PETSc Vec arrays, :493-497 / :552-553): H2D, apply, D2H, synchronises.  Pageable
+ * buffers are page-locked once per (pointer, size) with cudaHostRegister and remembered (up to 16 buffers,
+ * PD_HOST_REGISTER=0 disables), so that long-lived KSP work vectors travel at the full PCIe rate;
+ * pd_host_unregister_all drops the registrations (call it before freeing such a buffer early).     */
 int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host);
+int pd_host_unregister_all(pd_handle* h);
 /* Real-input fast path.  The vectors GMRES feeds the PC in this (real) problem are real: x_dev and
  * y_dev are float64 arrays in the same (field, node, time) layout, 2 n N_t doubles.  Their time spectra
  * are Hermitian, so only the frequencies 0..N_t/2 are transformed and solved: half the bytes of

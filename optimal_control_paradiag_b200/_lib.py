@@ -43,6 +43,7 @@ SYMBOLS = {
     "pd_launch_count": (_I64, [_VP]),
     "pd_pc_apply": (_I, [_VP, _VP, _VP, _VP]),
     "pd_pc_apply_host": (_I, [_VP, _VP, _VP]),
+    "pd_host_unregister_all": (_I, [_VP]),
     "pd_pc_apply_real": (_I, [_VP, _VP, _VP, _VP]),
     "pd_stage_rfft": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "pd_stage_solve_half": (_I, [_VP, _VP, _VP]),

@@ -1,6 +1,7 @@
 // C ABI of libparadiag.so: handle lifetime and the DiagFFTPC entry points.
 // See include/paradiag.h for the contract and the upstream lines each call replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pd_common.cuh"
@@ -15,6 +16,7 @@ void pd_set_error(const char* fmt, ...) {
 }
 
 void pd_krylov_free(pd_handle* h);
+static void hostreg_release(pd_handle* h);
 void pd_solve_free(pd_handle* h);
 
 extern "C" const char* pd_last_error(void) { return g_err; }
@@ -35,8 +37,11 @@ extern "C" int pd_destroy(pd_handle* h) {
   if (h->work) cudaFree(h->work);
   if (h->stage_x) cudaFree(h->stage_x);
   if (h->stage_y) cudaFree(h->stage_y);
-  if (h->pinned) cudaFreeHost(h->pinned);
+  hostreg_release(h);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->sched_aux) cudaStreamDestroy(h->sched_aux);
+  for (cudaEvent_t e : h->sched_ev)
+    if (e) cudaEventDestroy(e);
   delete h;
   return PD_OK;
 }
@@ -126,8 +131,93 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
     pd_destroy(h);
     return rc;
   }
+  // Schedule of the single-GPU apply.  PD_SCHED=interleave runs it NODE SLAB BY NODE SLAB as separate launches:
+  // inverse FFT of a slab of node rows, then pass A of the level-0 chunks in it while the slab is still in L2;
+  // later pass B of a slab, then its forward FFT (see apply_interleaved).  Bit-identical results, but MEASURED
+  // SLOWER on B200 at every slab size (cfg3: 3.2 ms with 28 MB slabs on two streams, 2.9 ms with 221 MB slabs,
+  // against 2.73 ms plain; the same under a CUDA graph -- the cost is the drain / refill of ~280 short kernels,
+  // not the host), so it stays opt-in.  PD_SCHED_CHUNKS = level-0 chunks per slab; PD_SCHED_STREAMS = 1|2.
+  {
+    const char* mode = getenv("PD_SCHED");
+    const bool on = mode && mode[0] == 'i';
+    const bool sharded = cfg->k_count > 0 || cfg->n_local > 0 || h->slab_count > 1;
+    if (on && !sharded && pd_fft_segments_supported(h) && pd_solve_nchunks(h) > 1) {
+      // default slab: ~2 resident waves of FFT lines (444 one-line CTAs fit on 148 SMs at N_t = 4096)
+      const char* ce = getenv("PD_SCHED_CHUNKS");
+      int per = ce ? atoi(ce) : 0;
+      if (per <= 0) {
+        const int64_t target_bytes = (int64_t)28 << 20;  // per slab, both fields
+        per = (int)(target_bytes / ((int64_t)sizeof(cplx) * 2 * 17 * cfg->N_t));
+        if (per < 1) per = 1;
+      }
+      h->sched_chunks = per;
+      const char* se = getenv("PD_SCHED_STREAMS");
+      h->sched_streams = se ? atoi(se) : 2;
+      if (h->sched_streams > 1) {
+        PD_CUDA(cudaStreamCreateWithFlags(&h->sched_aux, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) PD_CUDA(cudaEventCreateWithFlags(&h->sched_ev[i], cudaEventDisableTiming));
+      }
+    }
+  }
   PD_CUDA(cudaDeviceSynchronize());
   *out = h;
+  return PD_OK;
+}
+
+// The apply as node slabs (alpha = 1, power-of-two N_t <= 8192, vectors >> L2).  A slab = `sched_chunks`
+// consecutive level-0 chunks of the partition solve = a contiguous range of node rows of both fields:
+//   first half :  for every slab   inverse FFT of its rows (x -> work)  ->  pass A of its chunks
+//   interface  :  the small levels (whole x-range, ~6 % of the data)
+//   second half:  for every slab   pass B of its chunks (in place)      ->  forward FFT of its rows (work -> y)
+// Pass A reads what the FFT has just written and the FFT reads what pass B has just written: those two sweeps
+// are served by L2 (126 MB) instead of HBM.  Alternate slabs go to a second stream so that the ramp-down of one
+// small kernel overlaps the ramp-up of the next; fork/join by events, capturable in a CUDA graph.
+static int apply_interleaved(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st) {
+  const int nch = pd_solve_nchunks(h), per = h->sched_chunks, n = h->n;
+  const int nsl = (nch + per - 1) / per;
+  const bool two = h->sched_streams > 1 && nsl > 1 && h->sched_aux;
+  cudaStream_t q[2] = {st, two ? h->sched_aux : st};
+  auto rows = [&](int s, int& r0, int& r1, int& c0, int& c1) {
+    c0 = s * per;
+    c1 = c0 + per < nch ? c0 + per : nch;
+    r0 = c0 == 0 ? 0 : c0 * 17 + 1;   // chunk c = rows 17 c + 1 .. 17 c + 16 and the separator 17 c + 17
+    r1 = c1 == nch ? n : c1 * 17 + 1;
+  };
+  int rc;
+  if (two) {
+    PD_CUDA(cudaEventRecord(h->sched_ev[0], st));
+    PD_CUDA(cudaStreamWaitEvent(h->sched_aux, h->sched_ev[0], 0));
+  }
+  for (int s = 0; s < nsl; ++s) {
+    int r0, r1, c0, c1;
+    rows(s, r0, r1, c0, c1);
+    cudaStream_t qs = q[s & 1];
+    const int64_t off = (int64_t)r0 * h->cfg.N_t;
+    if ((rc = pd_fft_launch_segments(h, x + off, h->work + off, r1 - r0, 2, n, 1, qs))) return rc;
+    if ((rc = pd_solve_passA_range(h, h->work, c0, c1, qs))) return rc;
+  }
+  if (two) {
+    PD_CUDA(cudaEventRecord(h->sched_ev[1], h->sched_aux));
+    PD_CUDA(cudaStreamWaitEvent(st, h->sched_ev[1], 0));
+  }
+  if ((rc = pd_solve_interface(h, st))) return rc;
+  if (two) {
+    PD_CUDA(cudaEventRecord(h->sched_ev[2], st));
+    PD_CUDA(cudaStreamWaitEvent(h->sched_aux, h->sched_ev[2], 0));
+  }
+  // last slabs first: their rows are the most recently written ones, part of them is still in L2
+  for (int s = nsl - 1; s >= 0; --s) {
+    int r0, r1, c0, c1;
+    rows(s, r0, r1, c0, c1);
+    cudaStream_t qs = q[s & 1];
+    const int64_t off = (int64_t)r0 * h->cfg.N_t;
+    if ((rc = pd_solve_passB_range(h, h->work, c0, c1, qs))) return rc;
+    if ((rc = pd_fft_launch_segments(h, h->work + off, y + off, r1 - r0, 2, n, 0, qs))) return rc;
+  }
+  if (two) {
+    PD_CUDA(cudaEventRecord(h->sched_ev[3], h->sched_aux));
+    PD_CUDA(cudaStreamWaitEvent(st, h->sched_ev[3], 0));
+  }
   return PD_OK;
 }
 
@@ -395,6 +485,7 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
     if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
     return pd_gamma_launch(h, (const cplx*)y_dev, (cplx*)y_dev, nlines, 1, st);
   }
+  if (h->sched_chunks > 0) return apply_interleaved(h, (const cplx*)x_dev, (cplx*)y_dev, st);
   // :500-501 ifft along time, :445-540 per-frequency stage, :547-548 fft along time
   if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st))) return rc;
   if ((rc = pd_solve_launch(h, h->work, st))) return rc;
@@ -510,6 +601,76 @@ extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {
   return PD_ERR_UNSUPPORTED;
 }
 
+// Host buffers handed to pd_pc_apply_host are page-locked ONCE per (pointer, size) with cudaHostRegister and
+// remembered: a PETSc Vec array is pageable, and a pageable cudaMemcpyAsync runs at about half the PCIe rate
+// (staged through the driver's bounce buffer).  KSP work vectors keep their arrays for the life of the solve, so
+// the registration cost (~0.2 s per GB, once) is paid on the first apply only.  Up to PD_HOSTREG_SLOTS buffers
+// are kept (oldest evicted); PD_HOST_REGISTER=0 turns the cache off.  Memory that is already page-locked
+// (cudaHostAlloc, torch pin_memory) is detected and left alone.
+#define PD_HOSTREG_SLOTS 16
+struct HostReg {
+  const void* ptr[PD_HOSTREG_SLOTS];
+  size_t bytes[PD_HOSTREG_SLOTS];
+  bool ours[PD_HOSTREG_SLOTS];  // registered by us (to be unregistered)
+  int next;
+  int enabled;  // -1 unknown
+};
+
+static HostReg* hostreg_of(pd_handle* h) {
+  if (!h->pinned) {
+    HostReg* r = new HostReg();
+    memset(r, 0, sizeof(*r));
+    r->enabled = -1;
+    h->pinned = r;
+  }
+  return reinterpret_cast<HostReg*>(h->pinned);
+}
+
+static void hostreg_release(pd_handle* h) {
+  if (!h->pinned) return;
+  HostReg* r = reinterpret_cast<HostReg*>(h->pinned);
+  for (int i = 0; i < PD_HOSTREG_SLOTS; ++i)
+    if (r->ptr[i] && r->ours[i]) cudaHostUnregister(const_cast<void*>(r->ptr[i]));
+  cudaGetLastError();
+  delete r;
+  h->pinned = nullptr;
+}
+
+static void hostreg_pin(pd_handle* h, const void* p, size_t bytes) {
+  HostReg* r = hostreg_of(h);
+  if (r->enabled < 0) {
+    const char* e = getenv("PD_HOST_REGISTER");
+    r->enabled = !(e && e[0] == '0');
+  }
+  if (!r->enabled) return;
+  for (int i = 0; i < PD_HOSTREG_SLOTS; ++i)
+    if (r->ptr[i] == p && r->bytes[i] >= bytes) return;
+  cudaPointerAttributes at;
+  bool already = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  bool ours = false;
+  if (!already) {
+    ours = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();  // failure (e.g. overlapping registration, locked-memory limit) just means a pageable copy
+  }
+  const int slot = r->next;
+  r->next = (r->next + 1) % PD_HOSTREG_SLOTS;
+  if (r->ptr[slot] && r->ours[slot]) {
+    cudaHostUnregister(const_cast<void*>(r->ptr[slot]));
+    cudaGetLastError();
+  }
+  r->ptr[slot] = p;
+  r->bytes[slot] = bytes;
+  r->ours[slot] = ours;
+}
+
+extern "C" int pd_host_unregister_all(pd_handle* h) {
+  if (!h) return PD_OK;
+  PD_ON_DEVICE(h);
+  hostreg_release(h);
+  return PD_OK;
+}
+
 extern "C" int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host) {
   if (!h || !x_host || !y_host) {
     pd_set_error("pd_pc_apply_host: invalid argument");
@@ -523,6 +684,8 @@ extern "C" int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host) 
   }
   if (!h->own_stream) PD_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = h->own_stream;
+  hostreg_pin(h, x_host, bytes);
+  if (y_host != x_host) hostreg_pin(h, y_host, bytes);
   PD_CUDA(cudaMemcpyAsync(h->stage_x, x_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = pd_pc_apply(h, h->stage_x, h->stage_x, st);
   if (rc) return rc;

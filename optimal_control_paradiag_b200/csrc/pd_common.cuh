@@ -115,6 +115,12 @@ struct pd_handle {
   // work vector (2, n, N_t) for the single-GPU apply
   cplx* work;
 
+  // node-slab interleaved schedule of the single-GPU apply (pd_capi.cu): aux stream + fork/join events
+  int sched_chunks;        // level-0 chunks per slab; 0: plain schedule (3 whole-array stages)
+  int sched_streams;       // 1 or 2
+  cudaStream_t sched_aux;
+  cudaEvent_t sched_ev[4];
+
   // host staging for the *_host entry points
   cplx* stage_x;
   cplx* stage_y;
@@ -137,6 +143,13 @@ struct pd_handle {
 int pd_fft_plan(pd_handle* h);
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
                   cudaStream_t st);
+bool pd_fft_segments_supported(const pd_handle* h);
+int pd_fft_launch_segments(pd_handle* h, const cplx* in, cplx* out, int64_t seg_lines, int nseg, int64_t seg_stride,
+                           int inverse, cudaStream_t st);
+int pd_solve_nchunks(const pd_handle* h);
+int pd_solve_passA_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st);
+int pd_solve_interface(pd_handle* h, cudaStream_t st);
+int pd_solve_passB_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st);
 int pd_gamma_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st);
 bool pd_rfft_supported(const pd_handle* h);
 int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st);

@@ -288,7 +288,7 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
 template <int R0, int R1, int R2, int R3, bool INV>
 __global__ void __launch_bounds__(512)
 pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
-                   const cplx* __restrict__ tw, double scale) {
+                   const cplx* __restrict__ tw, double scale, int64_t seg_lines, int64_t seg_stride) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
@@ -299,7 +299,9 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
   for (int64_t line0 = (int64_t)blockIdx.x * lpb; line0 < nlines; line0 += (int64_t)gridDim.x * lpb) {
     const int64_t line = line0 + lane_line;
     // whole block must take the same path through __syncthreads: clamp the line
-    const int64_t ln = line < nlines ? line : nlines - 1;
+    int64_t ln = line < nlines ? line : nlines - 1;
+    // the lines may come in equal segments `seg_stride` lines apart (the same node rows of both fields)
+    if (ln >= seg_lines) ln = (ln / seg_lines) * seg_stride + ln % seg_lines;
     const cplx* gsrc = in + ln * N;
     cplx* gdst = out + ln * N;
     // a partially filled last block still runs every pass (block-wide barriers)
@@ -808,7 +810,8 @@ int pd_fft_plan(pd_handle* h) {
 
 template <int R0, int R1, int R2, int R3>
 static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
-                       cudaStream_t st) {
+                       cudaStream_t st, int64_t seg_lines = 0, int64_t seg_stride = 0) {
+  if (seg_lines <= 0) seg_lines = nlines;
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   int threads = T < 256 ? 256 : T;
@@ -819,11 +822,11 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   if (inverse) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride);
   } else {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride);
   }
   PD_CHECK_LAUNCH();
   h->launches++;
@@ -1067,6 +1070,32 @@ int pd_gamma_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
+}
+
+// true when pd_fft_launch_segments exists for this N_t (the register kernels up to 8192 points)
+bool pd_fft_segments_supported(const pd_handle* h) {
+  return h->fft_kind == 1 && h->cfg.N_t <= 8192;
+}
+
+// `nseg` segments of `seg_lines` lines each, `seg_stride` lines apart (in and out alike): the same node rows of
+// both fields in one launch
+int pd_fft_launch_segments(pd_handle* h, const cplx* in, cplx* out, int64_t seg_lines, int nseg, int64_t seg_stride,
+                           int inverse, cudaStream_t st) {
+  const int64_t nlines = seg_lines * nseg;
+  if (nlines <= 0) return PD_OK;
+  switch (h->fft_kind == 1 ? h->cfg.N_t : 0) {
+    case 64:   return launch_pow2<16, 4, 1, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 128:  return launch_pow2<16, 8, 1, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 256:  return launch_pow2<16, 16, 1, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 512:  return launch_pow2<16, 8, 4, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 1024: return launch_pow2<16, 16, 4, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 2048: return launch_pow2<16, 16, 8, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 4096: return launch_pow2<16, 16, 16, 1>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    case 8192: return launch_pow2<16, 16, 8, 4>(h, in, out, nlines, inverse, st, seg_lines, seg_stride);
+    default: break;
+  }
+  pd_set_error("pd_fft_launch_segments: N_t = %d has no segmented kernel", h->cfg.N_t);
+  return PD_ERR_UNSUPPORTED;
 }
 
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,

@@ -66,6 +66,7 @@ struct SolveParams {
   int first_dirichlet, last_dirichlet;
   int freq_perm;  // 1: columns hold [k mod 4 = 0 | 1 | 2 | 3] (the N_t = 16384 FFT kernel's frequency order)
   int koff, kend; // column range [koff, kend) this launch works on (row stride stays K)
+  int c0, c1;     // level-0 chunk range [c0, c1) this launch of pass A / pass B works on (all: 0, rows[1] + 1)
   int al;         // 1: alpha != 1 (extension, see make_coef<true>); 0: the upstream operator
   double lna;     // ln(alpha) / N_t
 };
@@ -326,7 +327,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
   const cplx* wp = w + sp.plane + kc_idx;
   const int64_t K = sp.K;
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
-  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+  for (int c = sp.c0 + blockIdx.y; c < sp.c1; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
     const int nrows = Lc + (c < P ? 1 : 0);  // chunk rows + the separator row that follows
@@ -662,7 +663,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       cRP = cneg(cmul(gr, oRP)); cRM = cneg(cmul(gr, oRM));
     }
   }
-  for (int c = blockIdx.y; c <= P; c += gridDim.y) {
+  for (int c = sp.c0 + blockIdx.y; c < sp.c1; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
     const int j0 = c * (PD_L + 1) + 1;
     cplx dP[PD_L], dM[PD_L];
@@ -1042,6 +1043,8 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   sp.plane = (int64_t)h->n * sp.K;
   sp.koff = 0;
   sp.kend = sp.K;
+  sp.c0 = 0;
+  sp.c1 = pl->rows[1] + 1;
   sp.nlev = pl->nlev;
   sp.first_dirichlet = h->slab_count <= 1 || h->slab_rank == 0;
   sp.last_dirichlet = h->slab_count <= 1 || h->slab_rank == h->slab_count - 1;
@@ -1212,6 +1215,44 @@ int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev, int
   // streaming passes of the other half was tried and does not help: pass A / pass B occupy the whole
   // register file of every SM, so nothing else becomes resident until they drain.)
   return solve_range(h, w, sp, lv, sl, 0, sp.K, st, ev);
+}
+
+// ---- the three parts of the solve stage as separate launches over level-0 chunk ranges (the node-slab
+// interleaved schedule of pd_pc_apply: pass A of a slab right after its inverse FFT, pass B right before its FFT)
+int pd_solve_nchunks(const pd_handle* h) {
+  const SolvePlan* pl = reinterpret_cast<const SolvePlan*>(h->solve_plan);
+  return pl->nlev >= 1 ? pl->rows[1] + 1 : 0;
+}
+int pd_solve_passA_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl, 0);
+  sp.c0 = c0; sp.c1 = c1;
+  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0);
+  if (sp.al)
+    pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+  else
+    pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+int pd_solve_interface(pd_handle* h, cudaStream_t st) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl, 0);
+  return run_interface(h, sp, lv, st);
+}
+int pd_solve_passB_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st) {
+  SolveParams sp; Levels lv; SlabPtrs sl;
+  fill_params(h, sp, lv, sl, 0);
+  sp.c0 = c0; sp.c1 = c1;
+  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0);
+  if (sp.al)
+    pd_solve_passB_kernel<false, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  else
+    pd_solve_passB_kernel<false, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
 }
 
 bool pd_slab_half_supported(const pd_handle* h) {

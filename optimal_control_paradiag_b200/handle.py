@@ -144,6 +144,10 @@ class ParaDiagHandle:
         check(self.lib.pd_pc_apply_host(self._h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
         return y
 
+    def host_unregister_all(self):
+        """Drop the page-lock registrations pc_apply_host made for host buffers (pd_host_unregister_all)."""
+        check(self.lib.pd_host_unregister_all(self._h))
+
     def pc_apply_transpose(self, x, y):
         st = self.lib.pd_pc_apply_transpose(self._h, None, None, None)
         if st == _lib.PD_ERR_UNSUPPORTED:
