@@ -220,6 +220,17 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
              int restart, int max_it, int* its, double* hist, int* reason,
              void* stream);
 
+/* Run-time options of a handle.  "gmres_residual_correction" (default 0): with 1, pd_gmres / pd_gmres_real form
+ * the preconditioned operator as  v + P^-1 ((A - P) v)  instead of  P^-1 (A v)  -- the same operator in exact
+ * arithmetic (Krylov vectors have zero Dirichlet rows), but (A - P) v only touches the wrap-around time levels
+ * and the half-weight rows (:117, :143, :93-110, :138), so the cancelling second differences of A v are never
+ * formed and the rounding noise that the ill-conditioned P^-1 amplifies is gone.  Opt-in: the default keeps KSP's
+ * order of operations (:347-359).                                                                          */
+int pd_set_option(pd_handle* h, const char* name, double value);
+/* d = (A - P) x (complex128, or float64 when real_vectors != 0).  d must be zero on entry outside the at most three
+ * time levels per field that A - P touches; only those entries are written.                                */
+int pd_delta(pd_handle* h, const void* x_dev, void* d_dev, int real_vectors, void* stream);
+
 /* float64 variants for the real problem (vectors of 2 n N_t doubles, same layout): the matvec, the
  * right-hand side and the whole GMRES solve with the half-spectrum preconditioner pd_pc_apply_real.
  * Same iteration as pd_gmres at half the memory traffic.                                          */

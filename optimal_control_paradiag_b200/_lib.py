@@ -70,6 +70,8 @@ SYMBOLS = {
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),
     "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
+    "pd_set_option": (_I, [_VP, C.c_char_p, _D]),
+    "pd_delta": (_I, [_VP, _VP, _VP, _I, _VP]),
     "pd_matvec_real": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs_real": (_I, [_VP, _VP, _VP]),
     "pd_gmres_real": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),

@@ -33,6 +33,7 @@ extern "C" int pd_destroy(pd_handle* h) {
   if (h->twiddle_quarter) cudaFree(h->twiddle_quarter);
   if (h->gamma_tab) cudaFree(h->gamma_tab);
   pd_solve_free(h);
+  pd_fused_free(h);
 
   if (h->work) cudaFree(h->work);
   if (h->stage_x) cudaFree(h->stage_x);
@@ -158,6 +159,20 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
         for (int i = 0; i < 4; ++i) PD_CUDA(cudaEventCreateWithFlags(&h->sched_ev[i], cudaEventDisableTiming));
       }
     }
+  }
+  // Fused inverse FFT + pass A (pd_fused.cu): on by default where it exists (power-of-two N_t in
+  // [1024, 8192], alpha = 1 or not, unsharded or x-slab handles).  PD_FUSE=0 selects the two separate kernels;
+  // PD_FUSE_CHUNKS / PD_FUSE_CPB / PD_FUSE_LAG tune the node-slab size, the chunks per pass-A CTA and the lag.
+  {
+    const char* e = getenv("PD_FUSE");
+    h->fuse_on = pd_fused_supported(h) && !(e && e[0] == '0');
+    const char* c = getenv("PD_FUSE_CHUNKS");
+    h->fuse_chunks = c && atoi(c) > 0 ? atoi(c) : 8;
+    const char* b = getenv("PD_FUSE_CPB");
+    h->fuse_cpb = b && atoi(b) > 0 ? atoi(b) : 2;
+    if (h->fuse_cpb > h->fuse_chunks) h->fuse_cpb = h->fuse_chunks;
+    const char* l = getenv("PD_FUSE_LAG");
+    h->fuse_lag = l && atoi(l) > 0 ? atoi(l) : 1;
   }
   PD_CUDA(cudaDeviceSynchronize());
   *out = h;
@@ -360,13 +375,18 @@ static int slab_apply_check(pd_handle* h, const void* p, const char* who, int re
 static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_input, cudaEvent_t* ev) {
   int rc = ensure_work(h);
   if (rc) return rc;
-  if (real_input)
+  int fused = 0;
+  if (real_input) {
     rc = pd_stage_rfft_pair(h, x, h->work, h->n, 1, st);
-  else
+  } else if (h->fuse_on) {
+    rc = pd_fused_ifft_passA_launch(h, (const cplx*)x, h->work, st, pd_slab_lastl(h));
+    fused = 1;
+  } else {
     rc = pd_fft_launch(h, (const cplx*)x, h->work, 2 * (int64_t)h->n, 1, st);
+  }
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[0], st);
-  return pd_slab_reduce_launch(h, h->work, nullptr, st, real_input, ev ? ev + 1 : nullptr);
+  return pd_slab_reduce_launch(h, h->work, nullptr, st, real_input, ev ? ev + 1 : nullptr, fused);
 }
 
 // second half: wait for the peers' functionals, separator solve, back-substitution, time transform
@@ -487,6 +507,13 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
   }
   if (h->sched_chunks > 0) return apply_interleaved(h, (const cplx*)x_dev, (cplx*)y_dev, st);
   // :500-501 ifft along time, :445-540 per-frequency stage, :547-548 fft along time
+  if (h->fuse_on) {
+    // inverse FFT and pass A in one launch (pass A reads its rows out of L2), then the interface and pass B
+    if ((rc = pd_fused_ifft_passA_launch(h, (const cplx*)x_dev, h->work, st, nullptr))) return rc;
+    if ((rc = pd_solve_interface(h, st))) return rc;
+    if ((rc = pd_solve_passB_range(h, h->work, 0, pd_solve_nchunks(h), st))) return rc;
+    return pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st);
+  }
   if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st))) return rc;
   if ((rc = pd_solve_launch(h, h->work, st))) return rc;
   if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
@@ -523,9 +550,19 @@ extern "C" int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev,
   for (int i = 0; i < 6; ++i) PD_CUDA(cudaEventCreate(&ev[i]));
   const int64_t nlines = 2 * (int64_t)h->n;
   PD_CUDA(cudaEventRecord(ev[0], st));
-  rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st);
-  PD_CUDA(cudaEventRecord(ev[1], st));
-  if (!rc) rc = pd_solve_launch(h, h->work, st, &ev[2]);  // records ev[2] after pass A, ev[3] after PCR
+  if (h->fuse_on && pd_solve_nchunks(h) > 0) {
+    // the path pd_pc_apply takes: ms[0] = fused inverse FFT + pass A (one launch), ms[1] = 0
+    rc = pd_fused_ifft_passA_launch(h, (const cplx*)x_dev, h->work, st, nullptr);
+    PD_CUDA(cudaEventRecord(ev[1], st));
+    PD_CUDA(cudaEventRecord(ev[2], st));
+    if (!rc) rc = pd_solve_interface(h, st);
+    PD_CUDA(cudaEventRecord(ev[3], st));
+    if (!rc) rc = pd_solve_passB_range(h, h->work, 0, pd_solve_nchunks(h), st);
+  } else {
+    rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st);
+    PD_CUDA(cudaEventRecord(ev[1], st));
+    if (!rc) rc = pd_solve_launch(h, h->work, st, &ev[2]);  // records ev[2] after pass A, ev[3] after PCR
+  }
   PD_CUDA(cudaEventRecord(ev[4], st));
   if (!rc) rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st);
   PD_CUDA(cudaEventRecord(ev[5], st));

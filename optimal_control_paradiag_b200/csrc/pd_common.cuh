@@ -121,6 +121,13 @@ struct pd_handle {
   cudaStream_t sched_aux;
   cudaEvent_t sched_ev[4];
 
+  // fused inverse FFT + pass A (pd_fused.cu): one launch, pass A fed out of L2
+  int fuse_on;             // 1: pd_pc_apply / pd_slab_apply use it
+  int fuse_chunks;         // level-0 chunks per node slab
+  int fuse_cpb;            // chunks per pass-A CTA
+  int fuse_lag;            // pass A trails the FFT by this many slabs
+  void* fuse_plan;
+
   // host staging for the *_host entry points
   cplx* stage_x;
   cplx* stage_y;
@@ -134,6 +141,9 @@ struct pd_handle {
   cplx* kry_w;
   cplx* kry_t;
   cplx* kry_partial;
+  cplx* kry_d;      // (A - P) v of the residual-correction mode: zero except on <= 3 time levels per field
+  int kry_d_mode;   // 0: not initialised, 1: complex layout, 2: float64 layout
+  int opt_gmres_correction;  // pd_set_option "gmres_residual_correction"
   cplx* kry_h;
   double* kry_host;
   cudaStream_t own_stream;
@@ -157,7 +167,12 @@ int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes,
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr, int half_spectrum = 0);
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0,
-                          cudaEvent_t* ev = nullptr);
+                          cudaEvent_t* ev = nullptr, int passA_done = 0);
+cplx* pd_slab_lastl(pd_handle* h);
+// fused inverse FFT + pass A (pd_fused.cu)
+bool pd_fused_supported(const pd_handle* h);
+int pd_fused_ifft_passA_launch(pd_handle* h, const cplx* x, cplx* w, cudaStream_t st, cplx* lastl);
+void pd_fused_free(pd_handle* h);
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0,
                           cudaEvent_t* ev = nullptr);
 bool pd_slab_half_supported(const pd_handle* h);
@@ -168,3 +183,5 @@ bool pd_slab_comm_ready(const pd_handle* h);
 int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int circulant,
                      const cplx* halo_lo = nullptr, const cplx* halo_hi = nullptr, int real_vectors = 0);
 int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors = 0);
+int pd_delta_launch(pd_handle* h, const cplx* x, cplx* d, cudaStream_t st, const cplx* halo_lo = nullptr,
+                    const cplx* halo_hi = nullptr, int real_vectors = 0);

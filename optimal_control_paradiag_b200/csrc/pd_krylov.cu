@@ -9,6 +9,7 @@
 //                      Gram-Schmidt without refinement, zero initial guess,
 //                      preconditioned-residual test relative to ||P^-1 b||).
 #include <math.h>
+#include <string.h>
 
 #include <vector>
 
@@ -146,6 +147,88 @@ int pd_matvec_launch(pd_handle* h, const cplx* x, cplx* y, cudaStream_t st, int 
     pd_matvec_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(x), reinterpret_cast<double*>(y), op);
   else
     pd_matvec_kernel<cplx><<<grid, 256, 0, st>>>(x, y, op);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
+// ------------------------------------------------------------- (A - P) x, the residual-correction operator
+// A (Build_L, :86-179) and the block-circulant P that DiagFFTPC inverts differ only where the time stencils
+// wrap around and in the three special factors (:117, :143, :138):
+//   state row i   : + 2 M u_{i-1+N} [i = 0],  - (M + dt^2/2 K) u_{i-2+N} [i = 0, 1],  + c/2 M p_0 [i = 0],
+//                   + (q - 1) dt^2/2 K (u_i + u_{i-2}) [i = N-1, q = sqrt(gamma) with bug138]
+//   adjoint row i : + 2 M p_{i+1-N} [i = N-1],  - (M + dt^2/2 K) p_{i+2-N} [i = N-2, N-1],  - c/2 M u_{N-1} [i = N-1]
+// so (A - P) x is non-zero on at most three time levels per field.  With it the preconditioned operator is
+//   P^-1 A v = v + P^-1 (A - P) v      (v with zero Dirichlet rows, as every Krylov vector is)
+// which never forms the cancelling second differences of A v: the rounding noise of the matvec -- amplified by the
+// ill-conditioned P^-1, it is what sets the GMRES iteration count at N_x >= 2000 -- is gone.
+// One thread per (node, slot); slots 0..2 = state rows i = 0, 1, N-1, slots 3..4 = adjoint rows i = N-2, N-1.  The
+// output vector must be zero everywhere else (the caller keeps one such vector: only these entries are ever written).
+template <class T>
+__global__ void __launch_bounds__(128)
+pd_delta_kernel(const T* __restrict__ x, T* __restrict__ d, OpParams op) {
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = blockIdx.y;
+  if (jl >= op.nloc) return;
+  const int N = op.N_t;
+  const int j = op.j0 + jl;
+  const bool state = slot < 3;
+  const int i = slot == 0 ? 0 : slot == 1 ? 1 : slot == 2 ? N - 1 : slot == 3 ? N - 2 : N - 1;
+  // duplicates for tiny N_t (N = 3: state rows {0, 1, 2}, adjoint rows {1, 2} are all distinct; nothing to skip)
+  if (state && slot == 2 && i <= 1) return;
+  if (!state && slot == 3 && i == N - 1) return;
+  const int64_t o = (int64_t)jl * N + i;
+  T* out = d + (state ? 0 : op.plane);
+  if (j == 0 || j == op.n - 1) {  // Dirichlet rows: A and P are both the identity there
+    out[o] = vzero(T());
+    return;
+  }
+  const T* u = x;
+  const T* p = x + op.plane;
+  const double m_off = op.h / 6.0, m_dia = 2.0 * op.h / 3.0, ih = 1.0 / op.h;
+  auto Mv = [&](const T* v, int f, int t) {
+    return vlin3(ld_or_zero<T>(v, f, j - 1, t, op), ld_or_zero<T>(v, f, j, t, op), ld_or_zero<T>(v, f, j + 1, t, op),
+                 m_off, m_dia);
+  };
+  auto Kv = [&](const T* v, int f, int t) {
+    const T c = ld_or_zero<T>(v, f, j, t, op);
+    return vscale(vadd(vsub(c, ld_or_zero<T>(v, f, j - 1, t, op)), vsub(c, ld_or_zero<T>(v, f, j + 1, t, op))), ih);
+  };
+  T acc = vzero(T());
+  if (state) {
+    if (i - 1 < 0) acc = vadd(acc, vscale(Mv(u, 0, i - 1 + N), 2.0));
+    if (i - 2 < 0) acc = vsub(acc, vadd(Mv(u, 0, i - 2 + N), vscale(Kv(u, 0, i - 2 + N), op.dt2h)));
+    if (i == 0) acc = vadd(acc, vscale(Mv(p, 1, 0), 0.5 * op.c));
+    if (i == N - 1 && op.qlast != 1.0) {
+      T k2 = Kv(u, 0, i);
+      if (i - 2 >= 0) k2 = vadd(k2, Kv(u, 0, i - 2));
+      acc = vadd(acc, vscale(k2, (op.qlast - 1.0) * op.dt2h));
+    }
+  } else {
+    if (i + 1 >= N) acc = vadd(acc, vscale(Mv(p, 1, i + 1 - N), 2.0));
+    if (i + 2 >= N) acc = vsub(acc, vadd(Mv(p, 1, i + 2 - N), vscale(Kv(p, 1, i + 2 - N), op.dt2h)));
+    if (i == N - 1) acc = vsub(acc, vscale(Mv(u, 0, N - 1), 0.5 * op.c));
+  }
+  out[o] = acc;
+}
+
+int pd_delta_launch(pd_handle* h, const cplx* x, cplx* d, cudaStream_t st, const cplx* halo_lo, const cplx* halo_hi,
+                    int real_vectors) {
+  OpParams op;
+  op.circulant = 0;
+  op.n = h->cfg.N_x + 1; op.N_t = h->cfg.N_t; op.h = h->h; op.dt2h = 0.5 * h->dt * h->dt; op.c = h->c;
+  op.nloc = h->n; op.j0 = h->node_begin; op.halo_lo = halo_lo; op.halo_hi = halo_hi;
+  op.qlast = h->cfg.bug138 ? sqrt(h->cfg.gamma) : 1.0;
+  op.plane = (int64_t)h->n * h->cfg.N_t;
+  if (h->slab_count > 1 && ((h->slab_rank > 0 && !halo_lo) || (h->slab_rank < h->slab_count - 1 && !halo_hi))) {
+    pd_set_error("(A - P) x in slab mode needs the neighbour rows (halo_lo / halo_hi)");
+    return PD_ERR_INVALID;
+  }
+  dim3 grid((h->n + 127) / 128, 5);
+  if (real_vectors)
+    pd_delta_kernel<double><<<grid, 128, 0, st>>>(reinterpret_cast<const double*>(x), reinterpret_cast<double*>(d), op);
+  else
+    pd_delta_kernel<cplx><<<grid, 128, 0, st>>>(x, d, op);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -508,6 +591,9 @@ void pd_krylov_free(pd_handle* h) {
     h->kry_V = nullptr;
   }
   if (h->kry_partial) cudaFree(h->kry_partial);
+  if (h->kry_d) cudaFree(h->kry_d);
+  h->kry_d = nullptr;
+  h->kry_d_mode = 0;
   if (h->kry_h) cudaFree(h->kry_h);
   if (h->kry_t) cudaFree(h->kry_t);
   if (h->kry_host) cudaFreeHost(h->kry_host);
@@ -559,6 +645,20 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
     h->ws_bytes += sizeof(cplx) * full;
   }
   cplx* t = h->kry_t;
+  // residual-correction mode (opt-in, pd_set_option "gmres_residual_correction"): w = v + P^-1 (A - P) v
+  const int correction = h->opt_gmres_correction;
+  if (correction) {
+    const size_t full = 2 * (size_t)h->n * h->cfg.N_t;
+    if (!h->kry_d) {
+      PD_CUDA(cudaMalloc(&h->kry_d, sizeof(cplx) * full));
+      h->ws_bytes += sizeof(cplx) * full;
+      h->kry_d_mode = 0;
+    }
+    if (h->kry_d_mode != (real_vectors ? 2 : 1)) {  // the few non-zero entries sit elsewhere in the other layout
+      PD_CUDA(cudaMemsetAsync(h->kry_d, 0, sizeof(cplx) * full, st));
+      h->kry_d_mode = real_vectors ? 2 : 1;
+    }
+  }
   cplx* hdev = h->kry_h;
   hcplx* hhost = reinterpret_cast<hcplx*>(h->kry_host);
   const int nb1 = (int)((len + 255) / 256 < (int64_t)h->num_sms * 16 ? (len + 255) / 256
@@ -619,8 +719,16 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
         break;
       }
       cplx* w = kc->V[j + 1];
-      if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0, nullptr, nullptr, real_vectors))) return rc;
-      if ((rc = PC(t, w))) return rc;
+      if (correction) {
+        if ((rc = pd_delta_launch(h, kc->V[j], h->kry_d, st, nullptr, nullptr, real_vectors))) return rc;
+        if ((rc = PC(h->kry_d, w))) return rc;
+        pd_axpby_kernel<<<nb1, 256, 0, st>>>(1.0, kc->V[j], 1.0, w, len);
+        PD_CHECK_LAUNCH();
+        h->launches++;
+      } else {
+        if ((rc = pd_matvec_launch(h, kc->V[j], t, st, 0, nullptr, nullptr, real_vectors))) return rc;
+        if ((rc = PC(t, w))) return rc;
+      }
       // classical Gram-Schmidt: all inner products against the unmodified w first
       if ((rc = mdot_list(h, kc->V.data(), j + 1, w, len, hdev, st))) return rc;
       if ((rc = maxpy_list(h, kc->V.data(), j + 1, hdev, -1.0, w, len, hdev + (j + 1), st))) return rc;
@@ -699,4 +807,30 @@ extern "C" int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, doubl
     return PD_ERR_UNSUPPORTED;
   }
   return gmres_impl(h, b_dev, x_dev, rtol, atol, restart, max_it, its_out, hist, reason_out, stream, 1);
+}
+
+// Run-time options of a handle (name, value).  Unknown names are an error.
+//   "gmres_residual_correction" : 0 (default) pd_gmres forms P^-1 (A v) as KSP does; 1: v + P^-1 ((A - P) v)
+extern "C" int pd_set_option(pd_handle* h, const char* name, double value) {
+  if (!h || !name) {
+    pd_set_error("pd_set_option: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  if (!strcmp(name, "gmres_residual_correction")) {
+    h->opt_gmres_correction = value != 0.0;
+    return PD_OK;
+  }
+  pd_set_error("pd_set_option: unknown option '%s'", name);
+  return PD_ERR_INVALID;
+}
+
+// d = (A - P) x on device vectors (complex128, or float64 with real_vectors != 0); d must be zero on entry outside
+// the <= 3 time levels per field the operator touches (see pd_delta_kernel).  x and d must not alias.
+extern "C" int pd_delta(pd_handle* h, const void* x_dev, void* d_dev, int real_vectors, void* stream) {
+  if (!h || !x_dev || !d_dev || x_dev == d_dev || h->slab_count > 1) {
+    pd_set_error("pd_delta: invalid argument (distinct device vectors, unsharded handle)");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  return pd_delta_launch(h, (const cplx*)x_dev, (cplx*)d_dev, (cudaStream_t)stream, nullptr, nullptr, real_vectors);
 }

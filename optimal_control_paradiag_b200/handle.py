@@ -296,10 +296,24 @@ class ParaDiagHandle:
         check(self.lib.pd_build_rhs(self._h, self._ptr(b, None, "b"), self._stream()))
         return b
 
-    def gmres(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
-        """Left-preconditioned GMRES (options of Control_Wave_PC.py:347-359).
+    def set_option(self, name, value):
+        check(self.lib.pd_set_option(self._h, name.encode(), float(value)))
+
+    def delta(self, x, d=None):
+        """d = (A - P) x, the operator of the residual-correction mode (pd_delta); complex128 or float64."""
+        torch = _torch()
+        real = x.dtype == torch.float64
+        if d is None:
+            d = torch.zeros_like(x)
+        check(self.lib.pd_delta(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(d.data_ptr()), int(real), self._stream()))
+        return d
+
+    def gmres(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000, correction=False):
+        """Left-preconditioned GMRES (options of Control_Wave_PC.py:347-359).  ``correction=True`` forms the
+        preconditioned operator as v + P^-1 (A - P) v (pd_set_option "gmres_residual_correction").
 
         Returns (x, iterations, residual_history, reason)."""
+        self.set_option("gmres_residual_correction", 1 if correction else 0)
         if x is None:
             x = self.empty()
         its, reason = C.c_int(0), C.c_int(0)
@@ -333,8 +347,9 @@ class ParaDiagHandle:
         check(self.lib.pd_build_rhs_real(self._h, self._rptr(b, "b"), self._stream()))
         return b
 
-    def gmres_real(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
+    def gmres_real(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000, correction=False):
         """pd_gmres_real: the same Krylov solve on float64 vectors with the half-spectrum preconditioner."""
+        self.set_option("gmres_residual_correction", 1 if correction else 0)
         if x is None:
             x = self.empty_real()
         its, reason = C.c_int(0), C.c_int(0)

@@ -19,7 +19,9 @@ import numpy as np
 
 
 def gmres(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1000,
-          monitor=None):
+          monitor=None, pc_matvec=None):
+    """``pc_matvec`` (optional): v -> P^-1 A v evaluated some other way (the residual-correction form
+    v + P^-1 (A - P) v of pd_set_option "gmres_residual_correction"); the rest of the iteration is unchanged."""
     b = np.asarray(b)
     its = 0
     hist = []
@@ -47,7 +49,7 @@ def gmres(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1000,
         j_done = 0
         converged = False
         for j in range(m):
-            w = pc_apply(matvec(V[j]))
+            w = pc_matvec(V[j]) if pc_matvec is not None else pc_apply(matvec(V[j]))
             Vm = np.array(V)
             h = Vm.conj() @ w                      # classical Gram-Schmidt: all dots first
             w = w - h @ Vm
@@ -93,7 +95,7 @@ def gmres(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1000,
     return x, its, hist, reason
 
 
-def gmres_lean(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1000, monitor=None):
+def gmres_lean(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1000, monitor=None, pc_matvec=None):
     """Same iteration as ``gmres`` (identical arithmetic order per step: classical Gram-Schmidt with all inner
     products taken against the unmodified w, Givens-rotated residual estimate) with the Krylov basis held in
     ONE growing 2-D array instead of a list that is re-stacked every step -- for the BASELINE-size golden
@@ -124,7 +126,7 @@ def gmres_lean(matvec, pc_apply, b, rtol=1e-5, atol=1e-50, restart=300, max_it=1
         g[0] = beta
         j_done, converged = 0, False
         for j in range(m):
-            w = pc_apply(matvec(V[j]))
+            w = pc_matvec(V[j]) if pc_matvec is not None else pc_apply(matvec(V[j]))
             h = V[: j + 1].conj() @ w
             w = w - h @ V[: j + 1]
             H[: j + 1, j] = h

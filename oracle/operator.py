@@ -81,6 +81,51 @@ class AllAtOnce:
         y[:, -1, :] = x[:, -1, :]
         return y.reshape(-1)
 
+    def pc_matvec(self, x):
+        """y = P x for the block-circulant matrix ``DiagFFTPC`` inverts: the operator above with the time stencils
+        made periodic (C1, C2 of mat_test.ipynb cells 8-9) and the factors d_0, e_{N-1}, q_{N-1} replaced by 1."""
+        n, N = self.n, self.N_t
+        x = np.asarray(x).reshape(2, n, N)
+        u, p = x[0], x[1]
+        dt2h = self.dt ** 2 / 2
+        Mu, Ku, Mp, Kp = self._M(u), self._K(u), self._M(p), self._K(p)
+        y = np.zeros_like(x)
+        y[0] = Mu - 2 * np.roll(Mu, 1, axis=1) + np.roll(Mu, 2, axis=1) + dt2h * (Ku + np.roll(Ku, 2, axis=1)) - self.c * Mp
+        y[1] = Mp - 2 * np.roll(Mp, -1, axis=1) + np.roll(Mp, -2, axis=1) + dt2h * (Kp + np.roll(Kp, -2, axis=1)) + self.c * Mu
+        y[:, 0, :] = x[:, 0, :]
+        y[:, -1, :] = x[:, -1, :]
+        return y.reshape(-1)
+
+    def delta(self, x):
+        """(A - P) x written out term by term -- the residual-correction operator (pd_delta): only the wrap-around
+        time levels and the special factors (:117, :143, :138) differ between A and P, so the result is non-zero on
+        at most three time levels per field and no second difference is ever formed."""
+        n, N = self.n, self.N_t
+        x = np.asarray(x).reshape(2, n, N)
+        u, p = x[0], x[1]
+        dt2h = self.dt ** 2 / 2
+        d = np.zeros_like(x)
+        Mc = lambda v: self._M(v.reshape(n, 1))[:, 0]
+        Kc = lambda v: self._K(v.reshape(n, 1))[:, 0]
+        for i in range(min(2, N)):
+            if i - 1 < 0:
+                d[0][:, i] += 2 * Mc(u[:, i - 1 + N])
+            if i - 2 < 0:
+                d[0][:, i] -= Mc(u[:, i - 2 + N]) + dt2h * Kc(u[:, i - 2 + N])
+        d[0][:, 0] += 0.5 * self.c * Mc(p[:, 0])
+        if self.bug138 and self.gamma != 1.0:
+            k2 = Kc(u[:, N - 1]) + (Kc(u[:, N - 3]) if N - 3 >= 0 else 0)
+            d[0][:, N - 1] += (np.sqrt(self.gamma) - 1.0) * dt2h * k2
+        for i in range(max(N - 2, 0), N):
+            if i + 1 >= N:
+                d[1][:, i] += 2 * Mc(p[:, i + 1 - N])
+            if i + 2 >= N:
+                d[1][:, i] -= Mc(p[:, i + 2 - N]) + dt2h * Kc(p[:, i + 2 - N])
+        d[1][:, N - 1] -= 0.5 * self.c * Mc(u[:, N - 1])
+        d[:, 0, :] = 0
+        d[:, -1, :] = 0
+        return d.reshape(-1)
+
     def rhs(self):
         """b of ``A U = b`` for the manufactured data (:48-83, pc=True scaling)."""
         n, N, dt, T, gamma = self.n, self.N_t, self.dt, self.T, self.gamma

@@ -9,6 +9,10 @@ complex solve carries is rounding noise (tests/test_oracle_operator_gmres.py che
 sizes).  One rtol = 1e-9 run per case yields the whole history; the count for any looser rtol is the first
 index whose residual is below rtol * hist[0] (no restart happens within 300 steps).
 
+Each case is also run in the residual-correction form of the preconditioned operator, v + P^-1 (A - P) v
+(``correction``): no cancelling second difference is formed, the count is the exact-arithmetic one and does not move
+under the perturbation.
+
 Also records, per case, how the count reacts to a relative perturbation eps of the PC output (a stand-in for a
 DIFFERENT but equally valid fp64 implementation of the same preconditioner): where the count moves, it is set
 by rounding and a +-1 comparison between implementations is not meaningful.
@@ -44,7 +48,7 @@ def count(hist, rtol):
     return None
 
 
-def run(N_x, N_t, gamma, eps=0.0, rtol=1e-9, max_it=60, seed=7):
+def run(N_x, N_t, gamma, eps=0.0, rtol=1e-9, max_it=60, seed=7, correction=False):
     op = AllAtOnce(N_x, N_t, 2.0, gamma)
     pc = DiagFFTPCFast(N_x, N_t, 2.0, gamma)
     rng = np.random.default_rng(seed)
@@ -57,7 +61,9 @@ def run(N_x, N_t, gamma, eps=0.0, rtol=1e-9, max_it=60, seed=7):
 
     b = op.rhs()
     t = time.time()
-    _, its, hist, reason = gmres_lean(op.matvec, pc_apply, b, rtol=rtol, max_it=max_it)
+    # correction: the preconditioned operator as v + P^-1 (A - P) v (pd_set_option "gmres_residual_correction")
+    pcm = (lambda v: v + pc_apply(op.delta(v))) if correction else None
+    _, its, hist, reason = gmres_lean(op.matvec, pc_apply, b, rtol=rtol, max_it=max_it, pc_matvec=pcm)
     return {"its_at_1e-9": its if reason.startswith("CONVERGED") else None, "hist": hist, "reason": reason,
             "seconds": time.time() - t}
 
@@ -76,8 +82,15 @@ def main():
         for eps in (1e-13, 1e-11):
             p = run(N_x, N_t, gamma, eps=eps)
             rec["perturbed"][f"{eps:g}"] = {f"{r:g}": count(p["hist"], r) for r in (1e-5, 1e-7, 1e-9)}
+        corr = run(N_x, N_t, gamma, correction=True)
+        rec["correction"] = {"hist": corr["hist"], "its": {f"{r:g}": count(corr["hist"], r) for r in (1e-5, 1e-7, 1e-9)},
+                             "perturbed": {}}
+        for eps in (1e-13, 1e-11):
+            p = run(N_x, N_t, gamma, eps=eps, correction=True)
+            rec["correction"]["perturbed"][f"{eps:g}"] = {f"{r:g}": count(p["hist"], r) for r in (1e-5, 1e-7, 1e-9)}
         db[name] = rec
-        print(name, rec["its"], rec["perturbed"], f"{rec['seconds']:.1f}s", flush=True)
+        print(name, rec["its"], rec["perturbed"], "| correction", rec["correction"]["its"],
+              rec["correction"]["perturbed"], f"{rec['seconds']:.1f}s", flush=True)
         json.dump(db, open(OUT, "w"), indent=1)
 
 
