@@ -160,12 +160,15 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
       }
     }
   }
-  // Fused inverse FFT + pass A (pd_fused.cu): on by default where it exists (power-of-two N_t in
-  // [1024, 8192], alpha = 1 or not, unsharded or x-slab handles).  PD_FUSE=0 selects the two separate kernels;
-  // PD_FUSE_CHUNKS / PD_FUSE_CPB / PD_FUSE_LAG tune the node-slab size, the chunks per pass-A CTA and the lag.
+  // Fused inverse FFT + pass A (pd_fused.cu; power-of-two N_t in [1024, 8192], unsharded or x-slab handles):
+  // OPT-IN with PD_FUSE=1.  Bit-identical results and pass A really is fed out of L2, but MEASURED SLOWER on B200:
+  // 1.40-1.50 ms for the fused launch against 0.68 + 0.38 ms for the two kernels at cfg3 (tools/fuse_probe.py, 24
+  // settings of slab size / chunks per CTA / lag).  Both roles are occupancy-bound at two CTAs per SM: an FFT CTA
+  // needs every resident slot to keep HBM busy, so slots given to pass-A CTAs slow the FFT by the same amount
+  // (DESIGN.md section 8).  PD_FUSE_CHUNKS / PD_FUSE_CPB / PD_FUSE_LAG tune it.
   {
     const char* e = getenv("PD_FUSE");
-    h->fuse_on = pd_fused_supported(h) && !(e && e[0] == '0');
+    h->fuse_on = pd_fused_supported(h) && e && e[0] == '1';
     const char* c = getenv("PD_FUSE_CHUNKS");
     h->fuse_chunks = c && atoi(c) > 0 ? atoi(c) : 8;
     const char* b = getenv("PD_FUSE_CPB");

@@ -39,6 +39,7 @@
 //            separator values, rotates back and stores in place.
 // The level-0 pivots m_i depend on (k, i) only; each CTA regenerates them once into a
 // per-thread shared-memory column and reuses them for all the chunks it visits.
+#include <stdlib.h>
 #include <string.h>
 
 #include "pd_common.cuh"
@@ -188,12 +189,126 @@ pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
   }
 }
 
+// ---- peer-store exchange of the slab functionals (the fused compute + collective step of slab mode)
+// Every rank owns one "symmetric" buffer, mapped into all ranks (cudaIpc between processes, plain peer access
+// inside one process):   gathered[2 parities][G ranks][6][kmax] complex  +  flags[2][G][nflag] (uint64 epochs).
+// The kernel that produces a slab's six functionals per frequency STORES them straight into slot [rank] of
+// every rank's buffer (NVLink peer stores, fire and forget), fences, and publishes one flag per (rank, block of
+// PD_KB frequencies) = the apply's epoch.  The kernel that consumes them (separator solve) waits at its head for
+// the G flags of ITS frequency block only.  No host-launched collective, no extra kernel, no barrier:
+//   * parity = epoch & 1 double-buffers the slots: a rank can be at most one apply ahead of a peer (its
+//     epoch e+1 separator solve needs the peer's e+1 functionals, which the peer issues after finishing e);
+//   * epochs live in device memory (bumped by pass B), so the whole apply is capturable in a CUDA graph;
+//   * the wait is bounded (PD_SLAB_SPIN_LIMIT clock ticks): on expiry the kernel raises err[0] and goes on,
+//     the host reports it (pd_slab_comm_status) -- a dead peer can never hang the GPU.
+#define PD_SLAB_SPIN_LIMIT (8ll * 1000 * 1000 * 1000)
+struct SlabCommDev {
+  cplx* peer_gath[PD_MAX_SLABS];                  // every rank's gathered buffer (own included)
+  unsigned long long* peer_flag[PD_MAX_SLABS];    // every rank's flag array
+  const unsigned long long* epoch;                // completed applies of THIS rank
+  int* err;
+  int64_t kmax;
+  int nflag, G, rank;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+#define PD_FKB 4  // frequencies per flag of the exchange (every producer covers whole groups of PD_FKB columns)
+
+// slot [parity][rank] of EVERY rank's buffer (peer stores over NVLink; the own copy is a local store)
+__device__ __forceinline__ void slab_push(const SlabCommDev& cm, unsigned long long ep, int kk, cplx fP, cplx fM,
+                                          cplx lP, cplx lM, cplx sP, cplx sM) {
+  const int64_t slot = (((int64_t)(ep & 1ull) * cm.G + cm.rank) * 6) * cm.kmax + kk;
+  for (int p = 0; p < cm.G; ++p) {
+    cplx* g = cm.peer_gath[p] + slot;
+    g[0] = fP; g[cm.kmax] = fM; g[2 * cm.kmax] = lP; g[3 * cm.kmax] = lM;
+    g[4 * cm.kmax] = sP; g[5 * cm.kmax] = sM;
+  }
+}
+// Publish the columns [k0, k0 + ncols) of this CTA to every rank: called by ALL threads of the CTA after their
+// slab_push calls; every thread's stores are ordered before the flags at system scope.
+__device__ __forceinline__ void slab_publish(const SlabCommDev& cm, unsigned long long ep, int k0, int ncols) {
+  __threadfence_system();
+  __syncthreads();
+  const int f0 = k0 / PD_FKB, nf = (ncols + PD_FKB - 1) / PD_FKB;
+  for (int i = threadIdx.x; i < nf * cm.G; i += blockDim.x) {
+    const int p = i / nf, f = f0 + (i - p * nf);
+    st_release_sys(cm.peer_flag[p] + ((int64_t)(ep & 1ull) * cm.G + cm.rank) * cm.nflag + f, ep);
+  }
+}
+// Wait (bounded) until the columns [k0, k0 + ncols) have arrived from every rank; all threads of the CTA call it.
+__device__ __forceinline__ void slab_wait(const SlabCommDev& cm, unsigned long long ep, int k0, int ncols) {
+  const int f0 = k0 / PD_FKB, nf = (ncols + PD_FKB - 1) / PD_FKB;
+  for (int i = threadIdx.x; i < nf * cm.G; i += blockDim.x) {
+    const int src = i / nf, f = f0 + (i - src * nf);
+    const unsigned long long* fl = cm.peer_flag[cm.rank] + ((int64_t)(ep & 1ull) * cm.G + src) * cm.nflag + f;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(fl) < ep) {
+      if (clock64() - t0 > PD_SLAB_SPIN_LIMIT) {
+        atomicExch(cm.err, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+// The six functionals of this slab for one frequency: first / last entry of the slab-local solve (two right-hand
+// sides each) and the rotated right-hand side of the separator row this slab owns.
+//   f0P/f0M : F[0] of chunk 0 (zero without interface), lastP/lastM : last entry of the last chunk (pass A),
+//   z0*, ze* : interface solution at the first / last level-1 row (unused when P == 0)
+__device__ __forceinline__ void slab_functionals(const KCoef& kc, const SolveParams& sp, const cplx* __restrict__ w,
+                                                 int kk, cplx f0P, cplx f0M, cplx lastP, cplx lastM, cplx z0P,
+                                                 cplx z0M, cplx zeP, cplx zeM, cplx& fP, cplx& fM, cplx& lP, cplx& lM,
+                                                 cplx& sP, cplx& sM) {
+  const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
+  fP = f0P; fM = f0M;
+  lP = cmake(0, 0); lM = cmake(0, 0);
+  if (Llast > 0) { lP = lastP; lM = lastM; }
+  if (P > 0) {
+    // first entry of chunk 0 and last entry of the last chunk, given the interface solution
+    VRec v;
+    v.init(kc.a, kc.sh, cmake(0, 0));
+    cplx rvL = cmake(0, 0), rvLl = cmake(0, 0);
+    if (!v.diag) {
+      for (int i = 1; i <= PD_L; ++i) {
+        v.step();
+        if (i == Llast) rvLl = cscale(crcp(v.V), v.one);
+      }
+      rvL = cscale(crcp(v.V), v.one);
+    }
+    fP = cfma(z0P, rvL, fP);  // f_0 - a z_sep0 (T_L^-1)_{1L} = f_0 + z_sep0 / V_L
+    fM = cfma(z0M, rvL, fM);
+    if (Llast > 0) {
+      lP = cfma(zeP, rvLl, lP);
+      lM = cfma(zeM, rvLl, lM);
+    } else {
+      lP = zeP;  // the last body row is the last separator itself
+      lM = zeM;
+    }
+  }
+  sP = cmake(0, 0); sM = cmake(0, 0);
+  if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+}
+
 // ------------------------------------------------ top interface system (PCR in smem)
 // One CTA solves the top-level systems of `kpb` consecutive frequencies (n <= PD_PCR_MAX rows
 // each, two right-hand sides) by parallel cyclic reduction.  Rows are kept normalised (unit
 // diagonal): (lo, 1, up | rP, rM).  smem slot = ks * n + q.
+// PUSH (slab mode, lev == 1 == top): the level-1 solution is still in shared memory when the kernel ends, so the
+// slab functionals are formed and stored into every rank's exchange buffer right here (no separate launch).
+template <bool PUSH>
 __global__ void __launch_bounds__(PD_PCR_THREADS)
-pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
+pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __restrict__ w, SlabPtrs sl,
+                    SlabCommDev cm) {
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   __shared__ cplx c_off[32], c_dmain[32], c_dlast[32], c_offb[32];
   const int n = sp.rows[lev];
@@ -294,6 +409,19 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb) {
     const int slot = ks * n + q;
     Rw[((int64_t)q * 2) * K + kk] = s_rp[slot];
     Rw[((int64_t)q * 2 + 1) * K + kk] = s_rm[slot];
+  }
+  if (PUSH) {
+    const unsigned long long ep = *cm.epoch + 1ull;
+    const int kk = kk0 + tid;
+    if (tid < kpb && kk < sp.kend) {
+      const KCoef kc = make_coef(freq_of(sp, kk), sp);
+      const int b0 = tid * n, b1 = tid * n + n - 1;
+      cplx fP, fM, lP, lM, sP, sM;
+      slab_functionals(kc, sp, w, kk, lv.F[0][kk], lv.F[0][K + kk], sl.lastl[kk], sl.lastl[K + kk], s_rp[b0], s_rm[b0],
+                       s_rp[b1], s_rm[b1], fP, fM, lP, lM, sP, sM);
+      slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
+    }
+    slab_publish(cm, ep, kk0, min(kpb, sp.kend - kk0));
   }
 }
 
@@ -438,100 +566,34 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
 // with rv_s = 1/V_{m_s}, dvv_s = (V_{m_s} - V_{m_s - 1}) / V_{m_s} (cancellation-free, see Sys) and
 // f_s / l_s the first / last entry of the slab-local solve with zero neighbours.
 
-// ---- peer-store exchange of the slab functionals (the fused compute + collective step of slab mode)
-// Every rank owns one "symmetric" buffer, mapped into all ranks (cudaIpc between processes, plain peer access
-// inside one process):   gathered[2 parities][G ranks][6][kmax] complex  +  flags[2][G][nflag] (uint64 epochs).
-// The kernel that produces a slab's six functionals per frequency STORES them straight into slot [rank] of
-// every rank's buffer (NVLink peer stores, fire and forget), fences, and publishes one flag per (rank, block of
-// PD_KB frequencies) = the apply's epoch.  The kernel that consumes them (separator solve) waits at its head for
-// the G flags of ITS frequency block only.  No host-launched collective, no extra kernel, no barrier:
-//   * parity = epoch & 1 double-buffers the slots: a rank can be at most one apply ahead of a peer (its
-//     epoch e+1 separator solve needs the peer's e+1 functionals, which the peer issues after finishing e);
-//   * epochs live in device memory (bumped by pass B), so the whole apply is capturable in a CUDA graph;
-//   * the wait is bounded (PD_SLAB_SPIN_LIMIT clock ticks): on expiry the kernel raises err[0] and goes on,
-//     the host reports it (pd_slab_comm_status) -- a dead peer can never hang the GPU.
-#define PD_SLAB_SPIN_LIMIT (8ll * 1000 * 1000 * 1000)
-struct SlabCommDev {
-  cplx* peer_gath[PD_MAX_SLABS];                  // every rank's gathered buffer (own included)
-  unsigned long long* peer_flag[PD_MAX_SLABS];    // every rank's flag array
-  const unsigned long long* epoch;                // completed applies of THIS rank
-  int* err;
-  int64_t kmax;
-  int nflag, G, rank;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // out[6][K] = (f+, f-, l+, l-, rho_sep+, rho_sep-) of this slab
 template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
                            cplx* __restrict__ out, SlabCommDev cm) {
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
   if (kk < sp.K) {
-  const int64_t K = sp.K;
-  const KCoef kc = make_coef(freq_of(sp, kk), sp);
-  const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
-  cplx fP = lv.F[0] ? lv.F[0][kk] : cmake(0, 0), fM = lv.F[0] ? lv.F[0][K + kk] : cmake(0, 0);
-  cplx lP = cmake(0, 0), lM = cmake(0, 0);
-  if (Llast > 0) { lP = sl.lastl[kk]; lM = sl.lastl[K + kk]; }
-  if (P > 0) {
-    // first entry of chunk 0 and last entry of the last chunk, given the interface solution
-    VRec v;
-    v.init(kc.a, kc.sh, cmake(0, 0));
-    cplx rvL = cmake(0, 0), rvLl = cmake(0, 0);
-    if (!v.diag) {
-      for (int i = 1; i <= PD_L; ++i) {
-        v.step();
-        if (i == Llast) rvLl = cscale(crcp(v.V), v.one);
-      }
-      rvL = cscale(crcp(v.V), v.one);
+    const int64_t K = sp.K;
+    const KCoef kc = make_coef(freq_of(sp, kk), sp);
+    const int P = sp.rows[1];
+    const cplx zero = cmake(0, 0);
+    cplx z0P = zero, z0M = zero, zeP = zero, zeM = zero;
+    if (P > 0) {
+      z0P = lv.R[1][kk]; z0M = lv.R[1][K + kk];
+      zeP = lv.R[1][((int64_t)(P - 1) * 2) * K + kk]; zeM = lv.R[1][((int64_t)(P - 1) * 2 + 1) * K + kk];
     }
-    const cplx z0P = lv.R[1][kk], z0M = lv.R[1][K + kk];
-    const cplx zeP = lv.R[1][((int64_t)(P - 1) * 2) * K + kk], zeM = lv.R[1][((int64_t)(P - 1) * 2 + 1) * K + kk];
-    fP = cfma(z0P, rvL, fP);  // f_0 - a z_sep0 (T_L^-1)_{1L} = f_0 + z_sep0 / V_L
-    fM = cfma(z0M, rvL, fM);
-    if (Llast > 0) {
-      lP = cfma(zeP, rvLl, lP);
-      lM = cfma(zeM, rvLl, lM);
+    cplx fP, fM, lP, lM, sP, sM;
+    slab_functionals(kc, sp, w, kk, lv.F[0] ? lv.F[0][kk] : zero, lv.F[0] ? lv.F[0][K + kk] : zero, sl.lastl[kk],
+                     sl.lastl[K + kk], z0P, z0M, zeP, zeM, fP, fM, lP, lM, sP, sM);
+    if (!PUSH) {
+      out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
+      out[4 * K + kk] = sP; out[5 * K + kk] = sM;
     } else {
-      lP = zeP;  // the last body row is the last separator itself
-      lM = zeM;
+      slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
     }
   }
-  cplx sP = cmake(0, 0), sM = cmake(0, 0);
-  if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
-  if (!PUSH) {
-    out[kk] = fP; out[K + kk] = fM; out[2 * K + kk] = lP; out[3 * K + kk] = lM;
-    out[4 * K + kk] = sP; out[5 * K + kk] = sM;
-  } else {
-    // slot [parity][rank] of EVERY rank's buffer (peer stores over NVLink; the own copy is a local store)
-    const unsigned long long ep = *cm.epoch + 1ull;
-    const int64_t slot = (((int64_t)(ep & 1ull) * cm.G + cm.rank) * 6) * cm.kmax + kk;
-    for (int p = 0; p < cm.G; ++p) {
-      cplx* g = cm.peer_gath[p] + slot;
-      g[0] = fP; g[cm.kmax] = fM; g[2 * cm.kmax] = lP; g[3 * cm.kmax] = lM;
-      g[4 * cm.kmax] = sP; g[5 * cm.kmax] = sM;
-    }
-  }
-  }  // kk < sp.K
-  if (PUSH) {
-    // publish: every thread's stores are ordered before the flag at system scope
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < cm.G) {
-      const unsigned long long ep = *cm.epoch + 1ull;
-      unsigned long long* f = cm.peer_flag[threadIdx.x] + ((int64_t)(ep & 1ull) * cm.G + cm.rank) * cm.nflag + blockIdx.x;
-      st_release_sys(f, ep);
-    }
-  }
+  if (PUSH) slab_publish(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.K - blockIdx.x * PD_KB));
 }
 
 struct SlabGeom {
@@ -569,18 +631,7 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   if (WAIT) {
     // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
     const unsigned long long ep = *cm.epoch + 1ull;
-    if (threadIdx.x < cm.G) {
-      const unsigned long long* f = cm.peer_flag[cm.rank] + ((int64_t)(ep & 1ull) * cm.G + threadIdx.x) * cm.nflag + blockIdx.x;
-      const long long t0 = clock64();
-      while (ld_acquire_sys(f) < ep) {
-        if (clock64() - t0 > PD_SLAB_SPIN_LIMIT) {
-          atomicExch(cm.err, 1);
-          break;
-        }
-        __nanosleep(64);
-      }
-    }
-    __syncthreads();
+    slab_wait(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.K - blockIdx.x * PD_KB));
     gathered = cm.peer_gath[cm.rank] + (int64_t)(ep & 1ull) * cm.G * 6 * cm.kmax;
   }
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
@@ -734,7 +785,15 @@ void pd_solve_fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& s
 }
 
 // levels 1..top: reduce, PCR on the top system, back-substitute; leaves the level-1 solution in R[1]
-static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, cudaStream_t st) {
+struct PushCtx {
+  const cplx* w;
+  SlabPtrs sl;
+  SlabCommDev cm;
+};
+// push != nullptr and a single-level interface: the PCR kernel also forms and pushes the slab functionals
+// (returns with *pushed = true); otherwise the caller launches pd_slab_functionals_kernel
+static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, cudaStream_t st,
+                         const PushCtx* push = nullptr, bool* pushed = nullptr) {
   const int top = sp.nlev;
   const int ncol = sp.kend - sp.koff;
   for (int lev = 1; lev < top; ++lev) {
@@ -750,7 +809,16 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   if (kpb < 1) kpb = 1;
   const size_t smem = (size_t)n * kpb * 64;
   const int nblk = (ncol + kpb - 1) / kpb;
-  pd_solve_pcr_kernel<<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb);
+  if (push && top == 1 && kpb % PD_FKB == 0) {
+    pd_solve_pcr_kernel<true><<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb, push->w, push->sl, push->cm);
+    if (pushed) *pushed = true;
+  } else {
+    SlabPtrs nosl;
+    SlabCommDev nocm;
+    memset(&nosl, 0, sizeof(nosl));
+    memset(&nocm, 0, sizeof(nocm));
+    pd_solve_pcr_kernel<false><<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb, nullptr, nosl, nocm);
+  }
   PD_CHECK_LAUNCH();
   h->launches++;
   for (int lev = top - 1; lev >= 1; --lev) {
@@ -763,14 +831,23 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
 
 int pd_solve_plan(pd_handle* h) {
   // largest dynamic shared memory the PCR kernel is ever launched with (set once, not per launch)
-  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               PD_PCR_THREADS * PD_PCR_MAXROWS * 64));
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                PD_PCR_THREADS * PD_PCR_MAXROWS * 64));
   SolvePlan* pl = new SolvePlan();
   memset(pl, 0, sizeof(*pl));
   h->solve_plan = pl;
   h->L = PD_L;
   const size_t K = (size_t)h->kcount;
-  // rows[0] = m; reduce while the interface is too large for the PCR kernel
+  // rows[0] = m; reduce while the interface is too large for the PCR kernel.  Few frequencies, or an x-slab of a
+  // multi-GPU run (a short local x-range: the chain of small launches is what limits scaling there): hand up to 128
+  // rows to PCR and save two launches per level.  PD_PCR_MAX overrides (experiments).
+  int pcr_max = (K <= 2048 || h->slab_count > 1) ? PD_PCR_MAX_SMALLK : PD_PCR_MAX;
+  if (const char* e = getenv("PD_PCR_MAX")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= PD_PCR_MAX_SMALLK) pcr_max = v;
+  }
   pl->rows[0] = h->m;
   int l = 0;
   while (true) {
@@ -781,7 +858,7 @@ int pd_solve_plan(pd_handle* h) {
     const int next = pl->rows[l] / (chunk_len(l) + 1);
     pl->rows[l + 1] = next;
     ++l;
-    if (next <= (K <= 2048 ? PD_PCR_MAX_SMALLK : PD_PCR_MAX)) break;
+    if (next <= pcr_max) break;
   }
   // l is the top level: solved by PCR when it has rows, absent when rows == 0
   pl->nlev = pl->rows[l] > 0 ? l : l - 1;
@@ -962,7 +1039,7 @@ int pd_slab_comm_create_impl(pd_handle* h, void* ipc_handle_out, void** base_out
     const int G = pl->sg.G;
     pl->comm_kmax = ((int64_t)h->cfg.N_t + 7) & ~7ll;  // covers the half spectrum's Kp as well (N_t >= 128)
     if (pl->comm_kmax < 8) pl->comm_kmax = 8;
-    pl->comm_nflag = (int)((pl->comm_kmax + PD_KB - 1) / PD_KB);
+    pl->comm_nflag = (int)((pl->comm_kmax + PD_FKB - 1) / PD_FKB);
     pl->comm_bytes = comm_gath_bytes(G, pl->comm_kmax) + sizeof(unsigned long long) * 2 * (size_t)G * pl->comm_nflag;
     PD_CUDA(cudaMalloc(&pl->comm_base, pl->comm_bytes));
     PD_CUDA(cudaMemset(pl->comm_base, 0, pl->comm_bytes));
@@ -1062,6 +1139,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
     pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
     return PD_ERR_INVALID;
   }
+  bool pushed = false;
   if (sp.nlev >= 1) {
     if (!passA_done) {
       pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
@@ -1069,7 +1147,11 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
       h->launches++;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    int rc = run_interface(h, sp, lv, st);
+    PushCtx pc;
+    if (!out) {
+      pc.w = w; pc.sl = sl; pc.cm = comm_dev_of(h);
+    }
+    int rc = run_interface(h, sp, lv, st, out ? nullptr : &pc, &pushed);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], st);
   } else {
@@ -1081,6 +1163,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
     h->launches++;
     if (ev) { cudaEventRecord(ev[0], st); cudaEventRecord(ev[1], st); }
   }
+  if (pushed) return PD_OK;  // the PCR kernel has already pushed the functionals
   if (out) {
     SlabCommDev none;
     memset(&none, 0, sizeof(none));
