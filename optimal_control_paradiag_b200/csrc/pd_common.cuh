@@ -111,6 +111,7 @@ struct pd_handle {
   int P;       // separators (interface unknowns per system)
   int Llast;   // rows in the last chunk
   void* solve_plan;  // SolvePlan of pd_solve.cu: level sizes and interface workspaces
+  int iface_thomas_max;  // interface systems up to this many rows use the one-launch sequential kernel
 
   // work vector (2, n, N_t) for the single-GPU apply
   cplx* work;

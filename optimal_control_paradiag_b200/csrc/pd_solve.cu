@@ -425,6 +425,104 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __r
   }
 }
 
+// --------------------------------------- the whole level-1 interface system in ONE launch (sequential LU)
+// thread = one frequency (both right-hand sides).  The level-1 system tridiag(off, dmain, off) with its modified
+// last row is factorised by the same cancellation-free pivot generator as the chunk-local systems
+// (m_q = -V_{q-1} / (off V_q), PivotGen) and swept once forward, once backward, straight out of global memory:
+// every row access of a warp is one contiguous 512-byte segment, the loads of the next PD_IT rows are issued
+// before the dependent recurrences of the current ones.  F[0][q+1] is dead once row q's right-hand side has been
+// formed, so its first slot keeps the pivot m_q for the way back -- nothing extra is stored.
+// Replaces the reduce / PCR / back chain (3-7 short launches) wherever the interface is short enough for the
+// sequential latency (rows[1] <= PD_ITHOMAS_MAX): small N_x and, above all, the x-slabs of a multi-GPU run, where
+// that chain of launches was the part of the apply that did not shrink with the number of GPUs.
+// PUSH (slab mode): the thread ends with the first and last interface values in registers, forms the slab
+// functionals and stores them into every rank's exchange buffer (no separate launch).
+#define PD_IT 4
+template <bool PUSH>
+__global__ void __launch_bounds__(PD_KB)
+pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ w, SlabPtrs sl, SlabCommDev cm) {
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
+  if (kk < sp.kend) {
+    const KCoef kc = make_coef(freq_of(sp, kk), sp);
+    const Sys below = level_sys(kc, sp, 0);
+    const Sys s = reduce_sys(below, PD_L);
+    const int64_t K = sp.K;
+    const int P = sp.rows[1];
+    cplx* R = lv.R[1] + kk;
+    cplx* F = lv.F[0] + kk;
+    PivotGen pg;
+    pg.init(s);
+    cplx dP = cmake(0, 0), dM = cmake(0, 0);
+    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q ; m_q parked in F[q+1].  Double-buffered batches of PD_IT rows:
+    // the loads of batch b+1 are in flight while the dependent recurrences of batch b run.
+    cplx rP[PD_IT], rM[PD_IT], fP[PD_IT], fM[PD_IT];
+    auto load_fwd = [&](int q0, cplx* aP, cplx* aM, cplx* bP, cplx* bM) {
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        const int64_t q = min(q0 + i, P - 1);
+        aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
+        bP[i] = F[((q + 1) * 2) * K]; bM[i] = F[((q + 1) * 2 + 1) * K];
+      }
+    };
+    load_fwd(0, rP, rM, fP, fM);
+    for (int q0 = 0; q0 < P; q0 += PD_IT) {
+      cplx nrP[PD_IT], nrM[PD_IT], nfP[PD_IT], nfM[PD_IT];
+      load_fwd(q0 + PD_IT, nrP, nrM, nfP, nfM);
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        const int64_t q = q0 + i;
+        if (q < P) {
+          cplx m = pg.next();
+          if (q == P - 1) m = last_row_pivot(m, s.glast);
+          dP = cmul(cfms(s.off, dP, cfms(below.off, fP[i], rP[i])), m);
+          dM = cmul(cfms(s.off, dM, cfms(below.off, fM[i], rM[i])), m);
+          R[(q * 2) * K] = dP; R[(q * 2 + 1) * K] = dM;
+          F[((q + 1) * 2) * K] = m;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) { rP[i] = nrP[i]; rM[i] = nrM[i]; fP[i] = nfP[i]; fM[i] = nfM[i]; }
+    }
+    // ---- backward: z_q = d_q - off m_q z_{q+1}
+    const cplx zeP = dP, zeM = dM;
+    cplx zP = dP, zM = dM;
+    cplx eP[PD_IT], eM[PD_IT], mm[PD_IT];
+    auto load_bwd = [&](int q0, cplx* aP, cplx* aM, cplx* am) {
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        const int64_t q = max(q0 - i, 0);
+        aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
+        am[i] = F[((q + 1) * 2) * K];
+      }
+    };
+    load_bwd(P - 2, eP, eM, mm);
+    for (int q0 = P - 2; q0 >= 0; q0 -= PD_IT) {
+      cplx neP[PD_IT], neM[PD_IT], nmm[PD_IT];
+      load_bwd(q0 - PD_IT, neP, neM, nmm);
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        const int64_t q = q0 - i;
+        if (q >= 0) {
+          const cplx cp = cmul(s.off, mm[i]);
+          zP = cfms(cp, zP, eP[i]);
+          zM = cfms(cp, zM, eM[i]);
+          R[(q * 2) * K] = zP; R[(q * 2 + 1) * K] = zM;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) { eP[i] = neP[i]; eM[i] = neM[i]; mm[i] = nmm[i]; }
+    }
+    if (PUSH) {
+      cplx fP, fM, lP, lM, sP, sM;
+      slab_functionals(kc, sp, w, kk, lv.F[0][kk], lv.F[0][K + kk], sl.lastl[kk], sl.lastl[K + kk], zP, zM, zeP, zeM,
+                       fP, fM, lP, lM, sP, sM);
+      slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
+    }
+  }
+  if (PUSH) slab_publish(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.kend - blockIdx.x * PD_KB));
+}
+
 // ------------------------------------------------------------------- pass B
 template <bool SLAB, bool AL>
 __global__ void __launch_bounds__(PD_KB)
@@ -796,6 +894,22 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
                          const PushCtx* push = nullptr, bool* pushed = nullptr) {
   const int top = sp.nlev;
   const int ncol = sp.kend - sp.koff;
+  if (h->iface_thomas_max > 0 && sp.rows[1] <= h->iface_thomas_max && sp.koff == 0) {
+    const int nblk = (ncol + PD_KB - 1) / PD_KB;
+    if (push) {
+      pd_solve_iface_thomas_kernel<true><<<nblk, PD_KB, 0, st>>>(lv, sp, push->w, push->sl, push->cm);
+      if (pushed) *pushed = true;
+    } else {
+      SlabPtrs nosl;
+      SlabCommDev nocm;
+      memset(&nosl, 0, sizeof(nosl));
+      memset(&nocm, 0, sizeof(nocm));
+      pd_solve_iface_thomas_kernel<false><<<nblk, PD_KB, 0, st>>>(lv, sp, nullptr, nosl, nocm);
+    }
+    PD_CHECK_LAUNCH();
+    h->launches++;
+    return PD_OK;
+  }
   for (int lev = 1; lev < top; ++lev) {
     pd_solve_level_reduce_kernel<<<stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
     PD_CHECK_LAUNCH();
@@ -840,14 +954,18 @@ int pd_solve_plan(pd_handle* h) {
   h->solve_plan = pl;
   h->L = PD_L;
   const size_t K = (size_t)h->kcount;
-  // rows[0] = m; reduce while the interface is too large for the PCR kernel.  Few frequencies, or an x-slab of a
-  // multi-GPU run (a short local x-range: the chain of small launches is what limits scaling there): hand up to 128
-  // rows to PCR and save two launches per level.  PD_PCR_MAX overrides (experiments).
-  int pcr_max = (K <= 2048 || h->slab_count > 1) ? PD_PCR_MAX_SMALLK : PD_PCR_MAX;
+  // rows[0] = m; reduce while the interface is too large for the PCR kernel (few frequencies: up to 128 rows go
+  // to PCR and save launches).  PD_PCR_MAX overrides (experiments; PCR of 120 rows at K = 4096 measured 0.23 ms
+  // against 0.05 ms for reduce / PCR(13) / back, and is less accurate).
+  int pcr_max = K <= 2048 ? PD_PCR_MAX_SMALLK : PD_PCR_MAX;
   if (const char* e = getenv("PD_PCR_MAX")) {
     const int v = atoi(e);
     if (v >= 1 && v <= PD_PCR_MAX_SMALLK) pcr_max = v;
   }
+  // interface systems of up to this many rows go to the one-launch sequential kernel (pd_solve_iface_thomas_kernel);
+  // PD_ITHOMAS_MAX overrides (0 = never)
+  h->iface_thomas_max = h->slab_count > 1 ? 1024 : 256;
+  if (const char* e = getenv("PD_ITHOMAS_MAX")) h->iface_thomas_max = atoi(e);
   pl->rows[0] = h->m;
   int l = 0;
   while (true) {

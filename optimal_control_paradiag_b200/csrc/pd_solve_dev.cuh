@@ -284,13 +284,16 @@ __device__ __forceinline__ void passA_chunk(const cplx* __restrict__ wu, const c
   const int nrows = Lc + (c < P ? 1 : 0);  // chunk rows + the separator row that follows
   // Software pipeline over groups of PD_AG rows: the next group's loads are in flight while the current
   // group's recurrences run.  (Loading all 17 rows up front costs 254 registers = 2 CTAs per SM.)
+  // (loads are unconditional on a clamped row index -- a row past the chunk is re-read, never used: predicated or
+  // branched loads are not issued back to back and cost a third of the kernel's bandwidth)
+  const int rlast = nrows > 0 ? nrows - 1 : 0;
   cplx bu[2][PD_AG], bp[2][PD_AG];
 #pragma unroll
-  for (int r = 0; r < PD_AG; ++r)
-    if (r < nrows) {
-      bu[0][r] = ldw<LDCG>(wu + (int64_t)(j0 + r) * K);
-      bp[0][r] = ldw<LDCG>(wp + (int64_t)(j0 + r) * K);
-    }
+  for (int r = 0; r < PD_AG; ++r) {
+    const int64_t ro = (int64_t)(j0 + min(r, rlast)) * K;
+    bu[0][r] = ldw<LDCG>(wu + ro);
+    bp[0][r] = ldw<LDCG>(wp + ro);
+  }
   cplx dP = cmake(0, 0), dM = cmake(0, 0), fP = cmake(0, 0), fM = cmake(0, 0);
   cplx pi = cmake(1, 0), sP = cmake(0, 0), sM = cmake(0, 0);
 #pragma unroll 1
@@ -301,11 +304,9 @@ __device__ __forceinline__ void passA_chunk(const cplx* __restrict__ wu, const c
       // prefetch the following group into the other buffer
 #pragma unroll
       for (int r = 0; r < PD_AG; ++r) {
-        const int i = base + PD_AG + r;
-        if (i < nrows) {
-          bu[half ^ 1][r] = ldw<LDCG>(wu + (int64_t)(j0 + i) * K);
-          bp[half ^ 1][r] = ldw<LDCG>(wp + (int64_t)(j0 + i) * K);
-        }
+        const int64_t ro = (int64_t)(j0 + min(base + PD_AG + r, rlast)) * K;
+        bu[half ^ 1][r] = ldw<LDCG>(wu + ro);
+        bp[half ^ 1][r] = ldw<LDCG>(wp + ro);
       }
 #pragma unroll
       for (int r = 0; r < PD_AG; ++r) {
