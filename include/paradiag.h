@@ -94,10 +94,11 @@ int64_t pd_launch_count(const pd_handle* h);
 
 /* DiagFFTPC.apply (:491-553): y = P^-1 x, device pointers.  x and y may alias.  */
 int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
-/* Same with host buffers (PETSc Vec arrays, :493-497 / :552-553): H2D, apply, D2H, synchronises.  Pageable
- * buffers are page-locked once per (pointer, size) with cudaHostRegister and remembered (up to 16 buffers,
- * PD_HOST_REGISTER=0 disables), so that long-lived KSP work vectors travel at the full PCIe rate;
- * pd_host_unregister_all drops the registrations (call it before freeing such a buffer early).     */
+/* Same with host buffers (PETSc Vec arrays, :493-497 / :552-553): H2D, apply, D2H, synchronises.  With the
+ * option "host_register" (pd_set_option, or PD_HOST_REGISTER=1) pageable buffers are page-locked once per
+ * (pointer, size) with cudaHostRegister and remembered (up to 16 buffers), so that long-lived KSP work vectors
+ * travel at the full PCIe rate.  Opt-in: the caller must keep such buffers alive as long as the handle, or call
+ * pd_host_unregister_all before freeing them.                                                        */
 int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host);
 int pd_host_unregister_all(pd_handle* h);
 /* Real-input fast path.  The vectors GMRES feeds the PC in this (real) problem are real: x_dev and
@@ -220,7 +221,8 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
              int restart, int max_it, int* its, double* hist, int* reason,
              void* stream);
 
-/* Run-time options of a handle.  "gmres_residual_correction" (default 0): with 1, pd_gmres / pd_gmres_real form
+/* Run-time options of a handle.  "host_register" (default 0): see pd_pc_apply_host.
+ * "gmres_residual_correction" (default 0): with 1, pd_gmres / pd_gmres_real form
  * the preconditioned operator as  v + P^-1 ((A - P) v)  instead of  P^-1 (A v)  -- the same operator in exact
  * arithmetic (Krylov vectors have zero Dirichlet rows), but (A - P) v only touches the wrap-around time levels
  * and the half-weight rows (:117, :143, :93-110, :138), so the cancelling second differences of A v are never

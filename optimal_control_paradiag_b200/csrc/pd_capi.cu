@@ -641,12 +641,16 @@ extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {
   return PD_ERR_UNSUPPORTED;
 }
 
-// Host buffers handed to pd_pc_apply_host are page-locked ONCE per (pointer, size) with cudaHostRegister and
-// remembered: a PETSc Vec array is pageable, and a pageable cudaMemcpyAsync runs at about half the PCIe rate
-// (staged through the driver's bounce buffer).  KSP work vectors keep their arrays for the life of the solve, so
-// the registration cost (~0.2 s per GB, once) is paid on the first apply only.  Up to PD_HOSTREG_SLOTS buffers
-// are kept (oldest evicted); PD_HOST_REGISTER=0 turns the cache off.  Memory that is already page-locked
-// (cudaHostAlloc, torch pin_memory) is detected and left alone.
+// OPT-IN (pd_set_option "host_register" 1, or PD_HOST_REGISTER=1): host buffers handed to pd_pc_apply_host are
+// page-locked ONCE per (pointer, size) with cudaHostRegister and remembered.  A PETSc Vec array is pageable, and a
+// pageable cudaMemcpyAsync runs at about half the PCIe rate (staged through the driver's bounce buffer); KSP work
+// vectors keep their arrays for the life of the solve, so the registration cost (~0.3 s per GB, once) is paid on
+// the first apply only.  Up to PD_HOSTREG_SLOTS buffers are kept (oldest evicted).  Memory that is already
+// page-locked (cudaHostAlloc, torch pin_memory) is detected and left alone.
+// It is opt-in because the library does not own these buffers: if the caller frees one while it is registered and
+// the allocator hands the same address out again, the stale registration would be used for the new buffer.  The
+// host must either keep its vectors alive as long as the handle (KSP work vectors) or call
+// pd_host_unregister_all before freeing them.
 #define PD_HOSTREG_SLOTS 16
 struct HostReg {
   const void* ptr[PD_HOSTREG_SLOTS];
@@ -680,9 +684,9 @@ static void hostreg_pin(pd_handle* h, const void* p, size_t bytes) {
   HostReg* r = hostreg_of(h);
   if (r->enabled < 0) {
     const char* e = getenv("PD_HOST_REGISTER");
-    r->enabled = !(e && e[0] == '0');
+    r->enabled = (e && e[0] == '1') ? 1 : 0;
   }
-  if (!r->enabled) return;
+  if (!r->enabled && !h->opt_host_register) return;
   for (int i = 0; i < PD_HOSTREG_SLOTS; ++i)
     if (r->ptr[i] == p && r->bytes[i] >= bytes) return;
   cudaPointerAttributes at;

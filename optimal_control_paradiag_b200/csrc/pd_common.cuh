@@ -145,6 +145,7 @@ struct pd_handle {
   cplx* kry_d;      // (A - P) v of the residual-correction mode: zero except on <= 3 time levels per field
   int kry_d_mode;   // 0: not initialised, 1: complex layout, 2: float64 layout
   int opt_gmres_correction;  // pd_set_option "gmres_residual_correction"
+  int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;
   cudaStream_t own_stream;

@@ -469,16 +469,37 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
     for (int q0 = 0; q0 < P; q0 += PD_IT) {
       cplx nrP[PD_IT], nrM[PD_IT], nfP[PD_IT], nfM[PD_IT];
       load_fwd(q0 + PD_IT, nrP, nrM, nfP, nfM);
+      // the pivots of the batch in three phases, so that the four reciprocals (the long part: a double-precision
+      // division each) are independent instruction streams instead of links of one chain:
+      // (1) the V recurrence, the only truly sequential part
+      cplx Vp[PD_IT], Vn[PD_IT], m[PD_IT];
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        Vp[i] = pg.v.V;
+        Vn[i] = cmake(pg.v.V.x + pg.v.one + pg.v.e.x, pg.v.V.y + pg.v.e.y);  // V_q before any rescaling
+        pg.v.step();
+      }
+      // (2) m_q = -V_{q-1} / (off V_q)
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        m[i] = pg.v.diag ? pg.mdiag : cneg(cmul(cmul(Vp[i], pg.roff), crcp(Vn[i])));
+        if (q0 + i == P - 1) m[i] = last_row_pivot(m[i], s.glast);
+      }
+      // (3) the forward recurrence of both right-hand sides
+      cplx gP[PD_IT], gM[PD_IT];
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        gP[i] = cfms(below.off, fP[i], rP[i]);
+        gM[i] = cfms(below.off, fM[i], rM[i]);
+      }
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = q0 + i;
         if (q < P) {
-          cplx m = pg.next();
-          if (q == P - 1) m = last_row_pivot(m, s.glast);
-          dP = cmul(cfms(s.off, dP, cfms(below.off, fP[i], rP[i])), m);
-          dM = cmul(cfms(s.off, dM, cfms(below.off, fM[i], rM[i])), m);
+          dP = cmul(cfms(s.off, dP, gP[i]), m[i]);
+          dM = cmul(cfms(s.off, dM, gM[i]), m[i]);
           R[(q * 2) * K] = dP; R[(q * 2 + 1) * K] = dM;
-          F[((q + 1) * 2) * K] = m;
+          F[((q + 1) * 2) * K] = m[i];
         }
       }
 #pragma unroll

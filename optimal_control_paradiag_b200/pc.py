@@ -13,7 +13,8 @@ problem description (N_x, N_t, T, gamma) is looked up, in this order:
 1. a Firedrake ``appctx`` (``get_appctx(pc)``) with key ``"paradiag"`` (a dict) or the keys
    ``N_x, N_t, T, gamma`` directly, when Firedrake's ``PCBase`` is the base class;
 2. PC-local options under the prefix PETSc hands the PC (``pc.getOptionsPrefix()``):
-   ``<prefix>diagfft_nx``, ``..._nt``, ``..._T``, ``..._gamma``, ``..._device``, ``..._alpha``
+   ``<prefix>diagfft_nx``, ``..._nt``, ``..._T``, ``..._gamma``, ``..._device``, ``..._alpha``,
+   ``..._register_vecs`` (page-lock the host Vec arrays once; the Vecs must outlive the PC)
    (alpha != 1 is an extension with no upstream counterpart, see oracle/pc_alpha.py);
 3. ``DiagFFTPC.configure(...)`` class-level defaults;
 4. the globals ``N_x, N_t, T, gamma`` of ``__main__`` (how the upstream script itself is laid out).
@@ -102,7 +103,7 @@ class DiagFFTPC(PCBase):
     def configure(cls, **kw):
         """Class-level problem description (replaces the module globals :362-368)."""
         for k in kw:
-            if k not in _KEYS + ("device", "node_order", "bug138", "alpha"):
+            if k not in _KEYS + ("device", "node_order", "bug138", "alpha", "register_vecs"):
                 raise TypeError(f"unknown DiagFFTPC option {k!r}")
         cls._defaults = dict(cls._defaults, **kw)
 
@@ -120,6 +121,9 @@ class DiagFFTPC(PCBase):
         dev = _options_lookup(pc, "diagfft_device", int)
         if dev is not None:
             cfg["device"] = dev
+        rv = _options_lookup(pc, "diagfft_register_vecs", int)
+        if rv is not None:
+            cfg["register_vecs"] = bool(rv)
         al = _options_lookup(pc, "diagfft_alpha", float)
         if al is not None:
             cfg["alpha"] = al
@@ -128,7 +132,7 @@ class DiagFFTPC(PCBase):
         except Exception:
             ctx = {}
         sub = ctx.get("paradiag", {}) if hasattr(ctx, "get") else {}
-        for k in _KEYS + ("device", "node_order", "bug138", "alpha"):
+        for k in _KEYS + ("device", "node_order", "bug138", "alpha", "register_vecs"):
             if k in sub:
                 cfg[k] = sub[k]
             elif hasattr(ctx, "get") and k in ctx:
@@ -158,6 +162,10 @@ class DiagFFTPC(PCBase):
         self.alpha = float(cfg.get("alpha", 1.0))
         self.handle = ParaDiagHandle(self.N_x, self.N_t, T=self.T, gamma=self.gamma, alpha=self.alpha,
                                      bug138=cfg.get("bug138", True), device=int(cfg.get("device", 0)))
+        # page-lock the host Vec arrays once (KSP work vectors live as long as the solve): opt-in, see
+        # pd_pc_apply_host in include/paradiag.h
+        if cfg.get("register_vecs"):
+            self.handle.set_option("host_register", 1)
         self.initialized = True
 
     def update(self, pc):                                           # :487-488
