@@ -430,17 +430,37 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __r
 // last row is factorised by the same cancellation-free pivot generator as the chunk-local systems
 // (m_q = -V_{q-1} / (off V_q), PivotGen) and swept once forward, once backward, straight out of global memory:
 // every row access of a warp is one contiguous 512-byte segment, the loads of the next PD_IT rows are issued
-// before the dependent recurrences of the current ones.  F[0][q+1] is dead once row q's right-hand side has been
-// formed, so its first slot keeps the pivot m_q for the way back -- nothing extra is stored.
+// before the dependent recurrences of the current ones.
 // Replaces the reduce / PCR / back chain (3-7 short launches) wherever the interface is short enough for the
 // sequential latency (rows[1] <= PD_ITHOMAS_MAX): small N_x and, above all, the x-slabs of a multi-GPU run, where
 // that chain of launches was the part of the apply that did not shrink with the number of GPUs.
 // PUSH (slab mode): the thread ends with the first and last interface values in registers, forms the slab
 // functionals and stores them into every rank's exchange buffer (no separate launch).
 #define PD_IT 4
+// The interface pivots m_q(k) depend on (k, q) only.  Generating them inside the sweep costs one double-precision
+// division per row on the critical path of a kernel that runs ONE warp per scheduler (measured 0.46 us per row);
+// the plan therefore factorises the interface once (this kernel) and keeps the pivots, [rows[1]][K] complex,
+// 3 % of a vector -- the per-frequency coefficients of the big level-0 systems are still regenerated in-kernel.
+__global__ void __launch_bounds__(PD_KB)
+pd_iface_pivots_kernel(SolveParams sp, cplx* __restrict__ piv) {
+  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.K) return;
+  const KCoef kc = make_coef(freq_of(sp, kk), sp);
+  const Sys s = reduce_sys(level_sys(kc, sp, 0), PD_L);
+  const int P = sp.rows[1];
+  PivotGen pg;
+  pg.init(s);
+  for (int q = 0; q < P; ++q) {
+    cplx m = pg.next();
+    if (q == P - 1) m = last_row_pivot(m, s.glast);
+    piv[(int64_t)q * sp.K + kk] = m;
+  }
+}
+
 template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
-pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ w, SlabPtrs sl, SlabCommDev cm) {
+pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
+                             SlabPtrs sl, SlabCommDev cm) {
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
   if (kk < sp.kend) {
@@ -450,42 +470,25 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
     const int64_t K = sp.K;
     const int P = sp.rows[1];
     cplx* R = lv.R[1] + kk;
-    cplx* F = lv.F[0] + kk;
-    PivotGen pg;
-    pg.init(s);
+    const cplx* F = lv.F[0] + kk;
+    const cplx* M = piv + kk;
     cplx dP = cmake(0, 0), dM = cmake(0, 0);
-    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q ; m_q parked in F[q+1].  Double-buffered batches of PD_IT rows:
-    // the loads of batch b+1 are in flight while the dependent recurrences of batch b run.
-    cplx rP[PD_IT], rM[PD_IT], fP[PD_IT], fM[PD_IT];
-    auto load_fwd = [&](int q0, cplx* aP, cplx* aM, cplx* bP, cplx* bM) {
+    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q.  Double-buffered batches of PD_IT rows: the loads of batch
+    // b+1 are in flight while the dependent recurrences of batch b run.
+    cplx rP[PD_IT], rM[PD_IT], fP[PD_IT], fM[PD_IT], mq[PD_IT];
+    auto load_fwd = [&](int q0, cplx* aP, cplx* aM, cplx* bP, cplx* bM, cplx* am) {
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = min(q0 + i, P - 1);
         aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
         bP[i] = F[((q + 1) * 2) * K]; bM[i] = F[((q + 1) * 2 + 1) * K];
+        am[i] = M[q * K];
       }
     };
-    load_fwd(0, rP, rM, fP, fM);
+    load_fwd(0, rP, rM, fP, fM, mq);
     for (int q0 = 0; q0 < P; q0 += PD_IT) {
-      cplx nrP[PD_IT], nrM[PD_IT], nfP[PD_IT], nfM[PD_IT];
-      load_fwd(q0 + PD_IT, nrP, nrM, nfP, nfM);
-      // the pivots of the batch in three phases, so that the four reciprocals (the long part: a double-precision
-      // division each) are independent instruction streams instead of links of one chain:
-      // (1) the V recurrence, the only truly sequential part
-      cplx Vp[PD_IT], Vn[PD_IT], m[PD_IT];
-#pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        Vp[i] = pg.v.V;
-        Vn[i] = cmake(pg.v.V.x + pg.v.one + pg.v.e.x, pg.v.V.y + pg.v.e.y);  // V_q before any rescaling
-        pg.v.step();
-      }
-      // (2) m_q = -V_{q-1} / (off V_q)
-#pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        m[i] = pg.v.diag ? pg.mdiag : cneg(cmul(cmul(Vp[i], pg.roff), crcp(Vn[i])));
-        if (q0 + i == P - 1) m[i] = last_row_pivot(m[i], s.glast);
-      }
-      // (3) the forward recurrence of both right-hand sides
+      cplx nrP[PD_IT], nrM[PD_IT], nfP[PD_IT], nfM[PD_IT], nmq[PD_IT];
+      load_fwd(q0 + PD_IT, nrP, nrM, nfP, nfM, nmq);
       cplx gP[PD_IT], gM[PD_IT];
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
@@ -496,14 +499,15 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = q0 + i;
         if (q < P) {
-          dP = cmul(cfms(s.off, dP, gP[i]), m[i]);
-          dM = cmul(cfms(s.off, dM, gM[i]), m[i]);
+          dP = cmul(cfms(s.off, dP, gP[i]), mq[i]);
+          dM = cmul(cfms(s.off, dM, gM[i]), mq[i]);
           R[(q * 2) * K] = dP; R[(q * 2 + 1) * K] = dM;
-          F[((q + 1) * 2) * K] = m[i];
         }
       }
 #pragma unroll
-      for (int i = 0; i < PD_IT; ++i) { rP[i] = nrP[i]; rM[i] = nrM[i]; fP[i] = nfP[i]; fM[i] = nfM[i]; }
+      for (int i = 0; i < PD_IT; ++i) {
+        rP[i] = nrP[i]; rM[i] = nrM[i]; fP[i] = nfP[i]; fM[i] = nfM[i]; mq[i] = nmq[i];
+      }
     }
     // ---- backward: z_q = d_q - off m_q z_{q+1}
     const cplx zeP = dP, zeM = dM;
@@ -514,7 +518,7 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = max(q0 - i, 0);
         aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
-        am[i] = F[((q + 1) * 2) * K];
+        am[i] = M[q * K];
       }
     };
     load_bwd(P - 2, eP, eM, mm);
@@ -827,6 +831,7 @@ struct SolvePlan {
   cplx* green_h;     // the same two plan-time tables for the half spectrum of the real-input path
   cplx* slabcoef_h;  //   (columns 0 .. N_t/2 in natural order, row stride Kp)
   SlabGeom sg;
+  cplx* ipiv[2];     // interface pivots [rows[1]][K] for the full ([0]) and the half spectrum ([1]); null: multi-level
   // peer-store exchange (pd_slab_comm_*): null / 0 until created
   void* comm_base;                    // this rank's symmetric buffer (gathered + flags), one allocation
   size_t comm_bytes;
@@ -848,6 +853,8 @@ void pd_solve_free(pd_handle* h) {
     if (pl->R[l]) cudaFree(pl->R[l]);
     if (pl->F[l]) cudaFree(pl->F[l]);
   }
+  if (pl->ipiv[0]) cudaFree(pl->ipiv[0]);
+  if (pl->ipiv[1]) cudaFree(pl->ipiv[1]);
   if (pl->green_h) cudaFree(pl->green_h);
   if (pl->slabcoef_h) cudaFree(pl->slabcoef_h);
   if (pl->lastl) cudaFree(pl->lastl);
@@ -915,17 +922,18 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
                          const PushCtx* push = nullptr, bool* pushed = nullptr) {
   const int top = sp.nlev;
   const int ncol = sp.kend - sp.koff;
-  if (h->iface_thomas_max > 0 && sp.rows[1] <= h->iface_thomas_max && sp.koff == 0) {
+  const cplx* piv = plan_of(h)->ipiv[sp.K == h->kcount ? 0 : 1];
+  if (piv && sp.koff == 0 && sp.kend == sp.K) {
     const int nblk = (ncol + PD_KB - 1) / PD_KB;
     if (push) {
-      pd_solve_iface_thomas_kernel<true><<<nblk, PD_KB, 0, st>>>(lv, sp, push->w, push->sl, push->cm);
+      pd_solve_iface_thomas_kernel<true><<<nblk, PD_KB, 0, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
       if (pushed) *pushed = true;
     } else {
       SlabPtrs nosl;
       SlabCommDev nocm;
       memset(&nosl, 0, sizeof(nosl));
       memset(&nocm, 0, sizeof(nocm));
-      pd_solve_iface_thomas_kernel<false><<<nblk, PD_KB, 0, st>>>(lv, sp, nullptr, nosl, nocm);
+      pd_solve_iface_thomas_kernel<false><<<nblk, PD_KB, 0, st>>>(lv, sp, piv, nullptr, nosl, nocm);
     }
     PD_CHECK_LAUNCH();
     h->launches++;
@@ -985,8 +993,9 @@ int pd_solve_plan(pd_handle* h) {
   }
   // interface systems of up to this many rows go to the one-launch sequential kernel (pd_solve_iface_thomas_kernel);
   // PD_ITHOMAS_MAX overrides (0 = never)
-  h->iface_thomas_max = h->slab_count > 1 ? 1024 : 256;
+  h->iface_thomas_max = 8192;
   if (const char* e = getenv("PD_ITHOMAS_MAX")) h->iface_thomas_max = atoi(e);
+  if (h->kcount != h->cfg.N_t) h->iface_thomas_max = 0;  // frequency-sharded handles keep the multi-level path
   pl->rows[0] = h->m;
   int l = 0;
   while (true) {
@@ -1013,6 +1022,20 @@ int pd_solve_plan(pd_handle* h) {
       size_t bytes = sizeof(cplx) * (size_t)(pl->rows[lev + 1] + 1) * 2 * K;
       PD_CUDA(cudaMalloc(&pl->F[lev], bytes));
       h->ws_bytes += bytes;
+    }
+  }
+  // one-launch sequential interface (pd_solve_iface_thomas_kernel): factorise the level-1 system once
+  if (pl->nlev >= 1 && h->iface_thomas_max > 0 && pl->rows[1] <= h->iface_thomas_max) {
+    const bool want_half = pd_rfft_supported(h) && h->cfg.alpha == 1.0;
+    for (int half = 0; half <= (want_half ? 1 : 0); ++half) {
+      SolveParams sp; Levels lv; SlabPtrs sl;
+      fill_params(h, sp, lv, sl, half);
+      if (half == 1 && sp.K == (int)K) break;  // (cannot tell the two apart by width: keep the multi-level path)
+      const size_t bytes = sizeof(cplx) * (size_t)pl->rows[1] * (size_t)sp.K;
+      PD_CUDA(cudaMalloc(&pl->ipiv[half], bytes));
+      h->ws_bytes += bytes;
+      pd_iface_pivots_kernel<<<(sp.K + PD_KB - 1) / PD_KB, PD_KB>>>(sp, pl->ipiv[half]);
+      PD_CHECK_LAUNCH();
     }
   }
   if (h->slab_count > 1) {

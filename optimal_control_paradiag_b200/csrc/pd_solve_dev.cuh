@@ -286,7 +286,8 @@ __device__ __forceinline__ void passA_chunk(const cplx* __restrict__ wu, const c
   // group's recurrences run.  (Loading all 17 rows up front costs 254 registers = 2 CTAs per SM.)
   // (loads are unconditional on a clamped row index -- a row past the chunk is re-read, never used: predicated or
   // branched loads are not issued back to back and cost a third of the kernel's bandwidth)
-  const int rlast = nrows > 0 ? nrows - 1 : 0;
+  // (an empty last chunk of an x-slab that does not end with the Dirichlet row has NO row j0: stay inside the array)
+  const int rlast = min(nrows > 0 ? nrows - 1 : 0, sp.n - 1 - j0);
   cplx bu[2][PD_AG], bp[2][PD_AG];
 #pragma unroll
   for (int r = 0; r < PD_AG; ++r) {
