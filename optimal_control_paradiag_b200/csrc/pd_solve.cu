@@ -563,28 +563,13 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
   cplx* wp = w + sp.plane + kc_idx;
   const cplx zero = cmake(0, 0);
   const int P = sp.rows[1], Llast = sp.m - P * (PD_L + 1);
-  // slab mode: outer separator values and the coefficients with which they enter the first / last
-  // interface row: -off_1 z_left = -(a / V_L) z_left and -(a / V_Llast) z_right (-a z_right if Llast = 0)
-  cplx oLP = zero, oLM = zero, oRP = zero, oRM = zero, cLP = zero, cLM = zero, cRP = zero, cRM = zero;
+  // slab mode: the outer separator values (left / right neighbour slab).  Their effect on the INTERIOR separators
+  // of this slab has already been folded into zsep by pd_slab_global_kernel (interface Green's vectors), so the
+  // chunk loop below is the single-GPU one.
+  cplx oLP = zero, oLM = zero, oRP = zero, oRM = zero;
   if (SLAB) {
     oLP = sl.zout[kc_idx]; oLM = sl.zout[sp.K + kc_idx];
     oRP = sl.zout[2 * (int64_t)sp.K + kc_idx]; oRM = sl.zout[3 * (int64_t)sp.K + kc_idx];
-    if (P > 0) {
-      VRec v;
-      v.init(kc.a, kc.sh, zero);
-      cplx gl = zero, gr = kc.a;  // a / V_L and a / V_Llast (V_0 = 1)
-      if (!v.diag) {
-        for (int i = 1; i <= PD_L; ++i) {
-          v.step();
-          if (i == Llast) gr = cmul(kc.a, cscale(crcp(v.V), v.one));
-        }
-        gl = cmul(kc.a, cscale(crcp(v.V), v.one));
-      } else if (Llast > 0) {
-        gr = zero;
-      }
-      cLP = cneg(cmul(gl, oLP)); cLM = cneg(cmul(gl, oLM));
-      cRP = cneg(cmul(gr, oRP)); cRM = cneg(cmul(gr, oRM));
-    }
   }
   for (int c = sp.c0 + blockIdx.y; c < sp.c1; c += gridDim.y) {
     const int Lc = c < P ? PD_L : Llast;
@@ -602,21 +587,11 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       const int64_t o = ((int64_t)(c - 1) * 2) * sp.K + kc_idx;
       zlP = zsep[o];
       zlM = zsep[o + sp.K];
-      if (SLAB) {
-        const cplx g0 = sl.green[o], g1 = sl.green[o + sp.K];
-        zlP = cfma(cLP, g0, cfma(cRP, g1, zlP));
-        zlM = cfma(cLM, g0, cfma(cRM, g1, zlM));
-      }
     }
     if (c < P) {
       const int64_t o = ((int64_t)c * 2) * sp.K + kc_idx;
       zrP = zsep[o];
       zrM = zsep[o + sp.K];
-      if (SLAB) {
-        const cplx g0 = sl.green[o], g1 = sl.green[o + sp.K];
-        zrP = cfma(cLP, g0, cfma(cRP, g1, zrP));
-        zrM = cfma(cLM, g0, cfma(cRM, g1, zrM));
-      }
     }
     // forward elimination (in place: d_i overwrites rho_i)
     cplx pP = zlP, pM = zlM;  // "d_{-1}" = known left neighbour value
@@ -747,10 +722,15 @@ pd_slab_coef_kernel(SolveParams sp, SlabGeom sg, cplx* __restrict__ coef) {
 }
 
 // gathered[G][6][K] -> zout[4][K] (left+, left-, right+, right-) of this rank
+// grid (frequency blocks, y): every CTA solves the tiny separator system of its frequencies (redundantly in y),
+// y = 0 stores the outer separator values zout, and all CTAs together add their effect on this slab's INTERIOR
+// separators, zsep[c] += cL g0[c] + cR g1[c] (g0, g1: interface Green's vectors of the plan; cL/cR = -(a / V_L) z_left,
+// -(a / V_Llast) z_right), so that pass B needs no slab-specific arithmetic in its chunk loop.
 template <bool WAIT>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveParams sp, SlabGeom sg,
-                      const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm) {
+                      const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm,
+                      cplx* __restrict__ zsep, const cplx* __restrict__ green) {
   if (WAIT) {
     // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
     const unsigned long long ep = *cm.epoch + 1ull;
@@ -805,7 +785,33 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
     if (r == sg.rank) { leftP = zP; leftM = zM; }
     if (r == sg.rank + 1) { rightP = zP; rightM = zM; }
   }
-  zout[kk] = leftP; zout[K + kk] = leftM; zout[2 * K + kk] = rightP; zout[3 * K + kk] = rightM;
+  if (blockIdx.y == 0) {
+    zout[kk] = leftP; zout[K + kk] = leftM; zout[2 * K + kk] = rightP; zout[3 * K + kk] = rightM;
+  }
+  const int P = sp.rows[1];
+  if (P > 0 && zsep) {
+    const int Llast = sp.m - P * (PD_L + 1);
+    VRec v;
+    v.init(kc.a, kc.sh, cmake(0, 0));
+    cplx gl = cmake(0, 0), gr = kc.a;  // a / V_L and a / V_Llast (V_0 = 1)
+    if (!v.diag) {
+      for (int i = 1; i <= PD_L; ++i) {
+        v.step();
+        if (i == Llast) gr = cmul(kc.a, cscale(crcp(v.V), v.one));
+      }
+      gl = cmul(kc.a, cscale(crcp(v.V), v.one));
+    } else if (Llast > 0) {
+      gr = cmake(0, 0);
+    }
+    const cplx cLP = cneg(cmul(gl, leftP)), cLM = cneg(cmul(gl, leftM));
+    const cplx cRP = cneg(cmul(gr, rightP)), cRM = cneg(cmul(gr, rightM));
+    for (int c = blockIdx.y; c < P; c += gridDim.y) {
+      const int64_t o = ((int64_t)c * 2) * K + kk;
+      const cplx g0 = green[o], g1 = green[o + K];
+      zsep[o] = cfma(cLP, g0, cfma(cRP, g1, zsep[o]));
+      zsep[o + K] = cfma(cLM, g0, cfma(cRM, g1, zsep[o + K]));
+    }
+  }
 }
 
 // R1 <- e_0 in slot 0, e_{P-1} in slot 1 (right-hand sides of the two interface Green's vectors)
@@ -1354,17 +1360,24 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
   const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
   const cplx* coef = half_spectrum ? pl->slabcoef_h : pl->slabcoef;
+  // enough CTAs in y for the correction sweep over the interior separators (rows[1] x 2 x K values)
+  int gy = sp.rows[1] / 8;
+  if (gy < 1) gy = 1;
+  if (gy > 16) gy = 16;
+  const dim3 ggrid(kblocks, gy);
+  cplx* zsep = sp.nlev >= 1 ? lv.R[1] : nullptr;
   if (gathered) {
     SlabCommDev none;
     memset(&none, 0, sizeof(none));
-    pd_slab_global_kernel<false><<<kblocks, PD_KB, 0, st>>>(gathered, (int64_t)sp.K, sp, pl->sg, coef, pl->zout, none);
+    pd_slab_global_kernel<false><<<ggrid, PD_KB, 0, st>>>(gathered, (int64_t)sp.K, sp, pl->sg, coef, pl->zout, none,
+                                                          zsep, sl.green);
   } else {
     if (!pl->comm_connected) {
       pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
       return PD_ERR_INVALID;
     }
-    pd_slab_global_kernel<true><<<kblocks, PD_KB, 0, st>>>(nullptr, pl->comm_kmax, sp, pl->sg, coef, pl->zout,
-                                                          comm_dev_of(h));
+    pd_slab_global_kernel<true><<<ggrid, PD_KB, 0, st>>>(nullptr, pl->comm_kmax, sp, pl->sg, coef, pl->zout,
+                                                        comm_dev_of(h), zsep, sl.green);
     sl.epoch_bump = pl->comm_epoch;
   }
   PD_CHECK_LAUNCH();

@@ -68,6 +68,7 @@ class _ShimPCBase:
 PCBase = _FiredrakePCBase if _FiredrakePCBase is not None else _ShimPCBase
 
 _KEYS = ("N_x", "N_t", "T", "gamma")
+_EXTRA = ("device", "node_order", "bug138", "alpha", "register_vecs", "distributed", "backend_factory", "group")
 _OPT_NAMES = {"N_x": "diagfft_nx", "N_t": "diagfft_nt", "T": "diagfft_T", "gamma": "diagfft_gamma"}
 
 
@@ -103,7 +104,7 @@ class DiagFFTPC(PCBase):
     def configure(cls, **kw):
         """Class-level problem description (replaces the module globals :362-368)."""
         for k in kw:
-            if k not in _KEYS + ("device", "node_order", "bug138", "alpha", "register_vecs"):
+            if k not in _KEYS + _EXTRA:
                 raise TypeError(f"unknown DiagFFTPC option {k!r}")
         cls._defaults = dict(cls._defaults, **kw)
 
@@ -121,6 +122,9 @@ class DiagFFTPC(PCBase):
         dev = _options_lookup(pc, "diagfft_device", int)
         if dev is not None:
             cfg["device"] = dev
+        ds = _options_lookup(pc, "diagfft_distributed", int)
+        if ds is not None:
+            cfg["distributed"] = bool(ds)
         rv = _options_lookup(pc, "diagfft_register_vecs", int)
         if rv is not None:
             cfg["register_vecs"] = bool(rv)
@@ -132,7 +136,7 @@ class DiagFFTPC(PCBase):
         except Exception:
             ctx = {}
         sub = ctx.get("paradiag", {}) if hasattr(ctx, "get") else {}
-        for k in _KEYS + ("device", "node_order", "bug138", "alpha", "register_vecs"):
+        for k in _KEYS + _EXTRA:
             if k in sub:
                 cfg[k] = sub[k]
             elif hasattr(ctx, "get") and k in ctx:
@@ -160,6 +164,21 @@ class DiagFFTPC(PCBase):
             self._inv_order = np.argsort(self.node_order)
         # alpha: extension (the upstream PC is the alpha = 1 block circulant); 1.0 unless asked for
         self.alpha = float(cfg.get("alpha", 1.0))
+        # A PC on a parallel communicator (the mode the vec_wo / vec_ro comments at :493, :552 anticipate: a
+        # spatial decomposition, every rank holding the node slab [u-block ; p-block] of its nodes): the x-slab
+        # distributed backend.  Chosen when asked for (appctx / <prefix>diagfft_distributed / configure), or when
+        # the PC's communicator and torch.distributed agree on a size > 1.
+        self.dpc = None
+        if self._want_distributed(pc, cfg):
+            from .dist import DistributedDiagFFTPC
+            if self.alpha != 1.0 or self.node_order is not None:
+                raise NotImplementedError("the distributed backend supports alpha = 1 and monotone node order")
+            self.dpc = DistributedDiagFFTPC(self.N_x, self.N_t, T=self.T, gamma=self.gamma,
+                                            device=int(cfg.get("device", 0)), group=cfg.get("group"),
+                                            backend_factory=cfg.get("backend_factory"), mode="slab")
+            self.handle = self.dpc.backend
+            self.initialized = True
+            return
         self.handle = ParaDiagHandle(self.N_x, self.N_t, T=self.T, gamma=self.gamma, alpha=self.alpha,
                                      bug138=cfg.get("bug138", True), device=int(cfg.get("device", 0)))
         # page-lock the host Vec arrays once (KSP work vectors live as long as the solve): opt-in, see
@@ -168,13 +187,51 @@ class DiagFFTPC(PCBase):
             self.handle.set_option("host_register", 1)
         self.initialized = True
 
+    @staticmethod
+    def _want_distributed(pc, cfg):
+        if cfg.get("distributed") is not None:
+            return bool(cfg["distributed"])
+        try:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                return False
+            size = pc.getComm().getSize()
+            return size > 1 and size == dist.get_world_size(cfg.get("group"))
+        except Exception:
+            return False
+
     def update(self, pc):                                           # :487-488
         pass
+
+    def _apply_distributed(self, x, y):
+        """This rank's node-slab block (2, n_r, N_t): device tensors zero-copy, host Vecs through pinned staging."""
+        import torch
+        d = self.dpc
+        if isinstance(x, torch.Tensor) and (x.is_cuda or d.device.type == "cpu"):
+            if x.dtype == torch.float64 and d.device.type == "cuda" and getattr(d.backend, "real_path_supported", False):
+                d.apply_real(x.reshape(-1), y.reshape(-1))
+            else:
+                d.apply(x.reshape(-1), y.reshape(-1))
+            return
+        xa = _host_array(x, readonly=True)
+        ya = _host_array(y, readonly=False)
+        if xa.size != d.local_size or ya.size != d.local_size:
+            raise ValueError(f"DiagFFTPC.apply: local Vec size {xa.size} != 2 * n_r * N_t = {d.local_size} "
+                             f"(rank {d.rank} owns {d.n_r} of the {d.n} nodes)")
+        if ya.dtype == np.complex128 and ya.flags.c_contiguous:
+            d.apply_host(np.ascontiguousarray(xa), ya)
+        else:
+            tmp = np.empty(d.local_size, dtype=np.complex128)
+            d.apply_host(np.ascontiguousarray(xa, dtype=np.complex128), tmp)
+            ya[...] = tmp.astype(ya.dtype, copy=False)
+        _restore(y, ya)
 
     def apply(self, pc, x, y):
         """Control_Wave_PC.py:491-553: y = P^-1 x."""
         if not getattr(self, "initialized", False) or not hasattr(self, "handle"):
             self.initialize(pc)
+        if self.dpc is not None:
+            return self._apply_distributed(x, y)
         try:
             import torch
             is_dev = isinstance(x, torch.Tensor) and x.is_cuda
@@ -214,7 +271,7 @@ class DiagFFTPC(PCBase):
         raise NotImplementedError
 
     def destroy(self, pc):
-        if hasattr(self, "handle"):
+        if hasattr(self, "handle") and hasattr(self.handle, "close"):
             self.handle.close()
 
 

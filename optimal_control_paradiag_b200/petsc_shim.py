@@ -47,6 +47,19 @@ class Vec:
         return float(np.linalg.norm(self._a))
 
 
+class Comm:
+    """Stand-in for a petsc4py communicator: ``getSize`` / ``getRank``."""
+
+    def __init__(self, size=1, rank=0):
+        self._size, self._rank = int(size), int(rank)
+
+    def getSize(self):
+        return self._size
+
+    def getRank(self):
+        return self._rank
+
+
 class Options:
     def __init__(self, entries=None):
         self._d = {}
@@ -75,8 +88,9 @@ class Options:
 class PC:
     """Just enough of ``PETSc.PC`` to drive a python-type preconditioner."""
 
-    def __init__(self, prefix="", options=None):
+    def __init__(self, prefix="", options=None, comm=None):
         self._prefix = prefix
+        self._comm = comm if comm is not None else Comm()
         self.options = options if options is not None else Options()
         self._ctx = None
         self._type = None
@@ -84,6 +98,9 @@ class PC:
 
     def getOptionsPrefix(self):
         return self._prefix
+
+    def getComm(self):
+        return self._comm
 
     def setOptionsPrefix(self, p):
         self._prefix = p

@@ -5,8 +5,9 @@ manufactured problem, the all-at-once operator and the GMRES solve that calls th
 Same constructor and method names as upstream (``Build_f``, ``Build_g``,
 ``Build_Initial_Condition``, ``Build_L``, ``solve(parameters, complex)``); the Firedrake
 forms are replaced by the device kernels of libparadiag (``pd_build_rhs``, ``pd_matvec``,
-``pd_gmres``).  ``write()`` (VTK output, :247-333) is out of scope; ``error_norm`` gives
-the analytic-solution check it contains (:299-300, :324-333).
+``pd_gmres``).  ``solve(parameters=None)`` is the direct-LU baseline of the ``pc=False`` branch (:186, :573-577).
+``write()`` (VTK output, :247-333) is out of scope; ``error_norm`` gives the analytic-solution check it contains
+(:299-300, :324-333).
 """
 import math
 import time
@@ -87,9 +88,11 @@ class Optimal_Control_Wave_Equation:
         params = _flatten(parameters if parameters else
                           {'ksp_type': 'preonly', 'pc_type': 'lu', 'mat_type': 'aij',
                            'pc_factor_mat_solver_type': 'mumps'})                      # :186
+        if params.get('ksp_type') == 'preonly' and params.get('pc_type') == 'lu':
+            return self._direct_solve(verbose)                                         # pc=False branch, :573-577
         if params.get('ksp_type') != 'gmres' or params.get('pc_type') != 'python':
-            raise NotImplementedError("only the GMRES + python-PC configuration of :347-359 is "
-                                      "accelerated; the direct MUMPS baseline (:186) is out of scope")
+            raise NotImplementedError("supported solver configurations: GMRES + python PC (:347-359) and the "
+                                      "direct LU baseline preonly + lu (:186)")
         if not str(params.get('pc_python_type', '')).endswith('DiagFFTPC'):
             raise ValueError(f"unknown pc_python_type {params.get('pc_python_type')!r}")
         self.Build_f()
@@ -124,6 +127,44 @@ class Optimal_Control_Wave_Equation:
         self.U = x
         X = x.view(2, self.n, self.N)
         return X[0], X[1]                                                                    # :200, :244
+
+    DIRECT_MAX_UNKNOWNS = 16384
+
+    def _direct_solve(self, verbose=True):
+        """The reference's ``pc=False`` baseline (:186, :573-577: ``ksp_type preonly``, ``pc_type lu``, MUMPS): a direct
+        LU solve of the all-at-once system, for end-to-end validation of the GMRES + PC solve at the small sizes the
+        upstream accuracy study uses (N_x = N_t = 5 ... 70, plot.py:5-18).  The matrix is assembled on the device
+        column by column from the matrix-free operator (``pd_matvec_real``: the problem is real) and factorised by
+        cuSOLVER through ``torch.linalg.solve`` -- a library LU standing in for MUMPS; it is a validation baseline,
+        not a hot path (dense: limited to DIRECT_MAX_UNKNOWNS unknowns).  Upstream assembles the UNSCALED formulation
+        for this branch (:124-133); the scaled system solved here has the same solution after the sqrt(gamma)
+        unscaling that ``error_norm`` applies."""
+        import torch
+        h = self.handle
+        sz = h.size
+        if sz > self.DIRECT_MAX_UNKNOWNS:
+            raise NotImplementedError(f"the dense direct-LU baseline is limited to {self.DIRECT_MAX_UNKNOWNS} unknowns "
+                                      f"(got {sz}); use the GMRES + DiagFFTPC parameters of :347-359")
+        dev = f"cuda:{h.device}"
+        solver_setted = time.time()
+        b = h.build_rhs_real()
+        A = torch.empty((sz, sz), dtype=torch.float64, device=dev)         # row-major; filled column by column
+        e = torch.zeros(sz, dtype=torch.float64, device=dev)
+        col = torch.empty(sz, dtype=torch.float64, device=dev)
+        for j in range(sz):
+            e[j] = 1.0
+            h.matvec_real(e, col)
+            A[:, j] = col
+            e[j] = 0.0
+        x = torch.linalg.solve(A, b)
+        torch.cuda.synchronize(h.device)
+        solver_solved = time.time()
+        self.ksp_its, self.ksp_reason, self.ksp_history = 1, "CONVERGED_ITS", []
+        if verbose:
+            print("The CPU time for solving the problem", solver_solved - solver_setted)    # :199
+        self.U = x.to(torch.complex128)
+        X = self.U.view(2, self.n, self.N)
+        return X[0], X[1]
 
     def error_norm(self, u_sol):
         """max over time levels of the nodal 2-norm error of u against the analytic state

@@ -300,3 +300,55 @@ def test_slab_bounds():
     assert c == [4, 3, 3] and o == [0, 4, 7, 10]
     c, o = slab_bounds(4096, 8)
     assert c == [512] * 8 and o[-1] == 4096
+
+
+# ----------------------------------------------------- DiagFFTPC itself on a parallel communicator
+def _pc_worker(rank, world, port, N_x, N_t, gamma, ret, how):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from optimal_control_paradiag_b200 import DiagFFTPC, petsc_shim
+        from oracle.pc_fast import DiagFFTPCFast
+        factory = lambda **kw: OracleStageBackend(N_x, N_t, 2.0, gamma, **kw)
+        opts = petsc_shim.Options()
+        if how == "option":          # <prefix>diagfft_distributed, like any other PC-local option
+            opts["fd_diagfft_distributed"] = 1
+            DiagFFTPC.configure(N_x=N_x, N_t=N_t, T=2.0, gamma=gamma, backend_factory=factory)
+            pc = petsc_shim.PC(prefix="fd_", options=opts)
+        else:                        # auto: the PC's communicator and torch.distributed agree on a size > 1
+            DiagFFTPC.configure(N_x=N_x, N_t=N_t, T=2.0, gamma=gamma, backend_factory=factory)
+            pc = petsc_shim.PC(comm=petsc_shim.Comm(world, rank))
+        pc.setPythonType("optimal_control_paradiag_b200.DiagFFTPC")
+        pc.setUp()
+        ctx = pc.getPythonContext()
+        assert ctx.dpc is not None and ctx.dpc.world == world and ctx.dpc.mode == "slab"
+        rng = np.random.default_rng(0)
+        size = 2 * (N_x + 1) * N_t
+        xg = rng.standard_normal(size) + 1j * rng.standard_normal(size)
+        j0, j1 = ctx.dpc.noff[rank], ctx.dpc.noff[rank + 1]
+        xl = np.ascontiguousarray(xg.reshape(2, N_x + 1, N_t)[:, j0:j1, :]).reshape(-1)   # this rank's local Vec
+        xv, yv = petsc_shim.Vec(xl), petsc_shim.Vec.zeros(xl.size)
+        pc.apply(xv, yv)                                                                   # the reference's call
+        ref = DiagFFTPCFast(N_x, N_t, 2.0, gamma).apply(xg).reshape(2, N_x + 1, N_t)[:, j0:j1, :].reshape(-1)
+        err = float(np.linalg.norm(yv.getArray() - ref) / np.linalg.norm(ref))
+        # a Vec of the wrong (global) size is an error, as a PETSc size mismatch would be
+        bad = False
+        try:
+            pc.apply(petsc_shim.Vec(xg), petsc_shim.Vec.zeros(size))
+        except ValueError:
+            bad = True
+        ret[rank] = (err, bad)
+        DiagFFTPC._defaults = {}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("how", ["option", "comm"])
+def test_diagfftpc_selects_the_distributed_backend_on_a_parallel_communicator(how):
+    world, N_x, N_t = 2, 21, 12
+    ret = mp.Manager().dict()
+    mp.spawn(_pc_worker, args=(world, _free_port(), N_x, N_t, 0.5, ret, how), nprocs=world, join=True)
+    for r in range(world):
+        err, bad = ret[r]
+        assert err < 1e-11 and bad, ret[r]

@@ -390,7 +390,24 @@ def test_problem_class_reproduces_the_reference_run():
     assert tuple(u_sol.shape) == (81, 81)
     assert equ.error_norm(u_sol) < 0.1
     with pytest.raises(NotImplementedError):
-        equ.solve(parameters=None, complex=True)
+        equ.solve(parameters={'ksp_type': 'cg', 'pc_type': 'jacobi'}, complex=True)
+
+
+@pytest.mark.parametrize("N,gamma", [(10, 1.0), (24, 1.0), (30, 1e-2), (40, 1.0)])
+def test_direct_lu_baseline_equals_gmres_with_the_pc(N, gamma):
+    # the pc=False branch of the upstream script (:186, :573-577) on the product path, against GMRES + DiagFFTPC
+    from optimal_control_paradiag_b200 import Optimal_Control_Wave_Equation, default_parameters
+    equ = Optimal_Control_Wave_Equation(N, 2, N, gamma)
+    u_d, p_d = equ.solve(parameters=None, complex=True, verbose=False)
+    u_d, p_d = u_d.clone(), p_d.clone()
+    u_g, p_g = equ.solve(parameters=default_parameters, complex=True, verbose=False, rtol=1e-13)
+    assert equ.ksp_reason.startswith("CONVERGED")
+    err = float(torch.linalg.norm(torch.cat([u_d - u_g, p_d - p_g])) / torch.linalg.norm(torch.cat([u_g, p_g])))
+    assert err < 1e-9, err
+    # and against the oracle's SuperLU restatement of the same branch
+    direct = AllAtOnce(N, N, 2.0, gamma).direct_solve().reshape(2, N + 1, N)
+    assert rel(u_d.cpu().numpy().real, direct[0]) < 1e-9
+    equ.handle.close()
 
 
 def test_errors_are_status_codes_not_aborts():
