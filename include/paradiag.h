@@ -222,6 +222,9 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
              void* stream);
 
 /* Run-time options of a handle.  "host_register" (default 0): see pd_pc_apply_host.
+ * "slab_overlap" (default 1): pd_slab_apply runs the per-frequency stage as two frequency halves on two streams so
+ * that the latency-bound interface / separator kernels of one half overlap the streaming passes of the other; 0
+ * keeps everything on the caller's stream (needed when one process drives several ranks on one GPU).
  * "gmres_residual_correction" (default 0): with 1, pd_gmres / pd_gmres_real form
  * the preconditioned operator as  v + P^-1 ((A - P) v)  instead of  P^-1 (A v)  -- the same operator in exact
  * arithmetic (Krylov vectors have zero Dirichlet rows), but (A - P) v only touches the wrap-around time levels

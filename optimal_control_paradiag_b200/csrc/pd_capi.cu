@@ -374,8 +374,39 @@ static int slab_apply_check(pd_handle* h, const void* p, const char* who, int re
   return PD_OK;
 }
 
+// aux stream + fork/join events (shared with the opt-in interleaved schedule), created on first use
+static int ensure_aux(pd_handle* h) {
+  if (!h->sched_aux) {
+    PD_CUDA(cudaStreamCreateWithFlags(&h->sched_aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i)
+      if (!h->sched_ev[i]) PD_CUDA(cudaEventCreateWithFlags(&h->sched_ev[i], cudaEventDisableTiming));
+  }
+  return PD_OK;
+}
+
+// The per-frequency part of the slab apply (pass A, interface + peer stores | wait + separator solve, pass B) is run
+// as TWO FREQUENCY HALVES ON TWO STREAMS: the interface and separator kernels are short, latency-bound launches
+// (one warp per scheduler, a system-scope fence, a wait for the peers) that leave most SMs idle -- with the halves
+// staggered they overlap the streaming pass A / pass B of the other half.  Frequencies are independent and the
+// exchange flags are per group of 4 frequencies, so the halves share nothing.  PD_SLAB_OVERLAP=0 or the option
+// "slab_overlap" 0 turns it off -- REQUIRED when one process drives several ranks on ONE GPU (LocalSlabGroup): there
+// the strict order "every first half before any second half" is what keeps a waiting kernel from being scheduled
+// ahead of its producer, and a second stream would break it.  The per-stage profile always runs unsplit (its
+// stage times are the un-overlapped costs).
+static bool slab_overlap(pd_handle* h, int real_input, int* split) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PD_SLAB_OVERLAP");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int K = real_input ? ((h->cfg.N_t / 2 + 1 + 7) & ~7) : h->cfg.N_t;
+  if (!env || h->opt_slab_no_overlap == 1 || K < 1024 || h->fuse_on) return false;
+  *split = ((K / 2 + 127) / 128) * 128;
+  return true;
+}
+
 // first half: time transform of this rank's lines, local elimination, functionals pushed to every rank
-static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_input, cudaEvent_t* ev) {
+static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_input, cudaEvent_t* ev, bool overlap) {
   int rc = ensure_work(h);
   if (rc) return rc;
   int fused = 0;
@@ -389,13 +420,36 @@ static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_inp
   }
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[0], st);
+  int split = 0;
+  if (overlap && !ev && slab_overlap(h, real_input, &split)) {
+    cudaStream_t sb = st;  // "slab_overlap" 2: the two halves one after the other on the caller's stream (tests)
+    if (h->opt_slab_no_overlap != 2) {
+      if ((rc = ensure_aux(h))) return rc;
+      sb = h->sched_aux;
+      PD_CUDA(cudaEventRecord(h->sched_ev[0], st));
+      PD_CUDA(cudaStreamWaitEvent(sb, h->sched_ev[0], 0));
+    }
+    if ((rc = pd_slab_reduce_launch(h, h->work, nullptr, st, real_input, nullptr, fused, 0, split))) return rc;
+    return pd_slab_reduce_launch(h, h->work, nullptr, sb, real_input, nullptr, fused, split, 1 << 30);
+  }
   return pd_slab_reduce_launch(h, h->work, nullptr, st, real_input, ev ? ev + 1 : nullptr, fused);
 }
 
 // second half: wait for the peers' functionals, separator solve, back-substitution, time transform
-static int slab_end(pd_handle* h, void* y, cudaStream_t st, int real_input, cudaEvent_t* ev) {
-  int rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev);
-  if (rc) return rc;
+static int slab_end(pd_handle* h, void* y, cudaStream_t st, int real_input, cudaEvent_t* ev, bool overlap) {
+  int rc, split = 0;
+  if (overlap && !ev && slab_overlap(h, real_input, &split)) {
+    cudaStream_t sb = h->opt_slab_no_overlap != 2 ? h->sched_aux : st;
+    if ((rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, nullptr, 0, split))) return rc;
+    if ((rc = pd_slab_finish_launch(h, h->work, nullptr, sb, real_input, nullptr, split, 1 << 30))) return rc;
+    if (sb != st) {
+      PD_CUDA(cudaEventRecord(h->sched_ev[1], sb));
+      PD_CUDA(cudaStreamWaitEvent(st, h->sched_ev[1], 0));
+    }
+  } else {
+    if ((rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev))) return rc;
+  }
+  if ((rc = pd_slab_epoch_bump_launch(h, st))) return rc;   // the apply's exchange is complete
   if (ev) cudaEventRecord(ev[1], st);
   if (real_input) return pd_stage_rfft_pair(h, h->work, y, h->n, 0, st);
   return pd_fft_launch(h, h->work, (cplx*)y, 2 * (int64_t)h->n, 0, st);
@@ -405,14 +459,14 @@ extern "C" int pd_slab_apply_begin(pd_handle* h, const void* x_dev, void* stream
   int rc = slab_apply_check(h, x_dev, "pd_slab_apply_begin", real_input);
   if (rc) return rc;
   PD_ON_DEVICE(h);
-  return slab_begin(h, x_dev, (cudaStream_t)stream, real_input, nullptr);
+  return slab_begin(h, x_dev, (cudaStream_t)stream, real_input, nullptr, true);
 }
 
 extern "C" int pd_slab_apply_end(pd_handle* h, void* y_dev, void* stream, int real_input) {
   int rc = slab_apply_check(h, y_dev, "pd_slab_apply_end", real_input);
   if (rc) return rc;
   PD_ON_DEVICE(h);
-  return slab_end(h, y_dev, (cudaStream_t)stream, real_input, nullptr);
+  return slab_end(h, y_dev, (cudaStream_t)stream, real_input, nullptr, true);
 }
 
 extern "C" int pd_slab_apply(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
@@ -423,8 +477,8 @@ extern "C" int pd_slab_apply(pd_handle* h, const void* x_dev, void* y_dev, void*
     return PD_ERR_INVALID;
   }
   PD_ON_DEVICE(h);
-  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 0, nullptr))) return rc;
-  return slab_end(h, y_dev, (cudaStream_t)stream, 0, nullptr);
+  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 0, nullptr, true))) return rc;
+  return slab_end(h, y_dev, (cudaStream_t)stream, 0, nullptr, true);
 }
 
 extern "C" int pd_slab_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
@@ -435,8 +489,8 @@ extern "C" int pd_slab_apply_real(pd_handle* h, const void* x_dev, void* y_dev, 
     return PD_ERR_INVALID;
   }
   PD_ON_DEVICE(h);
-  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 1, nullptr))) return rc;
-  return slab_end(h, y_dev, (cudaStream_t)stream, 1, nullptr);
+  if ((rc = slab_begin(h, x_dev, (cudaStream_t)stream, 1, nullptr, true))) return rc;
+  return slab_end(h, y_dev, (cudaStream_t)stream, 1, nullptr, true);
 }
 
 // one distributed apply with CUDA events between its stages: ms[0..6] = {inverse FFT, pass A, interface levels,
@@ -459,9 +513,9 @@ extern "C" int pd_slab_apply_profile(pd_handle* h, const void* x_dev, void* y_de
   } E;
   for (int i = 0; i < 8; ++i) PD_CUDA(cudaEventCreate(&E.ev[i]));
   PD_CUDA(cudaEventRecord(E.ev[0], st));
-  if ((rc = slab_begin(h, x_dev, st, 0, &E.ev[1]))) return rc;   // ev[1] ifft, ev[2] pass A, ev[3] interface
+  if ((rc = slab_begin(h, x_dev, st, 0, &E.ev[1], false))) return rc;   // ev[1] ifft, ev[2] pass A, ev[3] interface
   PD_CUDA(cudaEventRecord(E.ev[4], st));                          // functionals + peer stores
-  if ((rc = slab_end(h, y_dev, st, 0, &E.ev[5]))) return rc;      // ev[5] separator solve, ev[6] pass B
+  if ((rc = slab_end(h, y_dev, st, 0, &E.ev[5], false))) return rc;      // ev[5] separator solve, ev[6] pass B
   PD_CUDA(cudaEventRecord(E.ev[7], st));
   PD_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < 7; ++i) PD_CUDA(cudaEventElapsedTime(&ms[i], E.ev[i], E.ev[i + 1]));
@@ -500,8 +554,15 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
   int rc = ensure_work(h);
   if (rc) return rc;
   const int64_t nlines = 2 * (int64_t)h->n;
+  if (h->cfg.alpha != 1.0 && pd_fft_gamma_fused(h)) {
+    // extension: Gamma fused into the loads of the inverse FFT, alpha-shifted per-frequency stage, Gamma^-1 fused
+    // into the stores of the forward FFT -- the same three launches groups as alpha = 1
+    if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st, 1))) return rc;
+    if ((rc = pd_solve_launch(h, h->work, st))) return rc;
+    return pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st, 1);
+  }
   if (h->cfg.alpha != 1.0) {
-    // extension: Gamma, ifft, alpha-shifted per-frequency stage, fft, Gamma^-1 (two extra elementwise sweeps)
+    // (N_t = 16384 cluster kernel: Gamma / Gamma^-1 as two separate elementwise sweeps)
     if ((rc = pd_gamma_launch(h, (const cplx*)x_dev, h->work, nlines, 0, st))) return rc;
     if ((rc = pd_fft_launch(h, h->work, h->work, nlines, 1, st))) return rc;
     if ((rc = pd_solve_launch(h, h->work, st))) return rc;

@@ -145,6 +145,7 @@ struct pd_handle {
   cplx* kry_d;      // (A - P) v of the residual-correction mode: zero except on <= 3 time levels per field
   int kry_d_mode;   // 0: not initialised, 1: complex layout, 2: float64 layout
   int opt_gmres_correction;  // pd_set_option "gmres_residual_correction"
+  int opt_slab_no_overlap;   // pd_set_option "slab_overlap" 0: the slab apply stays on the caller's stream
   int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;
@@ -154,7 +155,8 @@ struct pd_handle {
 // stage launchers implemented in the .cu files
 int pd_fft_plan(pd_handle* h);
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
-                  cudaStream_t st);
+                  cudaStream_t st, int with_gamma = 0);
+bool pd_fft_gamma_fused(const pd_handle* h);
 bool pd_fft_segments_supported(const pd_handle* h);
 int pd_fft_launch_segments(pd_handle* h, const cplx* in, cplx* out, int64_t seg_lines, int nseg, int64_t seg_stride,
                            int inverse, cudaStream_t st);
@@ -169,14 +171,15 @@ int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes,
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr, int half_spectrum = 0);
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0,
-                          cudaEvent_t* ev = nullptr, int passA_done = 0);
+                          cudaEvent_t* ev = nullptr, int passA_done = 0, int koff = 0, int kend = 0);
+int pd_slab_epoch_bump_launch(pd_handle* h, cudaStream_t st);
 cplx* pd_slab_lastl(pd_handle* h);
 // fused inverse FFT + pass A (pd_fused.cu)
 bool pd_fused_supported(const pd_handle* h);
 int pd_fused_ifft_passA_launch(pd_handle* h, const cplx* x, cplx* w, cudaStream_t st, cplx* lastl);
 void pd_fused_free(pd_handle* h);
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0,
-                          cudaEvent_t* ev = nullptr);
+                          cudaEvent_t* ev = nullptr, int koff = 0, int kend = 0);
 bool pd_slab_half_supported(const pd_handle* h);
 int pd_slab_comm_create_impl(pd_handle* h, void* ipc_handle_out, void** base_out);
 int pd_slab_comm_connect_impl(pd_handle* h, const void* peers, int mode, const int* peer_devices);

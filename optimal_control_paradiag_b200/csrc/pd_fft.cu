@@ -60,7 +60,8 @@ struct PassList {
 template <bool INV>
 __global__ void __launch_bounds__(256)
 pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N,
-                      int64_t nlines, const cplx* __restrict__ tw, PassList pl, double scale) {
+                      int64_t nlines, const cplx* __restrict__ tw, PassList pl, double scale,
+                      const double* __restrict__ gam) {
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cplx* buf0 = reinterpret_cast<cplx*>(pd_smem_raw);
   cplx* buf1 = buf0 + N;
@@ -68,7 +69,8 @@ pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N
   for (int64_t line = blockIdx.x; line < nlines; line += gridDim.x) {
     const cplx* src_g = in + line * (int64_t)N;
     cplx* dst_g = out + line * (int64_t)N;
-    for (int i = tid; i < N; i += nth) buf0[i] = src_g[i];
+    // gam (alpha != 1): Gamma on load for the inverse transform, Gamma^-1 on store for the forward one
+    for (int i = tid; i < N; i += nth) buf0[i] = (INV && gam) ? cscale(src_g[i], gam[i]) : src_g[i];
     __syncthreads();
     cplx* s = buf0;
     cplx* d = buf1;
@@ -93,7 +95,7 @@ pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N
           if (e >= N) e -= N;
         }
         if (last)
-          dst_g[o] = cscale(acc, scale);
+          dst_g[o] = cscale(acc, (!INV && gam) ? scale * gam[o] : scale);
         else
           d[o] = acc;
       }
@@ -111,7 +113,8 @@ pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N
 template <int R0, int R1, int R2, int R3, bool INV>
 __global__ void __launch_bounds__(512)
 pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
-                   const cplx* __restrict__ tw, double scale, int64_t seg_lines, int64_t seg_stride) {
+                   const cplx* __restrict__ tw, double scale, int64_t seg_lines, int64_t seg_stride,
+                   const double* __restrict__ gam) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
@@ -131,17 +134,20 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
     // on the clamped line and only skips the final store
     const bool live = line < nlines;
     constexpr bool L0 = (R1 == 1);
-    pow2_pass<R0, INV, true, L0>(gsrc, gdst, sm, tw, N, 1, t, T, scale, live);
+    // (INV: Gamma on the loads of the first pass; forward: Gamma^-1 on the stores of the last pass)
+    const double* g_in = INV ? gam : nullptr;
+    const double* g_out = INV ? nullptr : gam;
+    pow2_pass<R0, INV, true, L0>(gsrc, gdst, sm, tw, N, 1, t, T, scale, live, nullptr, g_in);
     if (R1 > 1) {
       constexpr bool L1 = (R2 == 1);
-      pow2_pass<(R1 > 1 ? R1 : 2), INV, false, L1>(gsrc, gdst, sm, tw, N, R0, t, T, scale, live);
+      pow2_pass<(R1 > 1 ? R1 : 2), INV, false, L1>(gsrc, gdst, sm, tw, N, R0, t, T, scale, live, nullptr, L1 ? g_out : nullptr);
     }
     if (R2 > 1) {
       constexpr bool L2 = (R3 == 1);
-      pow2_pass<(R2 > 1 ? R2 : 2), INV, false, L2>(gsrc, gdst, sm, tw, N, R0 * R1, t, T, scale, live);
+      pow2_pass<(R2 > 1 ? R2 : 2), INV, false, L2>(gsrc, gdst, sm, tw, N, R0 * R1, t, T, scale, live, nullptr, L2 ? g_out : nullptr);
     }
     if (R3 > 1) {
-      pow2_pass<(R3 > 1 ? R3 : 2), INV, false, true>(gsrc, gdst, sm, tw, N, R0 * R1 * R2, t, T, scale, live);
+      pow2_pass<(R3 > 1 ? R3 : 2), INV, false, true>(gsrc, gdst, sm, tw, N, R0 * R1 * R2, t, T, scale, live, nullptr, g_out);
     }
     __syncthreads();
   }
@@ -307,7 +313,8 @@ __device__ __forceinline__ void st_hint(cplx* p, cplx v, uint64_t pol) {
 template <bool INV, bool TO_FREQ>
 __global__ void __launch_bounds__(256, 2)
 pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
-                     const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale) {
+                     const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale,
+                     const double* __restrict__ gam) {
   constexpr int N = PD_BIGN, Q = N / 4, T = Q / 16, J = Q / 4;
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw);
@@ -329,6 +336,7 @@ pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             cplx x = ld_in(src + jq * J + T * u + t + Q * m);
+            if (gam) x = cscale(x, gam[jq * J + T * u + t + Q * m]);  // Gamma on load (alpha != 1)
             if (INV) x.y = -x.y;
             v[u][m] = x;
           }
@@ -398,7 +406,7 @@ pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_
           for (int m = 0; m < 4; ++m) {
             cplx y = v[m];
             if (INV) y.y = -y.y;
-            st_out(dst + m * Q + n, cscale(y, scale));
+            st_out(dst + m * Q + n, cscale(y, gam ? scale * gam[m * Q + n] : scale));  // Gamma^-1 on store
           }
         }
       }
@@ -633,8 +641,10 @@ int pd_fft_plan(pd_handle* h) {
 
 template <int R0, int R1, int R2, int R3>
 static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
-                       cudaStream_t st, int64_t seg_lines = 0, int64_t seg_stride = 0) {
+                       cudaStream_t st, int64_t seg_lines = 0, int64_t seg_stride = 0, int with_gamma = 0) {
   if (seg_lines <= 0) seg_lines = nlines;
+  // alpha != 1: Gamma (inverse transform) / Gamma^-1 (forward) fused into the first / last pass
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (inverse ? 0 : R0 * R1 * R2 * R3) : nullptr;
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   int threads = T < 256 ? 256 : T;
@@ -645,28 +655,31 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   if (inverse) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
   } else {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
   }
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
 }
 
-static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
+static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st,
+                      int with_gamma = 0) {
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (inverse ? 0 : PD_BIGN) : nullptr;
   const double scale = inverse ? 1.0 / (double)PD_BIGN : 1.0;
   // inverse (time -> frequency, :500-501) leaves the permuted frequency order, forward (:547-548) consumes it.
   const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
   if (h->fft16k_l2) {
     const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
     if (inverse)
-      pd_fft_16k_l2_kernel<true, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter, scale);
+      pd_fft_16k_l2_kernel<true, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter, scale,
+                                                                gam);
     else
       pd_fft_16k_l2_kernel<false, false><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                 scale);
+                                                                 scale, gam);
     PD_CHECK_LAUNCH();
     h->launches++;
     return PD_OK;
@@ -921,24 +934,33 @@ int pd_fft_launch_segments(pd_handle* h, const cplx* in, cplx* out, int64_t seg_
   return PD_ERR_UNSUPPORTED;
 }
 
+// true when pd_fft_launch can apply the Gamma_alpha weights inside the transform (with_gamma)
+bool pd_fft_gamma_fused(const pd_handle* h) {
+  return !(h->cfg.N_t == PD_BIGN && h->fft_kind == 1 && !h->fft16k_l2);  // every kernel but the 16k cluster variant
+}
+
+// with_gamma (alpha != 1): the transform also applies Gamma (inverse != 0: on its input) / Gamma^-1 (inverse == 0:
+// on its output) -- the time-weight scaling of the alpha-circulant costs no sweep of its own
 int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse,
-                  cudaStream_t st) {
+                  cudaStream_t st, int with_gamma) {
   const int N = h->cfg.N_t;
   if (nlines <= 0) return PD_OK;
+  const int g = with_gamma;
   if (h->fft_kind == 1) {
     switch (N) {
-      case 64:   return launch_pow2<16, 4, 1, 1>(h, in, out, nlines, inverse, st);
-      case 128:  return launch_pow2<16, 8, 1, 1>(h, in, out, nlines, inverse, st);
-      case 256:  return launch_pow2<16, 16, 1, 1>(h, in, out, nlines, inverse, st);
-      case 512:  return launch_pow2<16, 8, 4, 1>(h, in, out, nlines, inverse, st);
-      case 1024: return launch_pow2<16, 16, 4, 1>(h, in, out, nlines, inverse, st);
-      case 2048: return launch_pow2<16, 16, 8, 1>(h, in, out, nlines, inverse, st);
-      case 4096: return launch_pow2<16, 16, 16, 1>(h, in, out, nlines, inverse, st);
-      case 8192: return launch_pow2<16, 16, 8, 4>(h, in, out, nlines, inverse, st);
-      case 16384: return launch_16k(h, in, out, nlines, inverse, st);
+      case 64:   return launch_pow2<16, 4, 1, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 128:  return launch_pow2<16, 8, 1, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 256:  return launch_pow2<16, 16, 1, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 512:  return launch_pow2<16, 8, 4, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 1024: return launch_pow2<16, 16, 4, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 2048: return launch_pow2<16, 16, 8, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 4096: return launch_pow2<16, 16, 16, 1>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 8192: return launch_pow2<16, 16, 8, 4>(h, in, out, nlines, inverse, st, 0, 0, g);
+      case 16384: return launch_16k(h, in, out, nlines, inverse, st, g);
       default: break;
     }
   }
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (inverse ? 0 : N) : nullptr;
   PassList pl;
   pl.n = h->npass;
   for (int i = 0; i < pl.n; ++i) pl.r[i] = h->radix[i];
@@ -946,9 +968,9 @@ int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int i
   int64_t nblk = nlines < (int64_t)h->num_sms * 8 ? nlines : (int64_t)h->num_sms * 8;
   double scale = inverse ? 1.0 / (double)N : 1.0;
   if (inverse)
-    pd_fft_generic_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale);
+    pd_fft_generic_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale, gam);
   else
-    pd_fft_generic_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale);
+    pd_fft_generic_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nlines, h->twiddle, pl, scale, gam);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;

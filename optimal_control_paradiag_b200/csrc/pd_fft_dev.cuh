@@ -112,7 +112,11 @@ __device__ __forceinline__ void cluster_store(uint32_t addr, cplx v) {
 template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false, bool CLARRIVE = false>
 __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
                                           cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
-                                          int t, int T, double scale, bool live, cplx* io = nullptr) {
+                                          int t, int T, double scale, bool live, cplx* io = nullptr,
+                                          const double* __restrict__ gam = nullptr) {
+  // gam (alpha != 1 only, else null): Gamma_alpha time weights fused into the transform -- the samples are scaled
+  // by gam[time index] as the FIRST pass loads them (Gamma before the inverse FFT) or as the LAST pass stores them
+  // (Gamma^-1 after the forward FFT): no separate elementwise sweep.
   constexpr int NB = 16 / R;  // butterflies per thread
   const int NR = N / R;
   const int tws = N / (Ns * R);
@@ -127,6 +131,7 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         x = io[u * R + q];
       } else {
         x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
+        if (FIRST && gam) x = cscale(x, gam[j + q * NR]);
         if (FIRST && INV) x.y = -x.y;
       }
       v[u][q] = x;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         io[u * R + r] = x;
       } else if (LAST) {
         if (INV) x.y = -x.y;
-        if (live) gdst[base + r * Ns] = cscale(x, scale);
+        if (live) gdst[base + r * Ns] = cscale(x, gam ? scale * gam[base + r * Ns] : scale);
       } else {
         sm[pad16(base + r * Ns)] = x;
       }

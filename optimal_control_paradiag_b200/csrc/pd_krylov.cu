@@ -811,6 +811,7 @@ extern "C" int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, doubl
 
 // Run-time options of a handle (name, value).  Unknown names are an error.
 //   "gmres_residual_correction" : 0 (default) pd_gmres forms P^-1 (A v) as KSP does; 1: v + P^-1 ((A - P) v)
+//   "slab_overlap"              : 1 (default): pd_slab_apply runs its two frequency halves on two streams; 0: one stream
 //   "host_register"             : 0 (default); 1: pd_pc_apply_host page-locks each host buffer once (see pd_capi.cu)
 extern "C" int pd_set_option(pd_handle* h, const char* name, double value) {
   if (!h || !name) {
@@ -819,6 +820,10 @@ extern "C" int pd_set_option(pd_handle* h, const char* name, double value) {
   }
   if (!strcmp(name, "gmres_residual_correction")) {
     h->opt_gmres_correction = value != 0.0;
+    return PD_OK;
+  }
+  if (!strcmp(name, "slab_overlap")) {
+    h->opt_slab_no_overlap = value == 0.0 ? 1 : (value == 2.0 ? 2 : 0);  // 2: split, but on one stream (tests)
     return PD_OK;
   }
   if (!strcmp(name, "host_register")) {

@@ -545,7 +545,7 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
       slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
     }
   }
-  if (PUSH) slab_publish(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.kend - blockIdx.x * PD_KB));
+  if (PUSH) slab_publish(cm, ep, sp.koff + blockIdx.x * PD_KB, min(PD_KB, sp.kend - sp.koff - blockIdx.x * PD_KB));
 }
 
 // ------------------------------------------------------------------- pass B
@@ -651,10 +651,11 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       wp[(int64_t)(sp.m + 1) * sp.K] = zero;
     }
   }
-  // peer-store exchange: this apply's functionals and separator kernels are complete (stream order), the next
-  // apply's have not started
-  if (SLAB && sl.epoch_bump && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *sl.epoch_bump += 1ull;
 }
+
+// peer-store exchange: marks the apply complete.  Launched once per apply after every separator kernel of the apply
+// (stream order / event join) and before anything of the next apply.
+__global__ void pd_slab_epoch_bump_kernel(unsigned long long* epoch) { *epoch += 1ull; }
 
 // ------------------------------------------------------------ slab-mode kernels
 // Slab mode = x-slab sharding kept through the solve (no transposes): rank r owns a contiguous node
@@ -669,9 +670,9 @@ template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
                            cplx* __restrict__ out, SlabCommDev cm) {
-  const int kk = blockIdx.x * PD_KB + threadIdx.x;
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
-  if (kk < sp.K) {
+  if (kk < sp.kend) {
     const int64_t K = sp.K;
     const KCoef kc = make_coef(freq_of(sp, kk), sp);
     const int P = sp.rows[1];
@@ -691,7 +692,7 @@ pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp
       slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
     }
   }
-  if (PUSH) slab_publish(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.K - blockIdx.x * PD_KB));
+  if (PUSH) slab_publish(cm, ep, sp.koff + blockIdx.x * PD_KB, min(PD_KB, sp.kend - sp.koff - blockIdx.x * PD_KB));
 }
 
 struct SlabGeom {
@@ -734,11 +735,11 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   if (WAIT) {
     // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
     const unsigned long long ep = *cm.epoch + 1ull;
-    slab_wait(cm, ep, blockIdx.x * PD_KB, min(PD_KB, sp.K - blockIdx.x * PD_KB));
+    slab_wait(cm, ep, sp.koff + blockIdx.x * PD_KB, min(PD_KB, sp.kend - sp.koff - blockIdx.x * PD_KB));
     gathered = cm.peer_gath[cm.rank] + (int64_t)(ep & 1ull) * cm.G * 6 * cm.kmax;
   }
-  const int kk = blockIdx.x * PD_KB + threadIdx.x;
-  if (kk >= sp.K) return;
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  if (kk >= sp.kend) return;
   const int64_t K = sp.K;
   const int64_t GS = gstride;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
@@ -876,10 +877,21 @@ void pd_solve_free(pd_handle* h) {
   h->solve_plan = nullptr;
 }
 
-static dim3 stream_grid(const pd_handle* h, int K, int nchunks) {
+// cps: CTAs of the kernel that are resident per SM (pass A 4, pass B 2, the small level kernels 8)
+static dim3 stream_grid(const pd_handle* h, int K, int nchunks, int cps = 8) {
   const int kblocks = (K + PD_KB - 1) / PD_KB;
   // enough CTAs for ~8 resident per SM; more chunks than that are looped over
   int ny = (h->num_sms * 8 + kblocks - 1) / kblocks;
+  // Short x-ranges (the x-slab of a multi-GPU run: 121 chunks at cfg3 on 8 GPUs): with that grid a CTA would see 3
+  // chunks, and its prologue (the pivot recurrences, ~a chunk's worth of time) plus a ragged last wave cost 25 %.
+  // Use whole waves of resident CTAs with at least ~8 chunks each instead.
+  if (nchunks < ny * 8) {
+    int per_wave = h->num_sms * cps / kblocks;
+    if (per_wave < 1) per_wave = 1;
+    int waves = nchunks / 8 / per_wave;
+    if (waves < 1) waves = 1;
+    if (per_wave * waves < ny) ny = per_wave * waves;
+  }
   if (ny > nchunks) ny = nchunks;
   if (ny < 1) ny = 1;
   if (ny > 65535) ny = 65535;
@@ -909,7 +921,6 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = half_spectrum ? pl->green_h : pl->green; sl.zout = pl->zout;
-  sl.epoch_bump = nullptr;
 }
 
 void pd_solve_fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl, int half_spectrum) {
@@ -929,7 +940,7 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   const int top = sp.nlev;
   const int ncol = sp.kend - sp.koff;
   const cplx* piv = plan_of(h)->ipiv[sp.K == h->kcount ? 0 : 1];
-  if (piv && sp.koff == 0 && sp.kend == sp.K) {
+  if (piv) {
     const int nblk = (ncol + PD_KB - 1) / PD_KB;
     if (push) {
       pd_solve_iface_thomas_kernel<true><<<nblk, PD_KB, 0, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
@@ -1110,12 +1121,13 @@ static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, 
                        cudaStream_t st, cudaEvent_t* ev, cudaEvent_t after_passA = nullptr) {
   sp.koff = koff;
   sp.kend = kend;
-  const dim3 grid0 = stream_grid(h, kend - koff, sp.rows[1] + 1);
+  const dim3 gridA = stream_grid(h, kend - koff, sp.rows[1] + 1, 4);
+  const dim3 grid0 = stream_grid(h, kend - koff, sp.rows[1] + 1, 2);
   if (sp.nlev >= 1) {
     if (sp.al)
-      pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+      pd_solve_passA_kernel<true><<<gridA, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
     else
-      pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+      pd_solve_passA_kernel<false><<<gridA, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
@@ -1155,7 +1167,7 @@ int pd_solve_passA_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st)
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, 0);
   sp.c0 = c0; sp.c1 = c1;
-  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0);
+  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0, 4);
   if (sp.al)
     pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
   else
@@ -1173,7 +1185,7 @@ int pd_solve_passB_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st)
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, 0);
   sp.c0 = c0; sp.c1 = c1;
-  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0);
+  const dim3 grid0 = stream_grid(h, sp.K, c1 - c0, 2);
   if (sp.al)
     pd_solve_passB_kernel<false, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   else
@@ -1304,11 +1316,16 @@ int pd_slab_comm_status_impl(pd_handle* h, int* timed_out, unsigned long long* e
 // slab mode, first half: pass A, interface levels, slab functionals -> out[6][K]
 // (out == nullptr: pushed to every rank's exchange buffer instead, see SlabCommDev)
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum, cudaEvent_t* ev,
-                          int passA_done) {
+                          int passA_done, int koff, int kend) {
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, half_spectrum);
-  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
-  const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
+  if (kend > koff) {  // column range [koff, kend) only (frequency halves of one apply on two streams)
+    sp.koff = koff;
+    sp.kend = kend < sp.K ? kend : sp.K;
+  }
+  const int ncol = sp.kend - sp.koff;
+  const dim3 grid0 = stream_grid(h, ncol, sp.rows[1] + 1, 4);
+  const int kblocks = (ncol + PD_KB - 1) / PD_KB;
   SolvePlan* pl = plan_of(h);
   if (!out && !pl->comm_connected) {
     pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
@@ -1351,14 +1368,28 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
   return PD_OK;
 }
 
+int pd_slab_epoch_bump_launch(pd_handle* h, cudaStream_t st) {
+  SolvePlan* pl = plan_of(h);
+  pd_slab_epoch_bump_kernel<<<1, 1, 0, st>>>(pl->comm_epoch);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
+}
+
 // slab mode, second half: global separator solve from the gathered functionals, then pass B
 // (gathered == nullptr: waits for the peers' stores into this rank's exchange buffer)
-int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum, cudaEvent_t* ev) {
+int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum, cudaEvent_t* ev,
+                          int koff, int kend) {
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, half_spectrum);
+  if (kend > koff) {
+    sp.koff = koff;
+    sp.kend = kend < sp.K ? kend : sp.K;
+  }
   SolvePlan* pl = plan_of(h);
-  const dim3 grid0 = stream_grid(h, sp.K, sp.rows[1] + 1);
-  const int kblocks = (sp.K + PD_KB - 1) / PD_KB;
+  const int ncol = sp.kend - sp.koff;
+  const dim3 grid0 = stream_grid(h, ncol, sp.rows[1] + 1, 2);
+  const int kblocks = (ncol + PD_KB - 1) / PD_KB;
   const cplx* coef = half_spectrum ? pl->slabcoef_h : pl->slabcoef;
   // enough CTAs in y for the correction sweep over the interior separators (rows[1] x 2 x K values)
   int gy = sp.rows[1] / 8;
@@ -1378,7 +1409,6 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
     }
     pd_slab_global_kernel<true><<<ggrid, PD_KB, 0, st>>>(nullptr, pl->comm_kmax, sp, pl->sg, coef, pl->zout,
                                                         comm_dev_of(h), zsep, sl.green);
-    sl.epoch_bump = pl->comm_epoch;
   }
   PD_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[0], st);

@@ -417,7 +417,7 @@ class LocalSlabGroup:
     only one GPU is leased: every first half ``pd_slab_apply_begin`` is issued before any second half, so no
     kernel ever waits for one queued behind it) or on several GPUs with peer access (one per slab)."""
 
-    def __init__(self, N_x, N_t, G, T=2.0, gamma=1.0, devices=None):
+    def __init__(self, N_x, N_t, G, T=2.0, gamma=1.0, devices=None, split_on_one_stream=False):
         import torch
 
         from .handle import ParaDiagHandle
@@ -430,6 +430,11 @@ class LocalSlabGroup:
         bases = [h.slab_comm_create()[1] for h in self.handles]
         for h in self.handles:
             h.slab_comm_connect_local(bases, self.devices)
+            # several ranks on one GPU: everything stays on ONE stream, so that every first half really runs before
+            # any second half (a second stream per handle would let a waiting kernel overtake its producer)
+            if len(set(self.devices)) < self.G:
+                # (2: still split into the two frequency halves, one after the other -- covers the range kernels)
+                h.set_option("slab_overlap", 2 if split_on_one_stream else 0)
 
     def close(self):
         for h in self.handles:

@@ -66,6 +66,19 @@ def test_peer_exchange_real_input_path_on_one_gpu(N_x, N_t, G):
         assert all(not to and ep == 4 for to, ep in grp.status())
 
 
+@pytest.mark.parametrize("N_x,N_t,G,real", [(1024, 1024, 4, False), (4096, 4096, 8, False), (2047, 2048, 3, True),
+                                             (300, 16384, 2, False), (4096, 4096, 8, True)])
+def test_frequency_halves_of_the_slab_apply(N_x, N_t, G, real):
+    # pd_slab_apply runs its per-frequency stage as two frequency halves (on two streams when every rank has its own
+    # GPU); here the halves run one after the other on one stream: same kernels, same column ranges
+    with ParaDiagHandle(N_x, N_t) as h, LocalSlabGroup(N_x, N_t, G, split_on_one_stream=True) as grp:
+        for rep in range(3):
+            x = rand_global(h.size, seed=rep, real=real)
+            ref = h.pc_apply_real(x) if real else h.pc_apply(x)
+            assert relerr(grp.apply(x, real=real), ref) < 1e-10
+        assert all(not to and ep == 3 for to, ep in grp.status())
+
+
 def test_peer_exchange_at_cfg3_with_eight_slabs_on_one_gpu():
     # the driver's scaling configuration (cfg3, 8 ranks) with all eight slabs on the one leased GPU
     N_x, N_t, G = 16384, 4096, 8
