@@ -110,7 +110,7 @@ pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N
 
 // N = R0 * R1 * R2 * R3 (unused radices = 1); T = N/16 threads per line,
 // LPB lines per block.
-template <int R0, int R1, int R2, int R3, bool INV>
+template <int R0, int R1, int R2, int R3, bool INV, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
                    const cplx* __restrict__ tw, double scale, int64_t seg_lines, int64_t seg_stride,
@@ -137,17 +137,17 @@ pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t 
     // (INV: Gamma on the loads of the first pass; forward: Gamma^-1 on the stores of the last pass)
     const double* g_in = INV ? gam : nullptr;
     const double* g_out = INV ? nullptr : gam;
-    pow2_pass<R0, INV, true, L0>(gsrc, gdst, sm, tw, N, 1, t, T, scale, live, nullptr, g_in);
+    pow2_pass<R0, INV, true, L0, false, false, false, GAM && INV>(gsrc, gdst, sm, tw, N, 1, t, T, scale, live, nullptr, g_in);
     if (R1 > 1) {
       constexpr bool L1 = (R2 == 1);
-      pow2_pass<(R1 > 1 ? R1 : 2), INV, false, L1>(gsrc, gdst, sm, tw, N, R0, t, T, scale, live, nullptr, L1 ? g_out : nullptr);
+      pow2_pass<(R1 > 1 ? R1 : 2), INV, false, L1, false, false, false, GAM && !INV && L1>(gsrc, gdst, sm, tw, N, R0, t, T, scale, live, nullptr, g_out);
     }
     if (R2 > 1) {
       constexpr bool L2 = (R3 == 1);
-      pow2_pass<(R2 > 1 ? R2 : 2), INV, false, L2>(gsrc, gdst, sm, tw, N, R0 * R1, t, T, scale, live, nullptr, L2 ? g_out : nullptr);
+      pow2_pass<(R2 > 1 ? R2 : 2), INV, false, L2, false, false, false, GAM && !INV && L2>(gsrc, gdst, sm, tw, N, R0 * R1, t, T, scale, live, nullptr, g_out);
     }
     if (R3 > 1) {
-      pow2_pass<(R3 > 1 ? R3 : 2), INV, false, true>(gsrc, gdst, sm, tw, N, R0 * R1 * R2, t, T, scale, live, nullptr, g_out);
+      pow2_pass<(R3 > 1 ? R3 : 2), INV, false, true, false, false, false, GAM && !INV>(gsrc, gdst, sm, tw, N, R0 * R1 * R2, t, T, scale, live, nullptr, g_out);
     }
     __syncthreads();
   }
@@ -310,7 +310,7 @@ __device__ __forceinline__ void st_hint(cplx* p, cplx v, uint64_t pol) {
 // first pass fed from registers and their last pass kept in registers.  Measured (B200, ncu): without the
 // policies 1.57 + 1.70 GB of DRAM traffic per 1.07 GB sweep and 3.7-3.9 TB/s; with them 1.08 + 1.06 GB and
 // 4.2 TB/s (an L2 prefetch of the next input piece and a persistent grid changed nothing).
-template <bool INV, bool TO_FREQ>
+template <bool INV, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(256, 2)
 pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
                      const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale,
@@ -336,7 +336,7 @@ pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             cplx x = ld_in(src + jq * J + T * u + t + Q * m);
-            if (gam) x = cscale(x, gam[jq * J + T * u + t + Q * m]);  // Gamma on load (alpha != 1)
+            if (GAM) x = cscale(x, gam[jq * J + T * u + t + Q * m]);  // Gamma on load (alpha != 1)
             if (INV) x.y = -x.y;
             v[u][m] = x;
           }
@@ -406,7 +406,7 @@ pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_
           for (int m = 0; m < 4; ++m) {
             cplx y = v[m];
             if (INV) y.y = -y.y;
-            st_out(dst + m * Q + n, cscale(y, gam ? scale * gam[m * Q + n] : scale));  // Gamma^-1 on store
+            st_out(dst + m * Q + n, cscale(y, GAM ? scale * gam[m * Q + n] : scale));  // Gamma^-1 on store
           }
         }
       }
@@ -584,9 +584,13 @@ int pd_fft_plan(pd_handle* h) {
                                  (int)smem));
     PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     {
       const char* env = getenv("PD_FFT16K");
@@ -652,12 +656,20 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   size_t smem = (size_t)lpb * (N + N / 16) * sizeof(cplx);
   int64_t nblk = (nlines + lpb - 1) / lpb;
   double scale = inverse ? 1.0 / (double)N : 1.0;
-  if (inverse) {
-    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true>;
+  if (inverse && !gam) {
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, false>;
+    PD_SET_SMEM_ONCE(k, smem);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+  } else if (!gam) {
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, false>;
+    PD_SET_SMEM_ONCE(k, smem);
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+  } else if (inverse) {
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, true>;
     PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
   } else {
-    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false>;
+    auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, true>;
     PD_SET_SMEM_ONCE(k, smem);
     k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
   }
@@ -674,12 +686,18 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
   const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
   if (h->fft16k_l2) {
     const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
-    if (inverse)
-      pd_fft_16k_l2_kernel<true, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter, scale,
-                                                                gam);
+    if (inverse && !gam)
+      pd_fft_16k_l2_kernel<true, true, false><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
+                                                                       scale, gam);
+    else if (!gam)
+      pd_fft_16k_l2_kernel<false, false, false><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle,
+                                                                        h->twiddle_quarter, scale, gam);
+    else if (inverse)
+      pd_fft_16k_l2_kernel<true, true, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
+                                                                      scale, gam);
     else
-      pd_fft_16k_l2_kernel<false, false><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                 scale, gam);
+      pd_fft_16k_l2_kernel<false, false, true><<<grid, 256, smem, st>>>(in, out, nlines, h->twiddle,
+                                                                       h->twiddle_quarter, scale, gam);
     PD_CHECK_LAUNCH();
     h->launches++;
     return PD_OK;

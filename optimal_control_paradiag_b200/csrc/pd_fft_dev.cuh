@@ -109,12 +109,14 @@ __device__ __forceinline__ void cluster_store(uint32_t addr, cplx v) {
   asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
 
-template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false, bool CLARRIVE = false>
+template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false, bool CLARRIVE = false,
+          bool GAM = false>
 __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
                                           cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
                                           int t, int T, double scale, bool live, cplx* io = nullptr,
                                           const double* __restrict__ gam = nullptr) {
-  // gam (alpha != 1 only, else null): Gamma_alpha time weights fused into the transform -- the samples are scaled
+  // GAM / gam (alpha != 1 only; a template flag so that the alpha = 1 kernels carry no trace of it -- a run-time
+  // test on the pointer inside the load loop cost the inverse transform 17 %): Gamma_alpha time weights fused into the transform -- the samples are scaled
   // by gam[time index] as the FIRST pass loads them (Gamma before the inverse FFT) or as the LAST pass stores them
   // (Gamma^-1 after the forward FFT): no separate elementwise sweep.
   constexpr int NB = 16 / R;  // butterflies per thread
@@ -131,7 +133,7 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         x = io[u * R + q];
       } else {
         x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
-        if (FIRST && gam) x = cscale(x, gam[j + q * NR]);
+        if (GAM && FIRST) x = cscale(x, gam[j + q * NR]);
         if (FIRST && INV) x.y = -x.y;
       }
       v[u][q] = x;
@@ -178,7 +180,7 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         io[u * R + r] = x;
       } else if (LAST) {
         if (INV) x.y = -x.y;
-        if (live) gdst[base + r * Ns] = cscale(x, gam ? scale * gam[base + r * Ns] : scale);
+        if (live) gdst[base + r * Ns] = cscale(x, GAM ? scale * gam[base + r * Ns] : scale);
       } else {
         sm[pad16(base + r * Ns)] = x;
       }
