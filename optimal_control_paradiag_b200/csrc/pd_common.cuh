@@ -100,6 +100,7 @@ struct pd_handle {
   cplx* twiddle_half;     // same for N_t / 2 (power-of-two N_t >= 128: real-input path)
   cplx* twiddle_quarter;  // same for N_t / 4 (only N_t = 16384: the 4-CTA cluster kernel)
   int fft16k_l2;          // 1: cluster-free 16k kernel (default), 0: 4-CTA cluster kernel (PD_FFT16K=cluster)
+  int fft16k_tma;         // 1: bulk-async-copy pipeline kernel (PD_FFT16K=tma)
   int fft16k_clusters;    // co-resident 4-CTA clusters (grid of the persistent 16k kernel)
   double* gamma_tab;      // alpha != 1 only: a^j (N_t entries) followed by a^-j, a = alpha^(1/N_t)
   int fft_kind;   // 0 generic smem Stockham, 1 power-of-two register kernel

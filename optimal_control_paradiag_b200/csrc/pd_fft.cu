@@ -414,6 +414,241 @@ pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// (3) pd_fft_16k_tma_kernel (PD_FFT16K=tma): the same 4 x 4096 decomposition with ALL global traffic on the bulk
+//     asynchronous copy engine (cp.async.bulk + mbarrier, SASS UBLKCP) instead of the load/store units.
+// ncu on (1): no pipe is saturated (DRAM 48 %, L1TEX 57-61 %, fp64 39 %, 16 of 64 warps resident) -- the kernel
+// is latency-bound: a CTA alternates between waiting for its 128-bit loads and computing, and two CTAs per SM
+// are all that registers and shared memory allow.  Here ONE persistent 256-thread CTA per SM runs a software
+// pipeline of "stages" over two 64 KiB shared-memory buffers:
+//      bulk load of stage s+1 / s+2   ||   compute of stage s (in place in its buffer)   ||   bulk store of stage s-1
+//   BFLY stage (one j-quarter): 4 strided 16 KiB pieces in, radix-4 butterflies + twiddles on registers, the 4 pieces
+//        of the result written back to the same shared-memory slots, 4 pieces out;
+//   FFTQ stage (one quarter)  : 64 KiB contiguous in, the 4096-point register pipeline (passes exchange through a third,
+//        padded buffer), result written back in place, 64 KiB contiguous out.
+// TO_FREQ lines are BFLY x4 (in -> mid, parked in L2 inside `out`) then FFTQ x4 (mid -> out, in place); !TO_FREQ lines
+// are FFTQ x4 then BFLY x4.  The second kind of a line may only be loaded once the stores of its first kind have
+// completed (cp.async.bulk.wait_group), so the stages of consecutive lines are interleaved (first kind of line i
+// between the second-kind stages of line i-1): the dependency is then always at least two stages old and costs no
+// bubble.  Loads and stores carry L2 eviction-priority hints like (1).  Every wait is bounded (trap, never a hang).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(b, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#define PD_TMA_BUF (PD_BIGN / 4 * 16)                                    // 64 KiB: one stage
+#define PD_TMA_X ((PD_BIGN / 4 + PD_BIGN / 64) * 16)                     // padded exchange buffer of the 4096-point passes
+#define PD_TMA_SMEM (2 * PD_TMA_BUF + PD_TMA_X + 64)
+
+template <bool INV, bool TO_FREQ>
+__global__ void __launch_bounds__(256, 1)
+pd_fft_16k_tma_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
+                      const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale) {
+  constexpr int N = PD_BIGN, Q = N / 4, T = Q / 16, J = Q / 4;
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  cplx* bufs[2] = {reinterpret_cast<cplx*>(pd_smem_raw), reinterpret_cast<cplx*>(pd_smem_raw + PD_TMA_BUF)};
+  cplx* X = reinterpret_cast<cplx*>(pd_smem_raw + 2 * PD_TMA_BUF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(pd_smem_raw + 2 * PD_TMA_BUF + PD_TMA_X);
+  const int t = threadIdx.x;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  // this CTA's lines: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int64_t cnt = (nlines - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  if (cnt <= 0) return;
+  const int64_t total = 8 * cnt;
+  if (t == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // stage s -> (line index i, second kind?, j)
+  auto decode = [&](int64_t s, int64_t& i, bool& second, int& j) {
+    if (s < 4) { i = 0; second = false; j = (int)s; return; }
+    if (s >= total - 4) { i = cnt - 1; second = true; j = (int)(s - (total - 4)); return; }
+    const int64_t r = s - 4, pair = r >> 1;
+    j = (int)(pair & 3);
+    second = (r & 1) != 0;
+    i = (pair >> 2) + (second ? 0 : 1);
+  };
+  // index of the last first-kind stage of line i (the stores a second-kind stage of line i depends on)
+  auto last_first = [&](int64_t i) -> int64_t { return i == 0 ? 3 : 4 + 2 * (4 * (i - 1) + 3); };
+  // the stage after whose compute the load of stage s is issued (-1: in the prologue)
+  auto issue_at = [&](int64_t s) -> int64_t {
+    int64_t i; bool second; int j;
+    decode(s, i, second, j);
+    const int64_t dep = second ? last_first(i) : -1;
+    return (s - 2 > dep) ? s - 2 : dep;
+  };
+  // BFLY pieces are strided by Q in global memory and packed [4][J] in the buffer; FFTQ is one contiguous quarter
+  const bool first_is_bfly = TO_FREQ;
+  auto issue_load = [&](int64_t s) {  // thread 0 only
+    int64_t i; bool second; int j;
+    decode(s, i, second, j);
+    const int64_t line = blockIdx.x + i * (int64_t)gridDim.x;
+    cplx* b = bufs[s & 1];
+    uint64_t* bar = &full[s & 1];
+    const bool bfly = (second != first_is_bfly);
+    // the first kind reads the caller's input (streaming), the second kind reads the parked intermediate in `out`
+    const cplx* src = (second ? out : in) + line * N;
+    const uint64_t pol = second ? pol_keep : pol_stream;
+    mbar_expect_tx(bar, PD_TMA_BUF);
+    if (bfly) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) bulk_g2s(b + m * J, src + (int64_t)m * Q + j * J, J * 16, bar, pol);
+    } else {
+      bulk_g2s(b, src + (int64_t)j * Q, Q * 16, bar, pol);
+    }
+  };
+  auto issue_store = [&](int64_t s) {  // thread 0 only
+    int64_t i; bool second; int j;
+    decode(s, i, second, j);
+    const int64_t line = blockIdx.x + i * (int64_t)gridDim.x;
+    cplx* b = bufs[s & 1];
+    const bool bfly = (second != first_is_bfly);
+    cplx* dst = out + line * N;
+    const uint64_t pol = second ? pol_stream : pol_keep;  // first kind writes the parked intermediate
+    if (bfly) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) bulk_s2g(dst + (int64_t)m * Q + j * J, b + m * J, J * 16, pol);
+    } else {
+      bulk_s2g(dst + (int64_t)j * Q, b, Q * 16, pol);
+    }
+    bulk_commit();
+  };
+
+  if (t == 0) {
+    issue_load(0);
+    if (total > 1 && issue_at(1) < 0) issue_load(1);
+  }
+  for (int64_t s = 0; s < total; ++s) {
+    int64_t li; bool second; int j;
+    decode(s, li, second, j);
+    cplx* b = bufs[s & 1];
+    mbar_wait(&full[s & 1], (uint32_t)((s >> 1) & 1));
+    const bool bfly = (second != first_is_bfly);
+    if (bfly) {
+      if (TO_FREQ) {
+        // y_q[jJ + n] = w^{(jJ+n) q} sum_m x[jJ + n + Q m] (-i)^{mq}, in place: slot [m][n] -> slot [q][n]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          cplx v[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            cplx x = b[m * J + T * u + t];
+            if (INV) x.y = -x.y;
+            v[m] = x;
+          }
+          dft_pow2<4>(v);
+          const cplx w1 = tw[j * J + T * u + t];
+          const cplx w2 = cmul(w1, w1);
+          v[1] = cmul(v[1], w1);
+          v[2] = cmul(v[2], w2);
+          v[3] = cmul(v[3], cmul(w2, w1));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) b[q * J + T * u + t] = v[q];
+        }
+      } else {
+        // x[n' + Q m] = sum_q (-i)^{mq} w^{n'q} Z_q[n'], n' = jJ + n, in place: slot [q][n] -> slot [m][n]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = j * J + T * u + t;
+          cplx v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = b[q * J + T * u + t];
+          const cplx w1 = tw[n];
+          const cplx w2 = cmul(w1, w1);
+          v[1] = cmul(v[1], w1);
+          v[2] = cmul(v[2], w2);
+          v[3] = cmul(v[3], cmul(w2, w1));
+          dft_pow2<4>(v);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            cplx y = v[m];
+            if (INV) y.y = -y.y;
+            b[m * J + T * u + t] = cscale(y, scale);
+          }
+        }
+      }
+    } else {
+      cplx io[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        cplx x = b[t + T * r];
+        if (!TO_FREQ && INV) x.y = -x.y;
+        io[r] = x;
+      }
+      pow2_pass<16, false, true, false, true, false>(nullptr, nullptr, X, tw_q, Q, 1, t, T, 1.0, true, io);
+      pow2_pass<16, false, false, false>(nullptr, nullptr, X, tw_q, Q, 16, t, T, 1.0, true);
+      pow2_pass<16, false, false, true, false, true>(nullptr, nullptr, X, tw_q, Q, 256, t, T, 1.0, true, io);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        cplx y = io[r];
+        if (TO_FREQ) {
+          if (INV) y.y = -y.y;
+          y = cscale(y, scale);
+        }
+        b[t + T * r] = y;
+      }
+    }
+    fence_proxy_async();  // this thread's shared-memory writes become visible to the bulk-copy engine
+    __syncthreads();      // ... of every thread; also: all reads of X are done before the next FFTQ stage writes it
+    if (t == 0) {
+      issue_store(s);
+      bulk_wait_read0();  // the engine has read buffer s & 1: it may be refilled
+      // loads whose turn it is: stage s+1 (if its dependency delayed it) and stage s+2
+      for (int64_t s2 = s + 1; s2 <= s + 2 && s2 < total; ++s2) {
+        if (issue_at(s2) != s) continue;
+        int64_t i2; bool sec2; int j2;
+        decode(s2, i2, sec2, j2);
+        if (sec2) {  // its input = the stores of the first kind of the same line: complete, not merely issued
+          if (s - last_first(i2) >= 1) bulk_wait1(); else bulk_wait0();
+        }
+        issue_load(s2);
+      }
+    }
+  }
+  if (t == 0) bulk_wait0();  // the last stores have left shared memory and reached global memory
+}
+
 // ------------------------------------------------------------ real-input fast path
 // The Krylov vectors of this (real) optimal-control problem are real, so their time spectra are
 // Hermitian and the frequencies k = 0..N_t/2 suffice: half the bytes in every stage.  A real line of
@@ -592,9 +827,15 @@ int pd_fft_plan(pd_handle* h) {
                                  (int)smem));
     PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_l2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PD_TMA_SMEM));
+    PD_CUDA(cudaFuncSetAttribute(pd_fft_16k_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PD_TMA_SMEM));
     {
+      // PD_FFT16K = l2 (default) | tma | cluster
       const char* env = getenv("PD_FFT16K");
-      h->fft16k_l2 = !(env && env[0] == 'c');  // default: the cluster-free kernel; PD_FFT16K=cluster selects the other
+      h->fft16k_l2 = !(env && env[0] == 'c');
+      h->fft16k_tma = (env && env[0] == 't') ? 1 : 0;
     }
     // co-resident 4-CTA clusters (GPC boundaries keep this a little below num_sms * 2 / 4: 71 on B200)
     cudaLaunchConfig_t lc = {};
@@ -684,6 +925,18 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
   const double scale = inverse ? 1.0 / (double)PD_BIGN : 1.0;
   // inverse (time -> frequency, :500-501) leaves the permuted frequency order, forward (:547-548) consumes it.
   const size_t smem = (size_t)(PD_BIGN / 4 + PD_BIGN / 64) * sizeof(cplx);
+  if (h->fft16k_tma && !gam) {
+    const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms ? nlines : (int64_t)h->num_sms);
+    if (inverse)
+      pd_fft_16k_tma_kernel<true, true><<<grid, 256, PD_TMA_SMEM, st>>>(in, out, nlines, h->twiddle, h->twiddle_quarter,
+                                                                        scale);
+    else
+      pd_fft_16k_tma_kernel<false, false><<<grid, 256, PD_TMA_SMEM, st>>>(in, out, nlines, h->twiddle,
+                                                                         h->twiddle_quarter, scale);
+    PD_CHECK_LAUNCH();
+    h->launches++;
+    return PD_OK;
+  }
   if (h->fft16k_l2) {
     const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
     if (inverse && !gam)

@@ -37,7 +37,7 @@ def rand_x(size, seed=0, real=False):
 
 
 # ---------------------------------------------------------------------------- time-axis FFT
-@pytest.mark.parametrize("variant", ["l2", "cluster"])
+@pytest.mark.parametrize("variant", ["l2", "cluster", "tma"])
 def test_fft_16384_both_kernels_many_lines(variant, monkeypatch):
     # both N_t = 16384 kernels (cluster-free default, 4-CTA cluster), enough lines for every persistent CTA to
     # loop: out of place and in place.  (A remote store overtaking a not-yet-performed shared-memory load in
