@@ -298,7 +298,7 @@ int pd_rhs_launch(pd_handle* h, cplx* b, cudaStream_t st, int real_vectors) {
 
 // ------------------------------------------------------------- BLAS-1 kernels
 #define PD_RED_THREADS 256
-#define PD_MAXB 8  // basis vectors handled per launch
+#define PD_MAXB 16  // basis vectors handled per launch (w is re-read once per batch)
 
 struct VecBatch {
   const cplx* v[PD_MAXB];
@@ -464,7 +464,15 @@ static int mdot_list(pd_handle* h, const cplx* const* vs, int nv, const cplx* w,
       case 5: rc = mdot_batch<5>(h, v, w, len, out + base, st); break;
       case 6: rc = mdot_batch<6>(h, v, w, len, out + base, st); break;
       case 7: rc = mdot_batch<7>(h, v, w, len, out + base, st); break;
-      default: rc = mdot_batch<8>(h, v, w, len, out + base, st); break;
+      case 8: rc = mdot_batch<8>(h, v, w, len, out + base, st); break;
+      case 9: rc = mdot_batch<9>(h, v, w, len, out + base, st); break;
+      case 10: rc = mdot_batch<10>(h, v, w, len, out + base, st); break;
+      case 11: rc = mdot_batch<11>(h, v, w, len, out + base, st); break;
+      case 12: rc = mdot_batch<12>(h, v, w, len, out + base, st); break;
+      case 13: rc = mdot_batch<13>(h, v, w, len, out + base, st); break;
+      case 14: rc = mdot_batch<14>(h, v, w, len, out + base, st); break;
+      case 15: rc = mdot_batch<15>(h, v, w, len, out + base, st); break;
+      default: rc = mdot_batch<16>(h, v, w, len, out + base, st); break;
     }
     if (rc) return rc;
   }
@@ -510,7 +518,15 @@ static int maxpy_list(pd_handle* h, const cplx* const* vs, int nv, const cplx* c
       case 5: rc = maxpy_batch<5>(h, v, cf, sign, w, len, norm, norm_out, st); break;
       case 6: rc = maxpy_batch<6>(h, v, cf, sign, w, len, norm, norm_out, st); break;
       case 7: rc = maxpy_batch<7>(h, v, cf, sign, w, len, norm, norm_out, st); break;
-      default: rc = maxpy_batch<8>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 8: rc = maxpy_batch<8>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 9: rc = maxpy_batch<9>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 10: rc = maxpy_batch<10>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 11: rc = maxpy_batch<11>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 12: rc = maxpy_batch<12>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 13: rc = maxpy_batch<13>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 14: rc = maxpy_batch<14>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      case 15: rc = maxpy_batch<15>(h, v, cf, sign, w, len, norm, norm_out, st); break;
+      default: rc = maxpy_batch<16>(h, v, cf, sign, w, len, norm, norm_out, st); break;
     }
     if (rc) return rc;
   }

@@ -457,11 +457,22 @@ pd_iface_pivots_kernel(SolveParams sp, cplx* __restrict__ piv) {
   }
 }
 
+// thread = (frequency, right-hand side): a half-warp owns 16 consecutive frequencies of one right-hand side, so every
+// row access is a contiguous 256-byte segment.  Three batches of PD_IT rows rotate through registers: while batch b
+// is being eliminated the loads of batches b+1 and b+2 are in flight (the kernel runs one warp per scheduler, nothing
+// else hides the latency of its loads).
+#define PD_ITK 64  // frequencies per CTA of the sequential interface kernel (2 threads each)
+struct IfaceBatch {
+  cplx r[PD_IT], f[PD_IT], m[PD_IT];
+};
 template <bool PUSH>
-__global__ void __launch_bounds__(PD_KB)
+__global__ void __launch_bounds__(2 * PD_ITK)
 pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
                              SlabPtrs sl, SlabCommDev cm) {
-  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int rhs = lane >> 4;                                         // 0: the + system, 1: the (conjugated) - system
+  const int k0 = sp.koff + blockIdx.x * PD_ITK;
+  const int kk = k0 + wrp * 16 + (lane & 15);
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
   if (kk < sp.kend) {
     const KCoef kc = make_coef(freq_of(sp, kk), sp);
@@ -469,83 +480,101 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
     const Sys s = reduce_sys(below, PD_L);
     const int64_t K = sp.K;
     const int P = sp.rows[1];
-    cplx* R = lv.R[1] + kk;
-    const cplx* F = lv.F[0] + kk;
+    cplx* R = lv.R[1] + (int64_t)rhs * K + kk;
+    const cplx* F = lv.F[0] + (int64_t)rhs * K + kk;
     const cplx* M = piv + kk;
-    cplx dP = cmake(0, 0), dM = cmake(0, 0);
-    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q.  Double-buffered batches of PD_IT rows: the loads of batch
-    // b+1 are in flight while the dependent recurrences of batch b run.
-    cplx rP[PD_IT], rM[PD_IT], fP[PD_IT], fM[PD_IT], mq[PD_IT];
-    auto load_fwd = [&](int q0, cplx* aP, cplx* aM, cplx* bP, cplx* bM, cplx* am) {
+    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q,  rhs_q = R[q] - off_below F[q+1]
+    auto load_fwd = [&](IfaceBatch& b, int q0) {
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = min(q0 + i, P - 1);
-        aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
-        bP[i] = F[((q + 1) * 2) * K]; bM[i] = F[((q + 1) * 2 + 1) * K];
-        am[i] = M[q * K];
+        b.r[i] = R[(q * 2) * K];
+        b.f[i] = F[((q + 1) * 2) * K];
+        b.m[i] = M[q * K];
       }
     };
-    load_fwd(0, rP, rM, fP, fM, mq);
-    for (int q0 = 0; q0 < P; q0 += PD_IT) {
-      cplx nrP[PD_IT], nrM[PD_IT], nfP[PD_IT], nfM[PD_IT], nmq[PD_IT];
-      load_fwd(q0 + PD_IT, nrP, nrM, nfP, nfM, nmq);
-      cplx gP[PD_IT], gM[PD_IT];
+    cplx d = cmake(0, 0);
+    auto elim = [&](const IfaceBatch& b, int q0) {
+      cplx g[PD_IT];
 #pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        gP[i] = cfms(below.off, fP[i], rP[i]);
-        gM[i] = cfms(below.off, fM[i], rM[i]);
-      }
+      for (int i = 0; i < PD_IT; ++i) g[i] = cfms(below.off, b.f[i], b.r[i]);
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = q0 + i;
         if (q < P) {
-          dP = cmul(cfms(s.off, dP, gP[i]), mq[i]);
-          dM = cmul(cfms(s.off, dM, gM[i]), mq[i]);
-          R[(q * 2) * K] = dP; R[(q * 2 + 1) * K] = dM;
+          d = cmul(cfms(s.off, d, g[i]), b.m[i]);
+          R[(q * 2) * K] = d;
         }
       }
-#pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        rP[i] = nrP[i]; rM[i] = nrM[i]; fP[i] = nfP[i]; fM[i] = nfM[i]; mq[i] = nmq[i];
-      }
+    };
+    IfaceBatch b0, b1, b2;
+    load_fwd(b0, 0);
+    load_fwd(b1, PD_IT);
+    for (int q0 = 0; q0 < P; q0 += 3 * PD_IT) {
+      load_fwd(b2, q0 + 2 * PD_IT);
+      elim(b0, q0);
+      load_fwd(b0, q0 + 3 * PD_IT);
+      elim(b1, q0 + PD_IT);
+      load_fwd(b1, q0 + 4 * PD_IT);
+      elim(b2, q0 + 2 * PD_IT);
     }
     // ---- backward: z_q = d_q - off m_q z_{q+1}
-    const cplx zeP = dP, zeM = dM;
-    cplx zP = dP, zM = dM;
-    cplx eP[PD_IT], eM[PD_IT], mm[PD_IT];
-    auto load_bwd = [&](int q0, cplx* aP, cplx* aM, cplx* am) {
+    const cplx ze = d;
+    cplx z = d;
+    auto load_bwd = [&](IfaceBatch& b, int q0) {
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = max(q0 - i, 0);
-        aP[i] = R[(q * 2) * K]; aM[i] = R[(q * 2 + 1) * K];
-        am[i] = M[q * K];
+        b.r[i] = R[(q * 2) * K];
+        b.m[i] = M[q * K];
       }
     };
-    load_bwd(P - 2, eP, eM, mm);
-    for (int q0 = P - 2; q0 >= 0; q0 -= PD_IT) {
-      cplx neP[PD_IT], neM[PD_IT], nmm[PD_IT];
-      load_bwd(q0 - PD_IT, neP, neM, nmm);
+    auto subst = [&](const IfaceBatch& b, int q0) {
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
         const int64_t q = q0 - i;
         if (q >= 0) {
-          const cplx cp = cmul(s.off, mm[i]);
-          zP = cfms(cp, zP, eP[i]);
-          zM = cfms(cp, zM, eM[i]);
-          R[(q * 2) * K] = zP; R[(q * 2 + 1) * K] = zM;
+          z = cfms(cmul(s.off, b.m[i]), z, b.r[i]);
+          R[(q * 2) * K] = z;
         }
       }
-#pragma unroll
-      for (int i = 0; i < PD_IT; ++i) { eP[i] = neP[i]; eM[i] = neM[i]; mm[i] = nmm[i]; }
+    };
+    load_bwd(b0, P - 2);
+    load_bwd(b1, P - 2 - PD_IT);
+    for (int q0 = P - 2; q0 >= 0; q0 -= 3 * PD_IT) {
+      load_bwd(b2, q0 - 2 * PD_IT);
+      subst(b0, q0);
+      load_bwd(b0, q0 - 3 * PD_IT);
+      subst(b1, q0 - PD_IT);
+      load_bwd(b1, q0 - 4 * PD_IT);
+      subst(b2, q0 - 2 * PD_IT);
     }
     if (PUSH) {
-      cplx fP, fM, lP, lM, sP, sM;
-      slab_functionals(kc, sp, w, kk, lv.F[0][kk], lv.F[0][K + kk], sl.lastl[kk], sl.lastl[K + kk], zP, zM, zeP, zeM,
-                       fP, fM, lP, lM, sP, sM);
-      slab_push(cm, ep, kk, fP, fM, lP, lM, sP, sM);
+      // this thread's half of the slab functionals (see slab_functionals): first / last entry of the slab-local
+      // solve and the rotated right-hand side of the separator row, for its own right-hand side
+      const int Llast = sp.m - P * (PD_L + 1);
+      VRec v;
+      v.init(kc.a, kc.sh, cmake(0, 0));
+      cplx rvL = cmake(0, 0), rvLl = cmake(0, 0);
+      if (!v.diag) {
+        for (int i = 1; i <= PD_L; ++i) {
+          v.step();
+          if (i == Llast) rvLl = cscale(crcp(v.V), v.one);
+        }
+        rvL = cscale(crcp(v.V), v.one);
+      }
+      const cplx fv = cfma(z, rvL, lv.F[0][(int64_t)rhs * K + kk]);
+      const cplx lvv = Llast > 0 ? cfma(ze, rvLl, sl.lastl[(int64_t)rhs * K + kk]) : ze;
+      cplx sP = cmake(0, 0), sM = cmake(0, 0);
+      if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+      const int64_t slot = (((int64_t)(ep & 1ull) * cm.G + cm.rank) * 6 + rhs) * cm.kmax + kk;
+      for (int p = 0; p < cm.G; ++p) {
+        cplx* g = cm.peer_gath[p] + slot;
+        g[0] = fv; g[2 * cm.kmax] = lvv; g[4 * cm.kmax] = rhs ? sM : sP;
+      }
     }
   }
-  if (PUSH) slab_publish(cm, ep, sp.koff + blockIdx.x * PD_KB, min(PD_KB, sp.kend - sp.koff - blockIdx.x * PD_KB));
+  if (PUSH) slab_publish(cm, ep, k0, min(PD_ITK, sp.kend - k0));
 }
 
 // ------------------------------------------------------------------- pass B
@@ -941,16 +970,16 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   const int ncol = sp.kend - sp.koff;
   const cplx* piv = plan_of(h)->ipiv[sp.K == h->kcount ? 0 : 1];
   if (piv) {
-    const int nblk = (ncol + PD_KB - 1) / PD_KB;
+    const int nblk = (ncol + PD_ITK - 1) / PD_ITK;
     if (push) {
-      pd_solve_iface_thomas_kernel<true><<<nblk, PD_KB, 0, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
+      pd_solve_iface_thomas_kernel<true><<<nblk, 2 * PD_ITK, 0, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
       if (pushed) *pushed = true;
     } else {
       SlabPtrs nosl;
       SlabCommDev nocm;
       memset(&nosl, 0, sizeof(nosl));
       memset(&nocm, 0, sizeof(nocm));
-      pd_solve_iface_thomas_kernel<false><<<nblk, PD_KB, 0, st>>>(lv, sp, piv, nullptr, nosl, nocm);
+      pd_solve_iface_thomas_kernel<false><<<nblk, 2 * PD_ITK, 0, st>>>(lv, sp, piv, nullptr, nosl, nocm);
     }
     PD_CHECK_LAUNCH();
     h->launches++;

@@ -94,3 +94,35 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def _header_config_fields():
+    """(name, C type, array length) of every member of `struct pd_config` in include/paradiag.h."""
+    import re
+    src = open(os.path.join(ROOT, "include", "paradiag.h")).read()
+    body = src[src.index("typedef struct pd_config {"):src.index("} pd_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for m in re.finditer(r"\b(int32_t|double)\s+(\w+)(?:\[(\d+)\])?\s*;", body):
+        out.append((m.group(2), m.group(1), int(m.group(3)) if m.group(3) else 0))
+    return out
+
+
+def test_pd_config_mirrors_match_the_header_field_for_field():
+    # the ctypes mirror of the package AND the inline stub of INTEGRATION.md section 2 against include/paradiag.h
+    import ctypes as C
+    import re
+    fields = _header_config_fields()
+    assert [f[0] for f in fields][:4] == ["abi_version", "N_x", "N_t", "bug138"] and fields[-1][0] == "reserved"
+    ctype = {"int32_t": C.c_int32, "double": C.c_double}
+    want = [(n, ctype[t] * ln if ln else ctype[t]) for n, t, ln in fields]
+    got = list(_lib.pd_config._fields_)
+    assert [g[0] for g in got] == [w[0] for w in want]
+    for (gn, gt), (wn, wt) in zip(got, want):
+        assert C.sizeof(gt) == C.sizeof(wt), gn
+    # INTEGRATION.md: the names inside its `_fields_ = [...]` list, in order
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class pd_config(C.Structure):"):doc.index("lib = C.CDLL(")]
+    names = re.findall(r'\("(\w+)",\s*C\.c_(?:int32|double)(?:\s*\*\s*(\d+))?\)', stub)
+    assert [n for n, _ in names] == [f[0] for f in fields]
+    assert [int(l) if l else 0 for _, l in names] == [f[2] for f in fields]
