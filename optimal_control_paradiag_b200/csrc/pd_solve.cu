@@ -1058,13 +1058,14 @@ int pd_solve_plan(pd_handle* h) {
   }
   // interface systems of up to this many rows go to the one-launch sequential kernel (pd_solve_iface_thomas_kernel);
   // PD_ITHOMAS_MAX overrides (0 = never)
-  // Measured on B200 (tools/scale_probe.py, K = 4096): the sequential kernel costs 0.42 us per interface row
-  // whatever the arithmetic (one warp per scheduler: latency-bound), i.e. 45 us at 120 rows (N_x = 2048), where the
-  // reduce / PCR / back chain takes 52 us plus, in slab mode, 24 us for the separate functionals launch; at 240
-  // rows the two are equal (88 vs 83 us), beyond that the multi-level chain wins (481 rows: 194 vs 135 us, 963 rows:
-  // 412 vs 205 us), and a single PCR launch (<= 128 rows at K <= 2048) beats it as well.  Hence: x-slabs of a
-  // multi-GPU run up to 300 rows, single-GPU handles up to 160 rows when the alternative is a multi-launch chain.
-  h->iface_thomas_max = h->slab_count > 1 ? 300 : 160;
+  // Measured on B200 (tools/scale_probe.py, K = 4096, interface rows 120 / 240 / 481 / 963 = N_x 2048 ... 16384):
+  //   reduce / PCR / back chain (3-5 launches)   52 /  83 / 137 / 205 us   (+ 24 us for the slab functionals launch)
+  //   sequential kernel, cp.async ring           30 /  50 /  98 / 169 us   (functionals and peer stores included)
+  //   (its first versions: one register batch in flight 45 / 88 / 194 / 412 us, two batches 39 / 73 / 150 / 308 us;
+  //    a single PCR launch on 120 rows: 233 us)
+  // so the sequential kernel is the default whenever the interface has more than one PCR launch's worth of rows;
+  // PD_ITHOMAS_MAX overrides (0 = never).
+  h->iface_thomas_max = 8192;
   if (const char* e = getenv("PD_ITHOMAS_MAX")) h->iface_thomas_max = atoi(e);
   if (h->kcount != h->cfg.N_t) h->iface_thomas_max = 0;  // frequency-sharded handles keep the multi-level path
   pl->rows[0] = h->m;
@@ -1097,7 +1098,7 @@ int pd_solve_plan(pd_handle* h) {
   }
   // one-launch sequential interface (pd_solve_iface_thomas_kernel): factorise the level-1 system once
   if (pl->nlev >= 1 && h->iface_thomas_max > 0 && pl->rows[1] <= h->iface_thomas_max &&
-      (pl->nlev >= 2 || h->slab_count > 1 || getenv("PD_ITHOMAS_MAX"))) {
+      (pl->rows[1] > PD_PCR_MAX || h->slab_count > 1 || getenv("PD_ITHOMAS_MAX"))) {
     const bool want_half = pd_rfft_supported(h) && h->cfg.alpha == 1.0;
     for (int half = 0; half <= (want_half ? 1 : 0); ++half) {
       SolveParams sp; Levels lv; SlabPtrs sl;

@@ -538,3 +538,21 @@ def test_gmres_residual_correction_mode(N_x, N_t, gamma):
             xr, its_r, _, rr = h.gmres_real(h.build_rhs_real(), rtol=1e-7, max_it=80, correction=True)
             assert rr == "CONVERGED_RTOL" and abs(its_r - its1) <= 1
             assert rel(xr.cpu().numpy(), x1.cpu().numpy().real) < 1e-5
+
+
+# ------------------------------------------- the two interface solvers give the same answer
+@pytest.mark.parametrize("N_x,N_t,gamma", [(600, 64, 1.0), (1024, 1024, 1.0), (4096, 128, 1.0), (9600, 8, 1.0),
+                                           (16384, 12, 1e-2), (65536, 4, 1.0)])
+def test_multilevel_and_sequential_interface_solvers_agree(N_x, N_t, gamma, monkeypatch):
+    # default: the one-launch sequential interface kernel (plan-time pivots, cp.async ring); PD_ITHOMAS_MAX=0: the
+    # recursive reduce / PCR / back chain.  Both against the 80-bit oracle, and against each other.
+    x = rand_x(2 * (N_x + 1) * N_t)
+    truth = DiagFFTPCFast(N_x, N_t, 2.0, gamma, dtype=np.longdouble).apply(x)
+    ys = []
+    for mode in ("8192", "0"):
+        monkeypatch.setenv("PD_ITHOMAS_MAX", mode)
+        with ParaDiagHandle(N_x, N_t, gamma=gamma) as h:
+            y = h.pc_apply_host(x)
+            assert float(np.linalg.norm(y - truth) / np.linalg.norm(truth)) < 1e-10, mode
+            ys.append(y)
+    assert rel(ys[0], ys[1]) < 1e-11
