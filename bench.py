@@ -438,14 +438,15 @@ def run_ours(args):
         # algorithmic bytes per launch: each FFT pass and the solve pass read S and write S;
         # the solve pass is pass A + interface + pass B, of which pass B carries the read+write sweep
         dom = max(prof, key=prof.get)
-        alg = {"ifft": 2 * S, "fft": 2 * S, "passB": 2 * S, "passA": S, "pcr": 0.3 * S}[dom]
+        alg = {"ifft": 2 * S, "fft": 2 * S, "passB": 2 * S, "passA": S, "interface": 0.3 * S}[dom]
         fftk = "pd_fft_16k_l2_kernel" if N_t == 16384 else ("pd_fft_pow2_kernel" if (N_t & (N_t - 1)) == 0 and N_t >= 64
                                                          else "pd_fft_generic_kernel")
         names = {"ifft": fftk + "<inv>", "fft": fftk + "<fwd>", "passA": "pd_solve_passA_kernel",
-                 "pcr": "pd_solve interface kernels", "passB": "pd_solve_passB_kernel"}
+                 "interface": "pd_solve_iface_thomas_kernel", "passB": "pd_solve_passB_kernel"}
         ach = alg / (prof[dom] * 1e-3) / 1e9
         key = {"ifft": "pd_fft_pow2_kernel<16, 16, 16, 1, 1>", "fft": "pd_fft_pow2_kernel<16, 16, 16, 1, 0>",
-               "passA": "pd_solve_passA_kernel", "passB": "pd_solve_passB_kernel", "pcr": "pd_solve_pcr_kernel"}[dom]
+               "passA": "pd_solve_passA_kernel", "passB": "pd_solve_passB_kernel",
+               "interface": "pd_solve_iface_thomas_kernel"}[dom]
         traffic, prov = ncu_traffic(args.workload, key)
         line["roofline"] = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": traffic, "traffic_provenance": prov,

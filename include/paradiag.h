@@ -114,7 +114,7 @@ int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream)
 int pd_stage_rfft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int to_freq, void* stream);
 int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream);
 /* One apply with CUDA events recorded on `stream` between its kernels; ms[0..4] receive
- * the device durations (milliseconds) of {inverse FFT, solve pass A, interface PCR, solve
+ * the device durations (milliseconds) of {inverse FFT, solve pass A, interface solve, solve
  * pass B, forward FFT}.  Synchronises the stream.  Measurement aid for bench.py.           */
 int pd_pc_apply_profile(pd_handle* h, const void* x_dev, void* y_dev, void* stream, float* ms,
                         int nms);

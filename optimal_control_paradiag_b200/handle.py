@@ -130,7 +130,7 @@ class ParaDiagHandle:
         ms = (C.c_float * 5)()
         check(self.lib.pd_pc_apply_profile(self._h, self._ptr(x, self.size, "x"), self._ptr(y, self.size, "y"),
                                            self._stream(), ms, 5))
-        return dict(zip(("ifft", "passA", "pcr", "passB", "fft"), [float(v) for v in ms]))
+        return dict(zip(("ifft", "passA", "interface", "passB", "fft"), [float(v) for v in ms]))
 
     def pc_apply_host(self, x, y=None):
         """Same through host buffers (numpy complex128): H2D, apply, D2H."""
