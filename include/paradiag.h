@@ -199,6 +199,10 @@ int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 int pd_matvec_slab(pd_handle* h, const void* x_dev, const void* halo_lo_dev, const void* halo_hi_dev,
                    void* y_dev, void* stream);
 
+/* The same for float64 blocks (2 n_r N_t doubles; halos 2 N_t doubles) -- the float64 distributed Krylov loop.       */
+int pd_matvec_slab_real(pd_handle* h, const void* x_dev, const void* halo_lo_dev, const void* halo_hi_dev,
+                        void* y_dev, void* stream);
+
 /* y = P x for the block-circulant matrix P that DiagFFTPC inverts (the operator above
  * with the time stencils of :121, :137 made periodic -- C1, C2 of mat_test.ipynb cells
  * 8-9 -- and the half weights :117, :143 and the :138 factor replaced by 1).  Lets a
@@ -222,6 +226,7 @@ int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double a
              void* stream);
 
 /* Run-time options of a handle.  "host_register" (default 0): see pd_pc_apply_host.
+ * "krylov_real_vectors" (default 0): pd_mdot / pd_maxpy are handed float64 vectors viewed as complex pairs.
  * "slab_overlap" (default 1): pd_slab_apply runs the per-frequency stage as two frequency halves on two streams so
  * that the latency-bound interface / separator kernels of one half overlap the streaming passes of the other; 0
  * keeps everything on the caller's stream (needed when one process drives several ranks on one GPU).

@@ -67,6 +67,7 @@ SYMBOLS = {
     "pd_slab_apply_profile": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_float), _I]),
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec_slab": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_matvec_slab_real": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),
     "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),

@@ -823,6 +823,17 @@ extern "C" int pd_matvec_slab(pd_handle* h, const void* x_dev, const void* halo_
                           (const cplx*)halo_hi_dev);
 }
 
+extern "C" int pd_matvec_slab_real(pd_handle* h, const void* x_dev, const void* halo_lo_dev, const void* halo_hi_dev,
+                                   void* y_dev, void* stream) {
+  if (!h || !x_dev || !y_dev || x_dev == y_dev || h->slab_count <= 1) {
+    pd_set_error("pd_matvec_slab_real: invalid argument or handle not in slab mode");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  return pd_matvec_launch(h, (const cplx*)x_dev, (cplx*)y_dev, (cudaStream_t)stream, 0, (const cplx*)halo_lo_dev,
+                          (const cplx*)halo_hi_dev, 1);
+}
+
 extern "C" int pd_pc_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
   if (!h || !x_dev || !y_dev || x_dev == y_dev) {
     pd_set_error("pd_pc_matvec: invalid argument (x and y must be distinct device vectors)");

@@ -147,6 +147,7 @@ struct pd_handle {
   int kry_d_mode;   // 0: not initialised, 1: complex layout, 2: float64 layout
   int opt_gmres_correction;  // pd_set_option "gmres_residual_correction"
   int opt_slab_no_overlap;   // pd_set_option "slab_overlap" 0: the slab apply stays on the caller's stream
+  int opt_kry_real;          // pd_set_option "krylov_real_vectors"
   int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;

@@ -542,7 +542,7 @@ extern "C" int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, cons
   PD_ON_DEVICE(h);
   std::vector<const cplx*> vs(nv);
   for (int i = 0; i < nv; ++i) vs[i] = (const cplx*)V_dev + (int64_t)i * ld;
-  h->kry_real = 0;
+  h->kry_real = h->opt_kry_real;  // float64 vectors seen as complex pairs: only the real part of the sums is meaningful
   return mdot_list(h, vs.data(), nv, (const cplx*)w_dev, len, (cplx*)out_dev, (cudaStream_t)stream);
 }
 
@@ -827,6 +827,8 @@ extern "C" int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, doubl
 
 // Run-time options of a handle (name, value).  Unknown names are an error.
 //   "gmres_residual_correction" : 0 (default) pd_gmres forms P^-1 (A v) as KSP does; 1: v + P^-1 ((A - P) v)
+//   "krylov_real_vectors"       : 0 (default); 1: pd_mdot treats its vectors as float64 data in complex pairs (the
+//                                 imaginary parts of the sums are zeroed) -- the float64 distributed Krylov loop
 //   "slab_overlap"              : 1 (default): pd_slab_apply runs its two frequency halves on two streams; 0: one stream
 //   "host_register"             : 0 (default); 1: pd_pc_apply_host page-locks each host buffer once (see pd_capi.cu)
 extern "C" int pd_set_option(pd_handle* h, const char* name, double value) {
@@ -836,6 +838,10 @@ extern "C" int pd_set_option(pd_handle* h, const char* name, double value) {
   }
   if (!strcmp(name, "gmres_residual_correction")) {
     h->opt_gmres_correction = value != 0.0;
+    return PD_OK;
+  }
+  if (!strcmp(name, "krylov_real_vectors")) {
+    h->opt_kry_real = value != 0.0;
     return PD_OK;
   }
   if (!strcmp(name, "slab_overlap")) {

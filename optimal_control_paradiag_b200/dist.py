@@ -267,8 +267,11 @@ class DistributedDiagFFTPC:
         return y_host
 
     # ------------------------------------------------------------------ distributed Krylov solve
-    def build_rhs(self):
-        """This rank's block of the manufactured right-hand side (Build_f/g/IC, :48-83)."""
+    def build_rhs(self, real=False):
+        """This rank's block of the manufactured right-hand side (Build_f/g/IC, :48-83); ``real``: float64."""
+        if real:
+            b = self.torch.empty(self.local_size, dtype=self.torch.float64, device=self.device)
+            return self.backend.build_rhs_real(b)
         b = self.torch.empty(self.local_size, dtype=self.torch.complex128, device=self.device)
         return self.backend.build_rhs(b)
 
@@ -290,48 +293,85 @@ class DistributedDiagFFTPC:
         self._halo_keepalive = alle
         return self.backend.matvec_slab(x_local.reshape(-1), lo, hi, y_local.reshape(-1))
 
+    def matvec_real(self, x_local, y_local=None):
+        """``matvec`` for float64 node-slab blocks (the real problem): same halo exchange on float64 rows."""
+        t = self.torch
+        if self.mode != "slab":
+            raise NotImplementedError("the distributed matvec / GMRES use the slab decomposition")
+        if y_local is None:
+            y_local = t.empty_like(x_local)
+        X = x_local.view(2, self.n_r, self.N_t)
+        edges = t.stack([X[:, 0, :], X[:, -1, :]]).contiguous()
+        alle = t.empty((self.world,) + tuple(edges.shape), dtype=edges.dtype, device=self.device)
+        self.dist.all_gather_into_tensor(alle.reshape(-1), edges.reshape(-1), group=self.group)
+        lo = alle[self.rank - 1, 1].reshape(-1) if self.rank > 0 else None
+        hi = alle[self.rank + 1, 0].reshape(-1) if self.rank < self.world - 1 else None
+        self._halo_keepalive = alle
+        return self.backend.matvec_slab_real(x_local.reshape(-1), lo, hi, y_local.reshape(-1))
+
     def _allreduce(self, v):
         self.dist.all_reduce(self.torch.view_as_real(v), group=self.group)
         return v
 
-    def gmres(self, b_local, rtol=1e-7, atol=1e-50, restart=300, max_it=1000):
+    def gmres(self, b_local, rtol=1e-7, atol=1e-50, restart=300, max_it=1000, real=None):
         """Left-preconditioned GMRES with the options of Control_Wave_PC.py:347-359 (classical
         Gram-Schmidt, zero initial guess, preconditioned-residual test) on slab-distributed vectors.
         Same arithmetic as pd_gmres; inner products are local pd_mdot + one all-reduce.
+        ``real`` (default: by the dtype of ``b_local``): float64 vectors, the half-spectrum preconditioner
+        ``apply_real`` and the float64 matvec -- half the bytes in every sweep (the problem is real).
         Returns (x_local, iterations, history, reason)."""
         t, be = self.torch, self.backend
+        if real is None:
+            real = b_local.dtype == t.float64
         c128, ln = t.complex128, self.local_size
-        x = t.zeros(ln, dtype=c128, device=self.device)
-        tmp = t.empty(ln, dtype=c128, device=self.device)
+        vdt = t.float64 if real else c128
+        esz = 8 if real else 16
+        x = t.zeros(ln, dtype=vdt, device=self.device)
+        tmp = t.empty(ln, dtype=vdt, device=self.device)
+        apply_fn = self.apply_real if real else self.apply
+        matvec_fn = self.matvec_real if real else self.matvec
+        # the BLAS-1 kernels see float64 vectors as complex pairs (only the real part of the sums is kept)
+        cv = (lambda v: t.view_as_complex(v.reshape(*v.shape[:-1], v.shape[-1] // 2, 2))) if real else (lambda v: v)
+        if real and hasattr(be, "set_option"):
+            be.set_option("krylov_real_vectors", 1)
         # Krylov basis in blocks of BS vectors, allocated as the iteration proceeds (a cfg3 vector is
         # 2.1 GB / G per rank: the restart length of 300 cannot be pre-allocated, SURVEY H7)
-        BS = max(1, min(8, (2 << 30) // (16 * ln)))      # ~2 GB per block
-        blocks = [t.empty((BS, ln), dtype=c128, device=self.device)]
+        BS = max(1, min(8, (2 << 30) // (esz * ln)))      # ~2 GB per block
+        blocks = [t.empty((BS, ln), dtype=vdt, device=self.device)]
 
         def vec(j):
             while j // BS >= len(blocks):
-                blocks.append(t.empty((BS, ln), dtype=c128, device=self.device))
+                blocks.append(t.empty((BS, ln), dtype=vdt, device=self.device))
             return blocks[j // BS][j % BS]
 
         def mdot_all(nv, w):
-            return t.cat([be.mdot(blocks[b][: min(BS, nv - b * BS)], w) for b in range((nv + BS - 1) // BS)])
+            return t.cat([be.mdot(cv(blocks[b][: min(BS, nv - b * BS)]), cv(w)) for b in range((nv + BS - 1) // BS)])
 
         def maxpy_all(nv, coef, sign, w, norm2_out=None):
             nb = (nv + BS - 1) // BS
             for b in range(nb):
                 cnt = min(BS, nv - b * BS)
-                be.maxpy(blocks[b][:cnt], coef[b * BS: b * BS + cnt], sign, w, norm2_out if b == nb - 1 else None)
+                be.maxpy(cv(blocks[b][:cnt]), coef[b * BS: b * BS + cnt], sign, cv(w), norm2_out if b == nb - 1 else None)
+        try:
+            return self._gmres_loop(b_local, x, tmp, vec, mdot_all, maxpy_all, apply_fn, matvec_fn, rtol, atol, restart,
+                                    max_it)
+        finally:
+            if real and hasattr(be, "set_option"):
+                be.set_option("krylov_real_vectors", 0)
+
+    def _gmres_loop(self, b_local, x, tmp, vec, mdot_all, maxpy_all, apply_fn, matvec_fn, rtol, atol, restart, max_it):
+        t, c128 = self.torch, self.torch.complex128
         hist, its, reason, first, converged = [], 0, "DIVERGED_ITS", True, False
         beta0 = target = 0.0
         hbuf = t.zeros(restart + 2, dtype=c128, device=self.device)
         while not converged and (its < max_it or first):
             v0 = vec(0)
             if first:
-                self.apply(b_local, v0)
+                apply_fn(b_local, v0)
             else:
-                self.matvec(x, tmp)
+                matvec_fn(x, tmp)
                 tmp.mul_(-1).add_(b_local)
-                self.apply(tmp, v0)
+                apply_fn(tmp, v0)
             beta = math.sqrt(self._allreduce(mdot_all(1, v0))[0].real.item())
             if first:
                 beta0, first = beta, False
@@ -350,8 +390,8 @@ class DistributedDiagFFTPC:
             jdone = 0
             for j in range(m):
                 w = vec(j + 1)
-                self.matvec(vec(j), tmp)
-                self.apply(tmp, w)
+                matvec_fn(vec(j), tmp)
+                apply_fn(tmp, w)
                 hd = self._allreduce(mdot_all(j + 1, w))                     # classical Gram-Schmidt
                 hbuf[: j + 1] = hd
                 maxpy_all(j + 1, hbuf, -1.0, w, hbuf[j + 1: j + 2])

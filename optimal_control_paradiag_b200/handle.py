@@ -273,6 +273,12 @@ class ParaDiagHandle:
                                       self._stream()))
         return y
 
+    def matvec_slab_real(self, x, halo_lo, halo_hi, y):
+        """pd_matvec_slab_real: float64 blocks, halos (2, N_t) float64 or None at the domain ends."""
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(self.lib.pd_matvec_slab_real(self._h, p(x), p(halo_lo), p(halo_hi), p(y), self._stream()))
+        return y
+
     def maxpy(self, V, coef, sign, w, norm2_out=None):
         """w += sign * sum_i coef[i] V[i] (pd_maxpy); V is (nv, len), coef a device tensor."""
         nv, ln = V.shape
@@ -342,9 +348,14 @@ class ParaDiagHandle:
         return y
 
     def build_rhs_real(self, b=None):
+        """float64 right-hand side; on an x-slab handle ``b`` is this rank's (2, n_r, N_t) block."""
         if b is None:
             b = self.empty_real()
-        check(self.lib.pd_build_rhs_real(self._h, self._rptr(b, "b"), self._stream()))
+        torch = _torch()
+        want = 2 * self.n_slab * self.N_t
+        if b.dtype != torch.float64 or not b.is_cuda or not b.is_contiguous() or b.numel() != want:
+            raise ValueError(f"b: need a contiguous float64 CUDA tensor with {want} entries")
+        check(self.lib.pd_build_rhs_real(self._h, C.c_void_p(b.data_ptr()), self._stream()))
         return b
 
     def gmres_real(self, b, x=None, rtol=1e-7, atol=1e-50, restart=300, max_it=1000, correction=False):

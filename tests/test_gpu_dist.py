@@ -76,7 +76,20 @@ def _gmres_worker(rank, world, port, N_x, N_t, ret):
             mv_err = float(torch.linalg.norm(mv - h.matvec(v)) / torch.linalg.norm(mv))
             xs, its_s, hist_s, reason_s = h.gmres(bg, rtol=1e-7)
             err = float(torch.linalg.norm(xg - xs) / torch.linalg.norm(xs))
-        ret[rank] = (its, its_s, reason, err, mv_err)
+        # the float64 solve (half-spectrum PC, float64 matvec and BLAS-1) on the same slab-distributed problem
+        real_ok = True
+        if N_t >= 128 and (N_t & (N_t - 1)) == 0:
+            br = dpc.build_rhs(real=True)
+            real_ok = bool(torch.equal(br, b.real))
+            vr = torch.randn(2 * (N_x + 1) * N_t, dtype=torch.float64, device=f"cuda:{rank}",
+                             generator=torch.Generator(device=f"cuda:{rank}").manual_seed(6))
+            mvr = dpc.matvec_real(dpc.scatter_from_global(vr))
+            mvc = dpc.matvec(dpc.scatter_from_global(vr.to(torch.complex128)))
+            real_ok = real_ok and bool(torch.equal(mvr, mvc.real))
+            xr, its_r, hist_r, reason_r = dpc.gmres(br, rtol=1e-7)
+            real_ok = real_ok and xr.dtype == torch.float64 and reason_r == "CONVERGED_RTOL" and abs(its_r - its) <= 1
+            real_ok = real_ok and float(torch.linalg.norm(xr - x.real) / torch.linalg.norm(x.real)) < 1e-6
+        ret[rank] = (its, its_s, reason, err, mv_err, real_ok)
     finally:
         dist.destroy_process_group()
 
@@ -89,8 +102,9 @@ def test_distributed_gmres_equals_single_gpu(N_x, N_t):
     ret = mp.Manager().dict()
     mp.spawn(_gmres_worker, args=(world, _free_port(), N_x, N_t, ret), nprocs=world, join=True)
     for r in range(world):
-        its, its_s, reason, err, mv_err = ret[r]
+        its, its_s, reason, err, mv_err, real_ok = ret[r]
         assert reason == "CONVERGED_RTOL" and abs(its - its_s) <= 1 and err < 1e-6 and mv_err == 0.0, ret[r]
+        assert real_ok, ret[r]
 
 
 def _real_worker(rank, world, port, cases, ret):
