@@ -51,8 +51,10 @@ def test_sharded_apply_equals_single_gpu_apply(N_x, N_t, mode):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), N_x, N_t, 1.0, ret, mode), nprocs=world, join=True)
     for r in range(world):
-        # all-to-all: same kernels on the same data; slab: a different elimination order
-        assert ret[r] < (1e-13 if mode == "alltoall" else 1e-10), (r, ret[r])
+        # all-to-all: the same streaming kernels on the same data, but the frequency-sharded handles solve the
+        # interface with the multi-level chain while the single-GPU handle uses the sequential kernel (6.8e-13
+        # apart at 1024 x 1024); slab: a different elimination order altogether
+        assert ret[r] < (1e-11 if mode == "alltoall" else 1e-10), (r, ret[r])
 
 
 def _gmres_worker(rank, world, port, N_x, N_t, ret):
