@@ -85,3 +85,47 @@ def test_fast_route_matches_golden(path):
 def test_golden_fixtures_exist():
     assert len(glob.glob(os.path.join(GOLDEN, "pc_apply_*.npz"))) >= 4
     assert len(glob.glob(os.path.join(GOLDEN, "gmres_*.npz"))) >= 2
+
+
+@pytest.mark.parametrize("N_x,N_t,gamma", [(16, 13, 1.0), (40, 64, 1e-2), (33, 20, 1e-4), (257, 128, 1.0)])
+def test_threaded_cpu_baseline_equals_the_numpy_route(N_x, N_t, gamma):
+    # bench.py's cpu_baseline / reference arm: scipy.fft with workers + the fused pthread stage of oracle/csrc/pc_solve.c
+    from oracle.pc_fast import DiagFFTPCFast
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(2 * (N_x + 1) * N_t) + 1j * rng.standard_normal(2 * (N_x + 1) * N_t)
+    pc = DiagFFTPCFast(N_x, N_t, 2.0, gamma)
+    y0, y1 = pc.apply(x), pc.apply_threaded(x)
+    assert np.linalg.norm(y1 - y0) <= 1e-11 * np.linalg.norm(y0)      # same recurrence, different complex-division rounding
+    assert np.abs(y1.reshape(2, N_x + 1, N_t)[:, [0, -1], :]).max() == 0.0
+    # sampled columns of the per-frequency stage (used by the full-size GPU tests), fp64 and 80-bit
+    import scipy.fft as sfft
+    xh = sfft.ifft(x.reshape(2, N_x + 1, N_t), axis=2)
+    ks = np.array([0, 1, N_t // 4, N_t // 2, N_t - 1])
+    rp, rm = pc.forward_stage(x)
+    zp, zm = pc.solve_stage(rp, rm)
+    full = np.stack([zp + zm, (-1j * pc.sigma * pc.z) * (zp - zm)])
+    assert np.abs(pc.stage_columns(ks, xh[:, :, ks]) - full[:, :, ks]).max() <= 1e-13 * np.abs(full).max()
+    ld = DiagFFTPCFast(N_x, N_t, 2.0, gamma, dtype=np.longdouble).stage_columns(ks, xh[:, :, ks])
+    assert np.abs(ld - full[:, :, ks]).max() <= 1e-9 * np.abs(full).max()
+
+
+def test_lean_gmres_equals_the_reference_restatement():
+    from oracle.gmres import gmres, gmres_lean
+    from oracle.operator import AllAtOnce
+    from oracle.pc_fast import DiagFFTPCFast
+    N_x, N_t = 24, 32
+    op, pc = AllAtOnce(N_x, N_t), DiagFFTPCFast(N_x, N_t)
+    b = np.random.default_rng(0).standard_normal(2 * (N_x + 1) * N_t)
+    b = b.reshape(2, N_x + 1, N_t)
+    b[:, 0] = b[:, -1] = 0
+    b = b.reshape(-1)
+    pcr = lambda v: pc.apply(v).real
+    x0, i0, h0, r0 = gmres(op.matvec, pcr, b, rtol=1e-8)
+    x1, i1, h1, r1 = gmres_lean(op.matvec, pcr, b, rtol=1e-8)
+    assert i0 == i1 and r0 == r1 and np.allclose(h0, h1, rtol=1e-10) and np.allclose(x0, x1, rtol=1e-9, atol=1e-12)
+    # residual-correction form of the preconditioned operator: same operator, same iteration
+    x2, i2, h2, _ = gmres_lean(op.matvec, pcr, b, rtol=1e-8, pc_matvec=lambda v: v + pcr(op.delta(v)))
+    assert abs(i2 - i0) <= 1 and np.allclose(x2, x0, rtol=1e-6, atol=1e-9)
+    xc = np.random.default_rng(1).standard_normal(b.size).reshape(2, N_x + 1, N_t)
+    xc[:, 0] = xc[:, -1] = 0
+    assert np.abs(op.delta(xc.reshape(-1)) - (op.matvec(xc.reshape(-1)) - op.pc_matvec(xc.reshape(-1)))).max() < 1e-13
