@@ -388,19 +388,20 @@ static int ensure_aux(pd_handle* h) {
 // as TWO FREQUENCY HALVES ON TWO STREAMS: the interface and separator kernels are short, latency-bound launches
 // (one warp per scheduler, a system-scope fence, a wait for the peers) that leave most SMs idle -- with the halves
 // staggered they overlap the streaming pass A / pass B of the other half.  Frequencies are independent and the
-// exchange flags are per group of 4 frequencies, so the halves share nothing.  PD_SLAB_OVERLAP=0 or the option
-// "slab_overlap" 0 turns it off -- REQUIRED when one process drives several ranks on ONE GPU (LocalSlabGroup): there
+// exchange flags are per group of 4 frequencies, so the halves share nothing.  MEASURED: no gain (pass A / pass B
+// occupy every SM's register file), so it is OFF unless PD_SLAB_OVERLAP=1; it must stay off when one process
+// drives several ranks on ONE GPU (LocalSlabGroup; option "slab_overlap" 0, or 2 = split on one stream): there
 // the strict order "every first half before any second half" is what keeps a waiting kernel from being scheduled
 // ahead of its producer, and a second stream would break it.  The per-stage profile always runs unsplit (its
 // stage times are the un-overlapped costs).
 static bool slab_overlap(pd_handle* h, int real_input, int* split) {
   static int env = -1;
-  if (env < 0) {
+  if (env < 0) {  // measured: no gain (0.440 vs 0.436 ms at cfg3 on 8 GPUs) -> off unless asked for
     const char* e = getenv("PD_SLAB_OVERLAP");
-    env = (e && e[0] == '0') ? 0 : 1;
+    env = (e && e[0] == '1') ? 1 : 0;
   }
   const int K = real_input ? ((h->cfg.N_t / 2 + 1 + 7) & ~7) : h->cfg.N_t;
-  if (!env || h->opt_slab_no_overlap == 1 || K < 1024 || h->fuse_on) return false;
+  if ((!env && h->opt_slab_no_overlap != 2) || h->opt_slab_no_overlap == 1 || K < 1024 || h->fuse_on) return false;
   *split = ((K / 2 + 127) / 128) * 128;
   return true;
 }
@@ -446,10 +447,10 @@ static int slab_end(pd_handle* h, void* y, cudaStream_t st, int real_input, cuda
       PD_CUDA(cudaEventRecord(h->sched_ev[1], sb));
       PD_CUDA(cudaStreamWaitEvent(st, h->sched_ev[1], 0));
     }
+    if ((rc = pd_slab_epoch_bump_launch(h, st))) return rc;  // after the join: the apply's exchange is complete
   } else {
-    if ((rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev))) return rc;
+    if ((rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev, 0, 0, 1))) return rc;  // pass B bumps
   }
-  if ((rc = pd_slab_epoch_bump_launch(h, st))) return rc;   // the apply's exchange is complete
   if (ev) cudaEventRecord(ev[1], st);
   if (real_input) return pd_stage_rfft_pair(h, h->work, y, h->n, 0, st);
   return pd_fft_launch(h, h->work, (cplx*)y, 2 * (int64_t)h->n, 0, st);

@@ -181,7 +181,7 @@ bool pd_fused_supported(const pd_handle* h);
 int pd_fused_ifft_passA_launch(pd_handle* h, const cplx* x, cplx* w, cudaStream_t st, cplx* lastl);
 void pd_fused_free(pd_handle* h);
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum = 0,
-                          cudaEvent_t* ev = nullptr, int koff = 0, int kend = 0);
+                          cudaEvent_t* ev = nullptr, int koff = 0, int kend = 0, int bump_epoch = 0);
 bool pd_slab_half_supported(const pd_handle* h);
 int pd_slab_comm_create_impl(pd_handle* h, void* ipc_handle_out, void** base_out);
 int pd_slab_comm_connect_impl(pd_handle* h, const void* peers, int mode, const int* peer_devices);

@@ -695,10 +695,12 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
       wp[(int64_t)(sp.m + 1) * sp.K] = zero;
     }
   }
+  // peer-store exchange, single-stream apply: this apply's functionals and separator kernels are complete (stream
+  // order), the next apply's have not started -> the apply is marked complete here, no extra launch
+  if (SLAB && sl.epoch_bump && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *sl.epoch_bump += 1ull;
 }
 
-// peer-store exchange: marks the apply complete.  Launched once per apply after every separator kernel of the apply
-// (stream order / event join) and before anything of the next apply.
+// The same as a launch of its own, for the two-stream variant of the apply (after the join of both halves).
 __global__ void pd_slab_epoch_bump_kernel(unsigned long long* epoch) { *epoch += 1ull; }
 
 // ------------------------------------------------------------ slab-mode kernels
@@ -771,7 +773,8 @@ pd_slab_coef_kernel(SolveParams sp, SlabGeom sg, cplx* __restrict__ coef) {
 // y = 0 stores the outer separator values zout, and all CTAs together add their effect on this slab's INTERIOR
 // separators, zsep[c] += cL g0[c] + cR g1[c] (g0, g1: interface Green's vectors of the plan; cL/cR = -(a / V_L) z_left,
 // -(a / V_Llast) z_right), so that pass B needs no slab-specific arithmetic in its chunk loop.
-template <bool WAIT>
+// GT: the slab count as a compile-time constant (2, 4, 8: the tiny Thomas arrays live in registers) or 0 (any G <= 16)
+template <bool WAIT, int GT>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveParams sp, SlabGeom sg,
                       const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm,
@@ -787,8 +790,10 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   const int64_t K = sp.K;
   const int64_t GS = gstride;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
-  const int G = sg.G;
-  cplx rv[PD_MAX_SLABS], dvv[PD_MAX_SLABS];
+  constexpr int GA = GT ? GT : PD_MAX_SLABS;
+  const int G = GT ? GT : sg.G;
+  cplx rv[GA], dvv[GA];
+#pragma unroll
   for (int s = 0; s < G; ++s) {
     rv[s] = coef[((int64_t)s * 2) * K + kk];
     dvv[s] = coef[((int64_t)s * 2 + 1) * K + kk];
@@ -798,8 +803,9 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   VRec t;
   t.init(kc.a, kc.sh, cmake(0, 0));
   const cplx eta = t.diag ? cmake(0, 0) : t.eta;
-  cplx cp[PD_MAX_SLABS], dP[PD_MAX_SLABS], dM[PD_MAX_SLABS];
+  cplx cp[GA], dP[GA], dM[GA];
   cplx prevc = cmake(0, 0), pP = cmake(0, 0), pM = cmake(0, 0);
+#pragma unroll
   for (int r = 1; r < G; ++r) {
     const cplx* gl = gathered + ((int64_t)(r - 1) * 6) * GS + kk;  // slab left of separator r
     const cplx* gr = gathered + ((int64_t)r * 6) * GS + kk;        // slab right of it (owns the separator)
@@ -824,6 +830,7 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   (void)roff;
   cplx zP = cmake(0, 0), zM = cmake(0, 0);
   cplx leftP = cmake(0, 0), leftM = cmake(0, 0), rightP = cmake(0, 0), rightM = cmake(0, 0);
+#pragma unroll
   for (int r = G - 1; r >= 1; --r) {
     zP = cfms(cp[r], zP, dP[r]);
     zM = cfms(cp[r], zM, dM[r]);
@@ -965,6 +972,7 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = half_spectrum ? pl->green_h : pl->green; sl.zout = pl->zout;
+  sl.epoch_bump = nullptr;
 }
 
 void pd_solve_fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl, int half_spectrum) {
@@ -1428,9 +1436,10 @@ int pd_slab_epoch_bump_launch(pd_handle* h, cudaStream_t st) {
 // slab mode, second half: global separator solve from the gathered functionals, then pass B
 // (gathered == nullptr: waits for the peers' stores into this rank's exchange buffer)
 int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStream_t st, int half_spectrum, cudaEvent_t* ev,
-                          int koff, int kend) {
+                          int koff, int kend, int bump_epoch) {
   SolveParams sp; Levels lv; SlabPtrs sl;
   fill_params(h, sp, lv, sl, half_spectrum);
+  if (bump_epoch && !gathered) sl.epoch_bump = plan_of(h)->comm_epoch;
   if (kend > koff) {
     sp.koff = koff;
     sp.kend = kend < sp.K ? kend : sp.K;
@@ -1446,18 +1455,26 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   if (gy > 16) gy = 16;
   const dim3 ggrid(kblocks, gy);
   cplx* zsep = sp.nlev >= 1 ? lv.R[1] : nullptr;
+#define PD_GLOBAL_LAUNCH(W, GT_, GPTR, GSTR, CM)                                                                   \
+  pd_slab_global_kernel<W, GT_><<<ggrid, PD_KB, 0, st>>>(GPTR, GSTR, sp, pl->sg, coef, pl->zout, CM, zsep, sl.green)
+#define PD_GLOBAL_DISPATCH(W, GPTR, GSTR, CM)                                                                      \
+  switch (pl->sg.G) {                                                                                              \
+    case 2: PD_GLOBAL_LAUNCH(W, 2, GPTR, GSTR, CM); break;                                                         \
+    case 4: PD_GLOBAL_LAUNCH(W, 4, GPTR, GSTR, CM); break;                                                         \
+    case 8: PD_GLOBAL_LAUNCH(W, 8, GPTR, GSTR, CM); break;                                                         \
+    default: PD_GLOBAL_LAUNCH(W, 0, GPTR, GSTR, CM); break;                                                        \
+  }
   if (gathered) {
     SlabCommDev none;
     memset(&none, 0, sizeof(none));
-    pd_slab_global_kernel<false><<<ggrid, PD_KB, 0, st>>>(gathered, (int64_t)sp.K, sp, pl->sg, coef, pl->zout, none,
-                                                          zsep, sl.green);
+    PD_GLOBAL_DISPATCH(false, gathered, (int64_t)sp.K, none);
   } else {
     if (!pl->comm_connected) {
       pd_set_error("slab apply: the peer-store exchange is not connected (pd_slab_comm_create / _connect)");
       return PD_ERR_INVALID;
     }
-    pd_slab_global_kernel<true><<<ggrid, PD_KB, 0, st>>>(nullptr, pl->comm_kmax, sp, pl->sg, coef, pl->zout,
-                                                        comm_dev_of(h), zsep, sl.green);
+    const SlabCommDev cmd = comm_dev_of(h);
+    PD_GLOBAL_DISPATCH(true, nullptr, pl->comm_kmax, cmd);
   }
   PD_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[0], st);

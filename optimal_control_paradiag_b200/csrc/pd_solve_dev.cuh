@@ -37,6 +37,7 @@ struct SlabPtrs {
   cplx* lastl;        // [2][K]     last entry of the last chunk's local solve (pass A)
   const cplx* green;  // [P][2][K]  interface Green's vectors T_1^-1 e_0 (slot 0), T_1^-1 e_{P-1} (slot 1)
   const cplx* zout;   // [4][K]     outer separator values: left (+, -), right (+, -)
+  unsigned long long* epoch_bump;  // peer-store exchange: pass B marks the apply complete (else null)
 };
 
 struct KCoef {
