@@ -443,29 +443,41 @@ pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __r
 // 3 % of a vector -- the per-frequency coefficients of the big level-0 systems are still regenerated in-kernel.
 __global__ void __launch_bounds__(PD_KB)
 pd_iface_pivots_kernel(SolveParams sp, cplx* __restrict__ piv) {
+  // TWISTED factorisation: rows 0 .. mid-1 are eliminated from the top, rows P-1 .. mid from the bottom (whose first
+  // row carries the modified diagonal dmain + glast), the two sweeps meet between rows mid-1 and mid.  Two threads
+  // per right-hand side then run the two sweeps of the solve concurrently: half the critical path of a kernel whose
+  // run time IS its critical path.
   const int kk = blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.K) return;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   const Sys s = reduce_sys(level_sys(kc, sp, 0), PD_L);
-  const int P = sp.rows[1];
+  const int P = sp.rows[1], mid = P / 2;
   PivotGen pg;
   pg.init(s);
-  for (int q = 0; q < P; ++q) {
-    cplx m = pg.next();
-    if (q == P - 1) m = last_row_pivot(m, s.glast);
+  for (int q = 0; q < mid; ++q) piv[(int64_t)q * sp.K + kk] = pg.next();
+  // from the bottom: the same generator with glast / off added to eta in its first step (cf. reduce_sys)
+  PivotGen pb;
+  pb.v.init(s.off, s.det, cmake(0, 0));  // (sets `diag`: decoupled systems have no off-diagonal to divide by)
+  if (!pb.v.diag) pb.v.init(s.off, s.det, cmul(s.glast, crcp(s.off)));
+  pb.roff = pb.v.diag ? cmake(0, 0) : crcp(s.off);
+  pb.mdiag = pb.v.diag ? crcp(sys_dmain(s)) : cmake(0, 0);
+  for (int q = P - 1; q >= mid; --q) {
+    cplx m = pb.next();
+    if (pb.v.diag && q == P - 1) m = crcp(cadd(sys_dmain(s), s.glast));
     piv[(int64_t)q * sp.K + kk] = m;
   }
 }
 
-// thread = (frequency, right-hand side): a half-warp owns 16 consecutive frequencies of one right-hand side, so every
-// row access is a contiguous 256-byte segment.  The kernel runs one warp per scheduler and nothing but its own
-// prefetching hides the latency of its loads: measured 0.42 us per row with one batch of 4 rows in flight in
-// registers, 0.30 us with two.  The rows therefore stream through a PER-THREAD RING IN SHARED MEMORY filled by
-// cp.async (LDGSTS): PD_IRING batches of PD_IT rows are in flight ahead of the elimination, every thread consumes
-// only what it copied itself (cp.async.wait_group, no block barrier anywhere in the sweep).
-#define PD_ITK 64    // frequencies per CTA of the sequential interface kernel (2 threads each)
+// thread = (frequency, right-hand side, direction): a half-warp owns 16 consecutive frequencies of one right-hand
+// side and one sweep direction, so every row access is a contiguous 256-byte segment.  The kernel runs one warp per
+// scheduler and nothing but its own prefetching hides the latency of its loads: measured 0.42 us per row with one
+// batch of 4 rows in flight in registers, 0.30 us with two.  The rows therefore stream through a PER-THREAD RING IN
+// SHARED MEMORY filled by cp.async (LDGSTS): PD_IRING batches of PD_IT rows are in flight ahead of the elimination,
+// every thread consumes only what it copied itself (cp.async.wait_group); the only block barrier is the meeting of
+// the top-down and the bottom-up sweep of the twisted factorisation.
+#define PD_ITK 32    // frequencies per CTA of the sequential interface kernel (4 threads each)
 #define PD_IRING 8   // batches of PD_IT rows in the ring
-#define PD_ISMEM (PD_IRING * PD_IT * 3 * 2 * PD_ITK * 16)
+#define PD_ISMEM (PD_IRING * PD_IT * 3 * 4 * PD_ITK * 16)
 __device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
@@ -475,98 +487,125 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool PUSH>
-__global__ void __launch_bounds__(2 * PD_ITK)
+__global__ void __launch_bounds__(4 * PD_ITK)
 pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
                              SlabPtrs sl, SlabCommDev cm) {
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
-  constexpr int NT = 2 * PD_ITK;
+  __shared__ cplx xch[4 * PD_ITK][2];                                // meeting point: (last value, off * pivot)
+  constexpr int NT = 4 * PD_ITK;
   cplx* ring = reinterpret_cast<cplx*>(pd_smem_raw) + threadIdx.x;   // slot (batch, item) of this thread: + (batch * 12 + item) * NT
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int rhs = lane >> 4;                                         // 0: the + system, 1: the (conjugated) - system
+  const bool up = (wrp & 2) != 0;                                    // warps 2, 3: the bottom-up sweep
   const int k0 = sp.koff + blockIdx.x * PD_ITK;
-  const int kk = k0 + wrp * 16 + (lane & 15);
+  const int kk = k0 + (wrp & 1) * 16 + (lane & 15);
+  const bool active = kk < sp.kend;
+  const int kc_idx = active ? kk : sp.kend - 1;                      // idle threads still meet at the barrier
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
-  if (kk < sp.kend) {
-    const KCoef kc = make_coef(freq_of(sp, kk), sp);
-    const Sys below = level_sys(kc, sp, 0);
-    const Sys s = reduce_sys(below, PD_L);
-    const int64_t K = sp.K;
-    const int P = sp.rows[1];
-    cplx* R = lv.R[1] + (int64_t)rhs * K + kk;
-    const cplx* F = lv.F[0] + (int64_t)rhs * K + kk;
-    const cplx* M = piv + kk;
-    const int nb = (P + PD_IT - 1) / PD_IT;  // batches
-    // ---- forward: d_q = (rhs_q - off d_{q-1}) m_q,  rhs_q = R[q] - off_below F[q+1]
-    auto issue_fwd = [&](int b) {
-      if (b < nb) {
-        cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
-#pragma unroll
-        for (int i = 0; i < PD_IT; ++i) {
-          const int64_t q = min(b * PD_IT + i, P - 1);
-          cp_async16(slot + (i * 3 + 0) * NT, R + (q * 2) * K);
-          cp_async16(slot + (i * 3 + 1) * NT, F + ((q + 1) * 2) * K);
-          cp_async16(slot + (i * 3 + 2) * NT, M + q * K);
-        }
-      }
-      cp_async_commit();  // (an empty group keeps the group count in step)
-    };
-    cplx d = cmake(0, 0);
-    for (int b = 0; b < PD_IRING - 1; ++b) issue_fwd(b);
-    for (int b = 0; b < nb; ++b) {
-      issue_fwd(b + PD_IRING - 1);
-      cp_async_wait<PD_IRING - 1>();
-      const cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
-      cplx g[PD_IT], m[PD_IT];
+  const KCoef kc = make_coef(freq_of(sp, kc_idx), sp);
+  const Sys below = level_sys(kc, sp, 0);
+  const Sys s = reduce_sys(below, PD_L);
+  const int64_t K = sp.K;
+  const int P = sp.rows[1], mid = P / 2;
+  cplx* R = lv.R[1] + (int64_t)rhs * K + kc_idx;
+  const cplx* F = lv.F[0] + (int64_t)rhs * K + kc_idx;
+  const cplx* M = piv + kc_idx;
+  // this thread's rows in sweep order: top-down 0 .. mid-1, bottom-up P-1 .. mid
+  const int nrow = up ? P - mid : mid;
+  auto row = [&](int i) -> int64_t { return up ? (int64_t)P - 1 - i : (int64_t)i; };
+  const int nb = (nrow + PD_IT - 1) / PD_IT;
+  // ---- elimination towards the middle: d_q = (rhs_q - off d_prev) m_q,  rhs_q = R[q] - off_below F[q+1]
+  auto issue_fwd = [&](int b) {
+    if (b < nb && active) {
+      cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
 #pragma unroll
       for (int i = 0; i < PD_IT; ++i) {
-        g[i] = cfms(below.off, slot[(i * 3 + 1) * NT], slot[(i * 3 + 0) * NT]);
-        m[i] = slot[(i * 3 + 2) * NT];
-      }
-#pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        const int64_t q = (int64_t)b * PD_IT + i;
-        if (q < P) {
-          d = cmul(cfms(s.off, d, g[i]), m[i]);
-          R[(q * 2) * K] = d;
-        }
+        const int64_t q = row(min(b * PD_IT + i, nrow - 1));
+        cp_async16(slot + (i * 3 + 0) * NT, R + (q * 2) * K);
+        cp_async16(slot + (i * 3 + 1) * NT, F + ((q + 1) * 2) * K);
+        cp_async16(slot + (i * 3 + 2) * NT, M + q * K);
       }
     }
-    cp_async_wait<0>();
-    __threadfence();  // the d_q just stored are read back (through L2) by the backward sweep of this same thread
-    // ---- backward: z_q = d_q - off m_q z_{q+1}, rows P-2 .. 0 in batches counted from the top
-    const cplx ze = d;
-    cplx z = d;
-    const int nbb = (P - 1 + PD_IT - 1) / PD_IT;
-    auto issue_bwd = [&](int b) {
-      if (b < nbb) {
-        cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
+    cp_async_commit();  // (an empty group keeps the group count in step)
+  };
+  cplx d = cmake(0, 0), clast = cmake(0, 0);
+  for (int b = 0; b < PD_IRING - 1; ++b) issue_fwd(b);
+  for (int b = 0; b < nb; ++b) {
+    issue_fwd(b + PD_IRING - 1);
+    cp_async_wait<PD_IRING - 1>();
+    const cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
+    cplx g[PD_IT], m[PD_IT];
 #pragma unroll
-        for (int i = 0; i < PD_IT; ++i) {
-          const int64_t q = max(P - 2 - (b * PD_IT + i), 0);
-          cp_async16(slot + (i * 3 + 0) * NT, R + (q * 2) * K);
-          cp_async16(slot + (i * 3 + 2) * NT, M + q * K);
-        }
-      }
-      cp_async_commit();
-    };
-    for (int b = 0; b < PD_IRING - 1; ++b) issue_bwd(b);
-    for (int b = 0; b < nbb; ++b) {
-      issue_bwd(b + PD_IRING - 1);
-      cp_async_wait<PD_IRING - 1>();
-      const cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
+    for (int i = 0; i < PD_IT; ++i) {
+      g[i] = cfms(below.off, slot[(i * 3 + 1) * NT], slot[(i * 3 + 0) * NT]);
+      m[i] = slot[(i * 3 + 2) * NT];
+    }
 #pragma unroll
-      for (int i = 0; i < PD_IT; ++i) {
-        const int64_t q = (int64_t)P - 2 - ((int64_t)b * PD_IT + i);
-        if (q >= 0) {
-          z = cfms(cmul(s.off, slot[(i * 3 + 2) * NT]), z, slot[(i * 3 + 0) * NT]);
-          R[(q * 2) * K] = z;
-        }
+    for (int i = 0; i < PD_IT; ++i) {
+      const int r = b * PD_IT + i;
+      if (r < nrow && active) {
+        d = cmul(cfms(s.off, d, g[i]), m[i]);
+        clast = cmul(s.off, m[i]);
+        R[(row(r) * 2) * K] = d;
       }
     }
-    cp_async_wait<0>();
-    if (PUSH) {
-      // this thread's half of the slab functionals (see slab_functionals): first / last entry of the slab-local
-      // solve and the rotated right-hand side of the separator row, for its own right-hand side
+  }
+  cp_async_wait<0>();
+  // ---- the meeting: x_a = d_a - c_a x_b (a = mid-1, top sweep),  x_b = e_b - c_b x_a (b = mid, bottom sweep)
+  xch[threadIdx.x][0] = d;       // (a sweep without rows contributes d = 0, c = 0)
+  xch[threadIdx.x][1] = clast;
+  __threadfence_block();
+  __syncthreads();
+  const cplx od = xch[threadIdx.x ^ 64][0], oc = xch[threadIdx.x ^ 64][1];
+  cplx z;
+  {
+    const cplx da = up ? od : d, ca = up ? oc : clast, eb = up ? d : od, cb = up ? clast : oc;
+    const cplx xa = cmul(cfms(ca, eb, da), crcp(cfms(ca, cb, cmake(1, 0))));   // (d_a - c_a e_b) / (1 - c_a c_b)
+    z = up ? cfms(cb, xa, eb) : xa;
+  }
+  // ---- substitution away from the middle: x_q = d_q - c_q x_next, this sweep's rows in reverse order.  The values
+  // d_q just stored are read back through L2 by this same thread.
+  __threadfence();
+  if (active && nrow > 0) R[(row(nrow - 1) * 2) * K] = z;
+  const int nrb = nrow - 1;  // rows still to substitute: sweep indices nrow-2 .. 0
+  const int nbb = (nrb + PD_IT - 1) / PD_IT;
+  auto issue_bwd = [&](int b) {
+    if (b < nbb && active) {
+      cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
+#pragma unroll
+      for (int i = 0; i < PD_IT; ++i) {
+        const int64_t q = row(max(nrow - 2 - (b * PD_IT + i), 0));
+        cp_async16(slot + (i * 3 + 0) * NT, R + (q * 2) * K);
+        cp_async16(slot + (i * 3 + 2) * NT, M + q * K);
+      }
+    }
+    cp_async_commit();
+  };
+  for (int b = 0; b < PD_IRING - 1; ++b) issue_bwd(b);
+  for (int b = 0; b < nbb; ++b) {
+    issue_bwd(b + PD_IRING - 1);
+    cp_async_wait<PD_IRING - 1>();
+    const cplx* slot = ring + (int64_t)((b % PD_IRING) * (PD_IT * 3)) * NT;
+#pragma unroll
+    for (int i = 0; i < PD_IT; ++i) {
+      const int r = nrow - 2 - (b * PD_IT + i);
+      if (r >= 0 && active) {
+        z = cfms(cmul(s.off, slot[(i * 3 + 2) * NT]), z, slot[(i * 3 + 0) * NT]);
+        R[(row(r) * 2) * K] = z;
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (PUSH) {
+    // the slab functionals (see slab_functionals), split between the two sweeps: the top-down thread ends with the
+    // FIRST interface value (first entry of the slab-local solve, rotated right-hand side of the separator row), the
+    // bottom-up thread with the LAST one (last entry of the slab-local solve)
+    if (P == 1) {  // a single interface row belongs to the bottom-up sweep: hand it to the top-down thread
+      xch[threadIdx.x][0] = z;
+      __syncthreads();
+      if (!up) z = xch[threadIdx.x ^ 64][0];
+    }
+    if (active) {
       const int Llast = sp.m - P * (PD_L + 1);
       VRec v;
       v.init(kc.a, kc.sh, cmake(0, 0));
@@ -578,18 +617,22 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
         }
         rvL = cscale(crcp(v.V), v.one);
       }
-      const cplx fv = cfma(z, rvL, lv.F[0][(int64_t)rhs * K + kk]);
-      const cplx lvv = Llast > 0 ? cfma(ze, rvLl, sl.lastl[(int64_t)rhs * K + kk]) : ze;
-      cplx sP = cmake(0, 0), sM = cmake(0, 0);
-      if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
       const int64_t slot = (((int64_t)(ep & 1ull) * cm.G + cm.rank) * 6 + rhs) * cm.kmax + kk;
-      for (int p = 0; p < cm.G; ++p) {
-        cplx* g = cm.peer_gath[p] + slot;
-        g[0] = fv; g[2 * cm.kmax] = lvv; g[4 * cm.kmax] = rhs ? sM : sP;
+      if (!up) {
+        const cplx fv = cfma(z, rvL, lv.F[0][(int64_t)rhs * K + kk]);
+        cplx sP = cmake(0, 0), sM = cmake(0, 0);
+        if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+        for (int p = 0; p < cm.G; ++p) {
+          cplx* g = cm.peer_gath[p] + slot;
+          g[0] = fv; g[4 * cm.kmax] = rhs ? sM : sP;
+        }
+      } else {
+        const cplx lvv = Llast > 0 ? cfma(z, rvLl, sl.lastl[(int64_t)rhs * K + kk]) : z;
+        for (int p = 0; p < cm.G; ++p) cm.peer_gath[p][slot + 2 * cm.kmax] = lvv;
       }
     }
+    slab_publish(cm, ep, k0, min(PD_ITK, sp.kend - k0));
   }
-  if (PUSH) slab_publish(cm, ep, k0, min(PD_ITK, sp.kend - k0));
 }
 
 // ------------------------------------------------------------------- pass B
@@ -995,14 +1038,14 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   if (piv) {
     const int nblk = (ncol + PD_ITK - 1) / PD_ITK;
     if (push) {
-      pd_solve_iface_thomas_kernel<true><<<nblk, 2 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
+      pd_solve_iface_thomas_kernel<true><<<nblk, 4 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
       if (pushed) *pushed = true;
     } else {
       SlabPtrs nosl;
       SlabCommDev nocm;
       memset(&nosl, 0, sizeof(nosl));
       memset(&nocm, 0, sizeof(nocm));
-      pd_solve_iface_thomas_kernel<false><<<nblk, 2 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, nullptr, nosl, nocm);
+      pd_solve_iface_thomas_kernel<false><<<nblk, 4 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, nullptr, nosl, nocm);
     }
     PD_CHECK_LAUNCH();
     h->launches++;
