@@ -476,8 +476,10 @@ pd_iface_pivots_kernel(SolveParams sp, cplx* __restrict__ piv) {
 // every thread consumes only what it copied itself (cp.async.wait_group); the only block barrier is the meeting of
 // the top-down and the bottom-up sweep of the twisted factorisation.
 #define PD_ITK 32    // frequencies per CTA of the sequential interface kernel (4 threads each)
-#define PD_IRING 8   // batches of PD_IT rows in the ring
-#define PD_ISMEM (PD_IRING * PD_IT * 3 * 4 * PD_ITK * 16)
+// ring depth (batches of PD_IT rows) = template parameter: 8 when the grid fits the GPU with one CTA per SM (196 KB of
+// ring each), 4 / 2 when there are more CTAs than SMs (N_t = 16384: 512 CTAs) -- then several CTAs per SM hide each
+// other's latency and one resident wave beats a deep ring in 3.5 waves (cfg4: 1.9 ms -> see DESIGN.md)
+#define PD_ISMEM(RING) ((RING) * PD_IT * 3 * 4 * PD_ITK * 16)
 __device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
@@ -486,7 +488,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool PUSH>
+template <bool PUSH, int PD_IRING>
 __global__ void __launch_bounds__(4 * PD_ITK)
 pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
                              SlabPtrs sl, SlabCommDev cm) {
@@ -1037,16 +1039,24 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   const cplx* piv = plan_of(h)->ipiv[sp.K == h->kcount ? 0 : 1];
   if (piv) {
     const int nblk = (ncol + PD_ITK - 1) / PD_ITK;
-    if (push) {
-      pd_solve_iface_thomas_kernel<true><<<nblk, 4 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, push->w, push->sl, push->cm);
-      if (pushed) *pushed = true;
-    } else {
-      SlabPtrs nosl;
-      SlabCommDev nocm;
-      memset(&nosl, 0, sizeof(nosl));
-      memset(&nocm, 0, sizeof(nocm));
-      pd_solve_iface_thomas_kernel<false><<<nblk, 4 * PD_ITK, PD_ISMEM, st>>>(lv, sp, piv, nullptr, nosl, nocm);
-    }
+    SlabPtrs nosl;
+    SlabCommDev nocm;
+    memset(&nosl, 0, sizeof(nosl));
+    memset(&nocm, 0, sizeof(nocm));
+    const int ring = nblk <= h->num_sms ? 8 : (nblk <= 2 * h->num_sms ? 4 : 2);
+#define PD_IFACE_LAUNCH(RING)                                                                                       \
+  do {                                                                                                              \
+    if (push)                                                                                                       \
+      pd_solve_iface_thomas_kernel<true, RING><<<nblk, 4 * PD_ITK, PD_ISMEM(RING), st>>>(lv, sp, piv, push->w,      \
+                                                                                       push->sl, push->cm);         \
+    else                                                                                                            \
+      pd_solve_iface_thomas_kernel<false, RING><<<nblk, 4 * PD_ITK, PD_ISMEM(RING), st>>>(lv, sp, piv, nullptr,     \
+                                                                                        nosl, nocm);                \
+  } while (0)
+    if (ring == 8) PD_IFACE_LAUNCH(8);
+    else if (ring == 4) PD_IFACE_LAUNCH(4);
+    else PD_IFACE_LAUNCH(2);
+    if (push && pushed) *pushed = true;
     PD_CHECK_LAUNCH();
     h->launches++;
     return PD_OK;
@@ -1090,10 +1100,14 @@ int pd_solve_plan(pd_handle* h) {
                                PD_PCR_THREADS * PD_PCR_MAXROWS * 64));
   PD_CUDA(cudaFuncSetAttribute(pd_solve_pcr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                PD_PCR_THREADS * PD_PCR_MAXROWS * 64));
-  PD_CUDA(cudaFuncSetAttribute(pd_solve_iface_thomas_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               PD_ISMEM));
-  PD_CUDA(cudaFuncSetAttribute(pd_solve_iface_thomas_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               PD_ISMEM));
+#define PD_IFACE_ATTR(RING)                                                                                         \
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_iface_thomas_kernel<false, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               PD_ISMEM(RING)));                                                                     \
+  PD_CUDA(cudaFuncSetAttribute(pd_solve_iface_thomas_kernel<true, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                               PD_ISMEM(RING)))
+  PD_IFACE_ATTR(8);
+  PD_IFACE_ATTR(4);
+  PD_IFACE_ATTR(2);
   SolvePlan* pl = new SolvePlan();
   memset(pl, 0, sizeof(*pl));
   h->solve_plan = pl;
