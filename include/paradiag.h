@@ -105,12 +105,15 @@ int pd_host_unregister_all(pd_handle* h);
  * y_dev are float64 arrays in the same (field, node, time) layout, 2 n N_t doubles.  Their time spectra
  * are Hermitian, so only the frequencies 0..N_t/2 are transformed and solved: half the bytes of
  * pd_pc_apply in every stage.  Result = real part of pd_pc_apply on (x + 0i) (the imaginary part of that
- * is rounding noise).  Needs a power-of-two N_t in [128, 16384]; PD_ERR_UNSUPPORTED otherwise.        */
+ * is rounding noise).  Needs N_t >= 8 (register pipelines for the powers of two in [128, 16384], a
+ * shared-memory pair kernel for every other length, N_t = 81 included); PD_ERR_UNSUPPORTED otherwise. */
 int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
 /* The stages of the real-input path: real lines of N_t samples <-> half spectra of N_t/2 + 1 complex
  * numbers (to_freq != 0: scipy ifft restricted to k <= N_t/2; to_freq == 0: scipy fft of the Hermitian
  * extension, real output), and the per-frequency stage on w = (2, n, Kp), in place; rows of a half
- * spectrum are padded to Kp = (N_t/2 + 1 rounded up to a multiple of 8) complex numbers.            */
+ * spectrum are padded to Kp = (N_t/2 + 1 rounded up to a multiple of 8) complex numbers.  pd_stage_rfft (one
+ * packed real line at a time) exists for the powers of two in [128, 16384] only; pd_stage_rfft_pair (below)
+ * covers every N_t >= 8.                                                                              */
 int pd_stage_rfft(pd_handle* h, const void* in_dev, void* out_dev, int64_t nlines, int to_freq, void* stream);
 int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream);
 /* One apply with CUDA events recorded on `stream` between its kernels; ms[0..4] receive
@@ -154,7 +157,7 @@ int pd_slab_finish(pd_handle* h, void* w_dev, const void* gathered_dev, void* st
  * numbers): pd_stage_rfft_pair transforms both fields of `nnodes` node lines, (2, nnodes, N_t) float64 <->
  * (2, nnodes, Kp) complex; pd_slab_reduce_half / pd_slab_finish_half are pd_slab_reduce / pd_slab_finish on
  * w = (2, n_r, Kp) with out (6, Kp) and gathered (G, 6, Kp).  No upstream counterpart (the reference has no
- * parallel decomposition).  Power-of-two N_t in [128, 16384]; PD_ERR_UNSUPPORTED otherwise.             */
+ * parallel decomposition).  N_t >= 8; PD_ERR_UNSUPPORTED otherwise.                                     */
 int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_dev, int64_t nnodes, int to_freq, void* stream);
 int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, void* stream);
 int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gathered_dev, void* stream);
@@ -173,7 +176,7 @@ int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gathered_dev, voi
  *                          (peer_devices[r] = CUDA ordinal of rank r's buffer, NULL if all on this device).
  *   pd_slab_apply        : y_local = P^-1 x on this rank's (2, n_r, N_t) complex128 block.  Collective in the
  *                          sense that every rank must call it the same number of times.
- *   pd_slab_apply_real   : the same on float64 blocks (half spectrum), power-of-two N_t in [128, 16384].
+ *   pd_slab_apply_real   : the same on float64 blocks (half spectrum), N_t >= 8.
  *   pd_slab_apply_begin / _end : the two halves (up to the peer stores / from the wait on), so that one process
  *                          driving several ranks can issue all first halves before any second half (kernels that
  *                          wait on one another must never be queued on ONE GPU in the wrong order).

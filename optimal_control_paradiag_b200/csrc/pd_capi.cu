@@ -66,14 +66,15 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
     return PD_ERR_INVALID;
   }
   // alpha != 1 is an extension (the upstream preconditioner is the alpha = 1 block circulant and has no alpha;
-  // definition in oracle/pc_alpha.py): single-GPU complex apply / GMRES only
+  // definition in oracle/pc_alpha.py): the single-GPU and slab-mode applies (complex and real-input) and GMRES,
+  // not the frequency-sharded stage handles of the all-to-all mode
   if (!(cfg->alpha > 0.0) || cfg->alpha > 1.0) {
     pd_set_error("pd_create: alpha = %g outside (0, 1]", cfg->alpha);
     return PD_ERR_INVALID;
   }
-  if (cfg->alpha != 1.0 && (cfg->k_count > 0 || cfg->n_local > 0 || cfg->slab_count > 1)) {
-    pd_set_error("pd_create: alpha = %g on a sharded handle is not supported (alpha != 1 is single-GPU only)",
-                 cfg->alpha);
+  if (cfg->alpha != 1.0 && (cfg->k_count > 0 || cfg->n_local > 0)) {
+    pd_set_error("pd_create: alpha = %g on a frequency- / node-sharded stage handle is not supported (alpha != 1: "
+                 "single-GPU or slab mode)", cfg->alpha);
     return PD_ERR_UNSUPPORTED;
   }
   int ndev = 0;
@@ -308,7 +309,7 @@ extern "C" int pd_slab_reduce_half(pd_handle* h, void* w_dev, void* out_dev, voi
   }
   PD_ON_DEVICE(h);
   if (!pd_slab_half_supported(h)) {
-    pd_set_error("pd_slab_reduce_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    pd_set_error("pd_slab_reduce_half: needs N_t >= 8 (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return pd_slab_reduce_launch(h, (cplx*)w_dev, (cplx*)out_dev, (cudaStream_t)stream, 1);
@@ -321,7 +322,7 @@ extern "C" int pd_slab_finish_half(pd_handle* h, void* w_dev, const void* gather
   }
   PD_ON_DEVICE(h);
   if (!pd_slab_half_supported(h)) {
-    pd_set_error("pd_slab_finish_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    pd_set_error("pd_slab_finish_half: needs N_t >= 8 (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return pd_slab_finish_launch(h, (cplx*)w_dev, (const cplx*)gathered_dev, (cudaStream_t)stream, 1);
@@ -368,7 +369,7 @@ static int slab_apply_check(pd_handle* h, const void* p, const char* who, int re
     return PD_ERR_INVALID;
   }
   if (real_input && !pd_slab_half_supported(h)) {
-    pd_set_error("%s: the real-input path needs a power-of-two N_t in [128, 16384] (got %d)", who, h->cfg.N_t);
+    pd_set_error("%s: the real-input path needs N_t >= 8 (got %d)", who, h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return PD_OK;
@@ -382,6 +383,28 @@ static int ensure_aux(pd_handle* h) {
       if (!h->sched_ev[i]) PD_CUDA(cudaEventCreateWithFlags(&h->sched_ev[i], cudaEventDisableTiming));
   }
   return PD_OK;
+}
+
+// The time transforms of the apply paths.  alpha != 1 (an extension, no upstream counterpart): the inverse transform
+// also applies Gamma_alpha to its input and the forward one Gamma_alpha^-1 to its output, inside the kernels where
+// they can (every kernel but the opt-in N_t = 16384 cluster variant), else as a separate elementwise launch.
+static int apply_fft(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st) {
+  if (h->cfg.alpha == 1.0) return pd_fft_launch(h, in, out, nlines, inverse, st);
+  if (pd_fft_gamma_fused(h)) return pd_fft_launch(h, in, out, nlines, inverse, st, 1);
+  int rc;
+  if (inverse) {
+    if ((rc = pd_gamma_launch(h, in, out, nlines, 0, st))) return rc;
+    return pd_fft_launch(h, out, out, nlines, 1, st);
+  }
+  if ((rc = pd_fft_launch(h, in, out, nlines, 0, st))) return rc;
+  return pd_gamma_launch(h, out, out, nlines, 1, st);
+}
+// real lines <-> half spectra of `nnodes` nodes (both fields), Gamma_alpha fused when alpha != 1
+static int apply_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st) {
+  const int g = h->cfg.alpha != 1.0;
+  int rc = pd_rfft_pair_launch(h, in, out, nnodes, to_freq, st, g);
+  if (rc == -100) rc = pd_rfft_launch(h, in, out, 2 * nnodes, to_freq, st, g);
+  return rc;
 }
 
 // The per-frequency part of the slab apply (pass A, interface + peer stores | wait + separator solve, pass B) is run
@@ -412,12 +435,12 @@ static int slab_begin(pd_handle* h, const void* x, cudaStream_t st, int real_inp
   if (rc) return rc;
   int fused = 0;
   if (real_input) {
-    rc = pd_stage_rfft_pair(h, x, h->work, h->n, 1, st);
-  } else if (h->fuse_on) {
+    rc = apply_rfft_pair(h, x, h->work, h->n, 1, st);
+  } else if (h->fuse_on && h->cfg.alpha == 1.0) {
     rc = pd_fused_ifft_passA_launch(h, (const cplx*)x, h->work, st, pd_slab_lastl(h));
     fused = 1;
   } else {
-    rc = pd_fft_launch(h, (const cplx*)x, h->work, 2 * (int64_t)h->n, 1, st);
+    rc = apply_fft(h, (const cplx*)x, h->work, 2 * (int64_t)h->n, 1, st);
   }
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[0], st);
@@ -452,8 +475,8 @@ static int slab_end(pd_handle* h, void* y, cudaStream_t st, int real_input, cuda
     if ((rc = pd_slab_finish_launch(h, h->work, nullptr, st, real_input, ev, 0, 0, 1))) return rc;  // pass B bumps
   }
   if (ev) cudaEventRecord(ev[1], st);
-  if (real_input) return pd_stage_rfft_pair(h, h->work, y, h->n, 0, st);
-  return pd_fft_launch(h, h->work, (cplx*)y, 2 * (int64_t)h->n, 0, st);
+  if (real_input) return apply_rfft_pair(h, h->work, y, h->n, 0, st);
+  return apply_fft(h, h->work, (cplx*)y, 2 * (int64_t)h->n, 0, st);
 }
 
 extern "C" int pd_slab_apply_begin(pd_handle* h, const void* x_dev, void* stream, int real_input) {
@@ -533,7 +556,7 @@ extern "C" int pd_stage_rfft_pair(pd_handle* h, const void* in_dev, void* out_de
   }
   PD_ON_DEVICE(h);
   if (!pd_rfft_supported(h)) {
-    pd_set_error("pd_stage_rfft_pair: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    pd_set_error("pd_stage_rfft_pair: needs N_t >= 8 (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   int rc = pd_rfft_pair_launch(h, in_dev, out_dev, nnodes, to_freq, (cudaStream_t)stream);
@@ -555,20 +578,12 @@ extern "C" int pd_pc_apply(pd_handle* h, const void* x_dev, void* y_dev, void* s
   int rc = ensure_work(h);
   if (rc) return rc;
   const int64_t nlines = 2 * (int64_t)h->n;
-  if (h->cfg.alpha != 1.0 && pd_fft_gamma_fused(h)) {
-    // extension: Gamma fused into the loads of the inverse FFT, alpha-shifted per-frequency stage, Gamma^-1 fused
-    // into the stores of the forward FFT -- the same three launches groups as alpha = 1
-    if ((rc = pd_fft_launch(h, (const cplx*)x_dev, h->work, nlines, 1, st, 1))) return rc;
-    if ((rc = pd_solve_launch(h, h->work, st))) return rc;
-    return pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st, 1);
-  }
   if (h->cfg.alpha != 1.0) {
-    // (N_t = 16384 cluster kernel: Gamma / Gamma^-1 as two separate elementwise sweeps)
-    if ((rc = pd_gamma_launch(h, (const cplx*)x_dev, h->work, nlines, 0, st))) return rc;
-    if ((rc = pd_fft_launch(h, h->work, h->work, nlines, 1, st))) return rc;
+    // extension: Gamma fused into the loads of the inverse FFT, alpha-shifted per-frequency stage, Gamma^-1 fused
+    // into the stores of the forward FFT -- the same three launch groups as alpha = 1
+    if ((rc = apply_fft(h, (const cplx*)x_dev, h->work, nlines, 1, st))) return rc;
     if ((rc = pd_solve_launch(h, h->work, st))) return rc;
-    if ((rc = pd_fft_launch(h, h->work, (cplx*)y_dev, nlines, 0, st))) return rc;
-    return pd_gamma_launch(h, (const cplx*)y_dev, (cplx*)y_dev, nlines, 1, st);
+    return apply_fft(h, h->work, (cplx*)y_dev, nlines, 0, st);
   }
   if (h->sched_chunks > 0) return apply_interleaved(h, (const cplx*)x_dev, (cplx*)y_dev, st);
   // :500-501 ifft along time, :445-540 per-frequency stage, :547-548 fft along time
@@ -653,12 +668,8 @@ extern "C" int pd_stage_solve_half(pd_handle* h, void* w_dev, void* stream) {
     return PD_ERR_INVALID;
   }
   PD_ON_DEVICE(h);
-  if (h->cfg.alpha != 1.0) {
-    pd_set_error("pd_stage_solve_half: alpha != 1 is not supported on the real-input path");
-    return PD_ERR_UNSUPPORTED;
-  }
   if (!pd_rfft_supported(h)) {  // the interface workspaces are sized for N_t columns; Kp > N_t for N_t < 8
-    pd_set_error("pd_stage_solve_half: needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+    pd_set_error("pd_stage_solve_half: needs N_t >= 8 (got %d)", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return pd_solve_launch(h, (cplx*)w_dev, (cudaStream_t)stream, nullptr, 1);
@@ -674,28 +685,21 @@ extern "C" int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, vo
     pd_set_error("pd_pc_apply_real: handle is sharded; the real-input path is single-GPU");
     return PD_ERR_INVALID;
   }
-  if (h->cfg.alpha != 1.0) {
-    pd_set_error("pd_pc_apply_real: alpha != 1 is not supported on the real-input path; use pd_pc_apply");
-    return PD_ERR_UNSUPPORTED;
-  }
   if (!pd_rfft_supported(h)) {
-    pd_set_error("pd_pc_apply_real: needs a power-of-two N_t in [128, 16384] (got %d); use pd_pc_apply", h->cfg.N_t);
+    pd_set_error("pd_pc_apply_real: needs N_t >= 8 (got %d); use pd_pc_apply", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_work(h);
   if (rc) return rc;
-  const int64_t nlines = 2 * (int64_t)h->n;
   // real lines -> half spectra (k = 0..N_t/2), the same per-frequency stage on half as many columns, back
   // u- and p-line of a node go through ONE complex N_t-point transform (pd_rfft_pair_kernel); sizes it does
   // not cover use the per-line packed kernel
-  rc = pd_rfft_pair_launch(h, x_dev, h->work, h->n, 1, st);
-  if (rc == -100) rc = pd_rfft_launch(h, x_dev, h->work, nlines, 1, st);
-  if (rc) return rc;
+  // (alpha != 1: Gamma is real, so Gamma x stays real and the alpha-shifted symbols keep lambda(N_t - k) =
+  // conj lambda(k): the half spectrum still suffices; Gamma / Gamma^-1 ride on the loads / stores of the transforms)
+  if ((rc = apply_rfft_pair(h, x_dev, h->work, h->n, 1, st))) return rc;
   if ((rc = pd_solve_launch(h, h->work, st, nullptr, 1))) return rc;
-  rc = pd_rfft_pair_launch(h, h->work, y_dev, h->n, 0, st);
-  if (rc == -100) rc = pd_rfft_launch(h, h->work, y_dev, nlines, 0, st);
-  return rc;
+  return apply_rfft_pair(h, h->work, y_dev, h->n, 0, st);
 }
 
 extern "C" int pd_pc_apply_transpose(pd_handle*, const void*, void*, void*) {

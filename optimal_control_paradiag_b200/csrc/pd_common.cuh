@@ -168,8 +168,11 @@ int pd_solve_interface(pd_handle* h, cudaStream_t st);
 int pd_solve_passB_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st);
 int pd_gamma_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int inverse, cudaStream_t st);
 bool pd_rfft_supported(const pd_handle* h);
-int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st);
-int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st);
+// with_gamma (alpha != 1): Gamma on the samples read (to_freq) / Gamma^-1 on the samples written (!to_freq)
+int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st,
+                   int with_gamma = 0);
+int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st,
+                        int with_gamma = 0);
 int pd_solve_plan(pd_handle* h);
 int pd_solve_launch(pd_handle* h, cplx* w, cudaStream_t st, cudaEvent_t* ev = nullptr, int half_spectrum = 0);
 int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int half_spectrum = 0,

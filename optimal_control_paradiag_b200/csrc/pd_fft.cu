@@ -106,6 +106,100 @@ pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N
   }
 }
 
+// ------------------------------------------------------------ generic real-input pair kernel
+// The two-for-one real transform of pd_rfft_pair_kernel (further down) for the time-axis lengths the register
+// pipelines do not cover -- every non-power-of-two N_t (the upstream default N_t = 81 included) and the powers of two
+// below 128: the u-line and the p-line of one node as ONE complex line c = u + i p through the shared-memory
+// passes of pd_fft_generic_kernel.  Half spectra hold the frequencies k = 0 .. N_t/2 (integer division) in rows of
+// KP = (N_t/2 + 1 rounded up to 8) complex numbers, padding columns zero.  gam: see pd_rfft_pair_kernel.
+__device__ __forceinline__ cplx* generic_forward_passes(cplx* s, cplx* d, int N, const cplx* __restrict__ tw,
+                                                        const PassList& pl, int tid, int nth) {
+  int Ns = 1;
+  for (int p = 0; p < pl.n; ++p) {
+    const int R = pl.r[p];
+    const int NR = N / R;
+    const int tws = N / (Ns * R);
+    for (int o = tid; o < N; o += nth) {
+      const int jl = o % Ns, t = o / Ns;
+      const int r = t % R, jh = t / R;
+      const int j = jh * Ns + jl;
+      const int step = (int)(((int64_t)jl * tws + (int64_t)r * NR) % N);
+      int e = 0;
+      cplx acc = cmake(0.0, 0.0);
+      for (int q = 0; q < R; ++q) {
+        acc = cfma(s[j + q * NR], tw[e], acc);
+        e += step;
+        if (e >= N) e -= N;
+      }
+      d[o] = acc;
+    }
+    __syncthreads();
+    cplx* tmp = s; s = d; d = tmp;
+    Ns *= R;
+  }
+  return s;
+}
+
+template <bool TO_FREQ>
+__global__ void __launch_bounds__(256)
+pd_rfft_pair_generic_kernel(const void* __restrict__ in_, void* __restrict__ out_, int N, int64_t nnodes,
+                            const cplx* __restrict__ tw, PassList pl, const double* __restrict__ gam) {
+  extern __shared__ __align__(16) unsigned char pd_smem_raw[];
+  cplx* buf0 = reinterpret_cast<cplx*>(pd_smem_raw);
+  cplx* buf1 = buf0 + N;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int H = N / 2;
+  const int KP = (H + 1 + 7) & ~7;
+  for (int64_t node = blockIdx.x; node < nnodes; node += gridDim.x) {
+    if (TO_FREQ) {
+      const double* xu = reinterpret_cast<const double*>(in_) + node * N;
+      const double* xp = xu + nnodes * N;
+      cplx* gu = reinterpret_cast<cplx*>(out_) + node * KP;
+      cplx* gp = gu + nnodes * KP;
+      for (int i = tid; i < N; i += nth) {
+        const double g = gam ? gam[i] : 1.0;
+        buf0[i] = cmake(xu[i] * g, xp[i] * g);
+      }
+      __syncthreads();
+      const cplx* C = generic_forward_passes(buf0, buf1, N, tw, pl, tid, nth);
+      // u-hat[k] = conj(A)/N, p-hat[k] = conj(B)/N with A = (C[k] + conj C[N-k])/2, B = -i (C[k] - conj C[N-k])/2
+      const double sc = 0.5 / (double)N;
+      for (int k = tid; k < KP; k += nth) {
+        if (k <= H) {
+          const cplx a = C[k], b = cconj(C[k == 0 ? 0 : N - k]);
+          gu[k] = cmake((a.x + b.x) * sc, -(a.y + b.y) * sc);
+          gp[k] = cmake((a.y - b.y) * sc, (a.x - b.x) * sc);
+        } else {
+          gu[k] = cmake(0.0, 0.0);
+          gp[k] = cmake(0.0, 0.0);
+        }
+      }
+      __syncthreads();
+    } else {
+      const cplx* wu = reinterpret_cast<const cplx*>(in_) + node * KP;
+      const cplx* wp = wu + nnodes * KP;
+      double* yu = reinterpret_cast<double*>(out_) + node * N;
+      double* yp = yu + nnodes * N;
+      // D[k] = Wu[k] + i Wp[k] (k <= N/2), the Hermitian extension of both above; y_u + i y_p = FFT(D)
+      for (int k = tid; k < N; k += nth) {
+        const bool lo = k <= H;
+        const int kk = lo ? k : N - k;
+        cplx a = wu[kk], b = wp[kk];
+        if (!lo) { a.y = -a.y; b.y = -b.y; }
+        buf0[k] = cmake(a.x - b.y, a.y + b.x);
+      }
+      __syncthreads();
+      const cplx* Y = generic_forward_passes(buf0, buf1, N, tw, pl, tid, nth);
+      for (int i = tid; i < N; i += nth) {
+        const double g = gam ? gam[i] : 1.0;
+        yu[i] = Y[i].x * g;
+        yp[i] = Y[i].y * g;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 #include "pd_fft_dev.cuh"
 
 // N = R0 * R1 * R2 * R3 (unused radices = 1); T = N/16 threads per line,
@@ -658,10 +752,13 @@ pd_fft_16k_tma_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64
 //   !TO_FREQ : y = fft of the Hermitian extension of Y[0..M]: F = FFT_M(G(Y)[0..M-1]),
 //              y[2n] + i y[2n+1] = 2 conj(F[n])                    (= scipy fft, :547-548, real part)
 // Both directions reuse the M-point register pipeline above plus one extra shared-memory exchange.
-template <int R0, int R1, int R2, int R3, bool TO_FREQ>
+// GAM (alpha != 1, an extension): gam[j] multiplies the real sample j as it is loaded (TO_FREQ: Gamma) or stored
+// (!TO_FREQ: Gamma^-1), see pow2_pass.
+template <int R0, int R1, int R2, int R3, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nlines,
-               const cplx* __restrict__ twN, const cplx* __restrict__ twM) {
+               const cplx* __restrict__ twN, const cplx* __restrict__ twM, const double* __restrict__ gam) {
+  constexpr int G2 = GAM ? 2 : 0;
   constexpr int M = R0 * R1 * R2 * R3;  // complex length = N_t / 2
   constexpr int T = M / 16;
   constexpr int KP = (M + 1 + 7) & ~7;   // row stride of a half spectrum: M + 1 rounded up to 128 bytes
@@ -683,9 +780,9 @@ pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nl
       cplx* gdst = reinterpret_cast<cplx*>(out_) + ln * KP;
       // M-point transform, last pass kept in registers
       if (R1 == 1) {
-        pow2_pass<R0, false, true, true, false, true>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live, io);
+        pow2_pass<R0, false, true, true, false, true, false, G2>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live, io, gam);
       } else {
-        pow2_pass<R0, false, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live);
+        pow2_pass<R0, false, true, false, false, false, false, G2>(gsrc, gdst, sm, twM, M, 1, t, T, 1.0, live, nullptr, gam);
         if (R2 == 1) {
           pow2_pass<(R1 > 1 ? R1 : 2), false, false, true, false, true>(gsrc, gdst, sm, twM, M, R0, t, T, 1.0, live, io);
         } else {
@@ -737,18 +834,18 @@ pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nl
       __syncthreads();
       // F = FFT_M(io); stored as 2 conj(F): the real samples y[2n], y[2n+1]
       if (R1 == 1) {
-        pow2_pass<R0, true, true, true, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 2.0, live, io);
+        pow2_pass<R0, true, true, true, true, false, false, G2>(gsrc, gdst, sm, twM, M, 1, t, T, 2.0, live, io, gam);
       } else {
         pow2_pass<R0, false, true, false, true, false>(gsrc, gdst, sm, twM, M, 1, t, T, 2.0, live, io);
         if (R2 == 1) {
-          pow2_pass<(R1 > 1 ? R1 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0, t, T, 2.0, live);
+          pow2_pass<(R1 > 1 ? R1 : 2), true, false, true, false, false, false, G2>(gsrc, gdst, sm, twM, M, R0, t, T, 2.0, live, nullptr, gam);
         } else {
           pow2_pass<(R1 > 1 ? R1 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0, t, T, 2.0, live);
           if (R3 == 1) {
-            pow2_pass<(R2 > 1 ? R2 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 2.0, live);
+            pow2_pass<(R2 > 1 ? R2 : 2), true, false, true, false, false, false, G2>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 2.0, live, nullptr, gam);
           } else {
             pow2_pass<(R2 > 1 ? R2 : 2), false, false, false>(gsrc, gdst, sm, twM, M, R0 * R1, t, T, 2.0, live);
-            pow2_pass<(R3 > 1 ? R3 : 2), true, false, true>(gsrc, gdst, sm, twM, M, R0 * R1 * R2, t, T, 2.0, live);
+            pow2_pass<(R3 > 1 ? R3 : 2), true, false, true, false, false, false, G2>(gsrc, gdst, sm, twM, M, R0 * R1 * R2, t, T, 2.0, live, nullptr, gam);
           }
         }
       }
@@ -792,9 +889,15 @@ static void factorize(int N, PassList& pl) {
 
 static bool is_pow2(int N) { return N > 0 && (N & (N - 1)) == 0; }
 
-bool pd_rfft_supported(const pd_handle* h) {
+// the real-input (half-spectrum) path: register pipelines for the powers of two in [128, 16384], the generic
+// shared-memory pair kernel for every other N_t >= 8 (a half-spectrum row, N_t/2 + 1 rounded up to 8 columns, must fit
+// the N_t columns the workspaces are sized for)
+static bool rfft_register_path(const pd_handle* h) {
   const int N = h->cfg.N_t;
   return is_pow2(N) && N >= 128 && N <= 16384 && h->twiddle_half != nullptr;
+}
+bool pd_rfft_supported(const pd_handle* h) {
+  return rfft_register_path(h) || (h->cfg.N_t >= 8 && h->twiddle != nullptr);
 }
 
 int pd_fft_plan(pd_handle* h) {
@@ -879,6 +982,10 @@ int pd_fft_plan(pd_handle* h) {
     PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     PD_CUDA(cudaFuncSetAttribute(pd_fft_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+    PD_CUDA(cudaFuncSetAttribute(pd_rfft_pair_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+    PD_CUDA(cudaFuncSetAttribute(pd_rfft_pair_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
   }
   return PD_OK;
@@ -977,10 +1084,12 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
 //   !TO_FREQ: D[k] = Wu[k] + i Wp[k] (k <= N/2), D[k] = conj(Wu[N-k]) + i conj(Wp[N-k]) (k > N/2);
 //             y_u + i y_p = FFT(D)
 // x / y are (2, n, N_t) float64, the half spectra (2, n, KP) complex; one "line" = one node.
-template <int R0, int R1, int R2, int R3, bool TO_FREQ>
+// GAM (alpha != 1, an extension): the samples are scaled by gam[time index] on load (TO_FREQ: Gamma) or on store
+// (!TO_FREQ: Gamma^-1).
+template <int R0, int R1, int R2, int R3, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nnodes,
-                    const cplx* __restrict__ tw) {
+                    const cplx* __restrict__ tw, const double* __restrict__ gam) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   constexpr int H = N / 2;
@@ -1004,7 +1113,10 @@ pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64
       cplx* gu = reinterpret_cast<cplx*>(out_) + nd * KP;
       cplx* gp = gu + nnodes * KP;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) io[q] = cmake(xu[t + T * q], xp[t + T * q]);
+      for (int q = 0; q < 16; ++q) {
+        io[q] = cmake(xu[t + T * q], xp[t + T * q]);
+        if (GAM) io[q] = cscale(io[q], gam[t + T * q]);
+      }
       if (R2 == 1) {
         pow2_pass<R0, false, true, false, true, false>(nullptr, nullptr, sm, tw, N, 1, t, T, 1.0, live, io);
         pow2_pass<(R1 > 1 ? R1 : 2), false, false, true, false, true>(nullptr, nullptr, sm, tw, N, R0, t, T, 1.0, live, io);
@@ -1074,8 +1186,9 @@ pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64
 #pragma unroll
           for (int r = 0; r < NL; ++r) {
             const int i = t + u * T + r * NsL;
-            yu[i] = io[u * NL + r].x;
-            yp[i] = io[u * NL + r].y;
+            const double g = GAM ? gam[i] : 1.0;
+            yu[i] = GAM ? io[u * NL + r].x * g : io[u * NL + r].x;
+            yp[i] = GAM ? io[u * NL + r].y * g : io[u * NL + r].y;
           }
       }
       __syncthreads();
@@ -1084,81 +1197,112 @@ pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64
 }
 
 template <int R0, int R1, int R2, int R3>
-static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st) {
+static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st,
+                            int with_gamma) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   int threads = T < 256 ? 256 : T;
   int lpb = threads / T;
   size_t smem = (size_t)lpb * (N + N / 16) * sizeof(cplx);
   int64_t nblk = (nnodes + lpb - 1) / lpb;
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (to_freq ? 0 : N) : nullptr;
+#define PD_RFFT_PAIR_GO(TF, GM)                                            \
+  do {                                                                     \
+    auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, TF, GM>;                  \
+    PD_SET_SMEM_ONCE(k, smem);                                             \
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle, gam); \
+  } while (0)
   if (to_freq) {
-    auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, true>;
-    PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
+    if (gam) PD_RFFT_PAIR_GO(true, true); else PD_RFFT_PAIR_GO(true, false);
   } else {
-    auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, false>;
-    PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nnodes, h->twiddle);
+    if (gam) PD_RFFT_PAIR_GO(false, true); else PD_RFFT_PAIR_GO(false, false);
   }
+#undef PD_RFFT_PAIR_GO
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
 }
 
 // both fields of `nnodes` nodes at once: (2, nnodes, N_t) float64 <-> (2, nnodes, KP) complex half spectra
-int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st) {
+int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes, int to_freq, cudaStream_t st,
+                        int with_gamma) {
   if (nnodes <= 0) return PD_OK;
+  const int g = with_gamma;
   switch (h->cfg.N_t) {
-    case 128:  return launch_rfft_pair<16, 8, 1, 1>(h, in, out, nnodes, to_freq, st);
-    case 256:  return launch_rfft_pair<16, 16, 1, 1>(h, in, out, nnodes, to_freq, st);
-    case 512:  return launch_rfft_pair<16, 8, 4, 1>(h, in, out, nnodes, to_freq, st);
-    case 1024: return launch_rfft_pair<16, 16, 4, 1>(h, in, out, nnodes, to_freq, st);
-    case 2048: return launch_rfft_pair<16, 16, 8, 1>(h, in, out, nnodes, to_freq, st);
-    case 4096: return launch_rfft_pair<16, 16, 16, 1>(h, in, out, nnodes, to_freq, st);
-    case 8192: return launch_rfft_pair<16, 16, 8, 4>(h, in, out, nnodes, to_freq, st);
+    case 128:  return launch_rfft_pair<16, 8, 1, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 256:  return launch_rfft_pair<16, 16, 1, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 512:  return launch_rfft_pair<16, 8, 4, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 1024: return launch_rfft_pair<16, 16, 4, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 2048: return launch_rfft_pair<16, 16, 8, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 4096: return launch_rfft_pair<16, 16, 16, 1>(h, in, out, nnodes, to_freq, st, g);
+    case 8192: return launch_rfft_pair<16, 16, 8, 4>(h, in, out, nnodes, to_freq, st, g);
     default: break;
   }
-  return -100;  // not covered (N_t = 16384): the caller falls back to the per-line kernel
+  if (rfft_register_path(h)) return -100;  // N_t = 16384: the caller falls back to the per-line packed kernel
+  // every other length: the shared-memory pair kernel
+  const int N = h->cfg.N_t;
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (to_freq ? 0 : N) : nullptr;
+  PassList pl;
+  pl.n = h->npass;
+  for (int i = 0; i < pl.n; ++i) pl.r[i] = h->radix[i];
+  const size_t smem = 2 * sizeof(cplx) * (size_t)N;
+  const int64_t cap = (int64_t)h->num_sms * 8;
+  const int64_t nblk = nnodes < cap ? nnodes : cap;
+  if (to_freq)
+    pd_rfft_pair_generic_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nnodes, h->twiddle, pl, gam);
+  else
+    pd_rfft_pair_generic_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(in, out, N, nnodes, h->twiddle, pl, gam);
+  PD_CHECK_LAUNCH();
+  h->launches++;
+  return PD_OK;
 }
 
 template <int R0, int R1, int R2, int R3>
-static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st) {
+static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st,
+                       int with_gamma) {
   constexpr int M = R0 * R1 * R2 * R3;
   constexpr int T = M / 16;
   int threads = T < 256 ? 256 : T;
   int lpb = threads / T;
   size_t smem = (size_t)lpb * (M + M / 16 + 16) * sizeof(cplx);
   int64_t nblk = (nlines + lpb - 1) / lpb;
+  const double* gam = (with_gamma && h->gamma_tab) ? h->gamma_tab + (to_freq ? 0 : 2 * M) : nullptr;
+#define PD_RFFT_GO(TF, GM)                                                                              \
+  do {                                                                                                  \
+    auto k = pd_rfft_kernel<R0, R1, R2, R3, TF, GM>;                                                    \
+    PD_SET_SMEM_ONCE(k, smem);                                                                          \
+    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half, gam);        \
+  } while (0)
   if (to_freq) {
-    auto k = pd_rfft_kernel<R0, R1, R2, R3, true>;
-    PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
+    if (gam) PD_RFFT_GO(true, true); else PD_RFFT_GO(true, false);
   } else {
-    auto k = pd_rfft_kernel<R0, R1, R2, R3, false>;
-    PD_SET_SMEM_ONCE(k, smem);
-    k<<<(unsigned)nblk, threads, smem, st>>>(in, out, nlines, h->twiddle, h->twiddle_half);
+    if (gam) PD_RFFT_GO(false, true); else PD_RFFT_GO(false, false);
   }
+#undef PD_RFFT_GO
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
 }
 
 // real lines of N_t samples <-> half spectra of N_t/2 + 1 complex numbers (power-of-two N_t in [128, 16384])
-int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st) {
+int pd_rfft_launch(pd_handle* h, const void* in, void* out, int64_t nlines, int to_freq, cudaStream_t st,
+                   int with_gamma) {
   if (nlines <= 0) return PD_OK;
-  if (!pd_rfft_supported(h)) {
-    pd_set_error("the real-input path needs a power-of-two N_t in [128, 16384] (got %d)", h->cfg.N_t);
+  const int g = with_gamma;
+  if (!rfft_register_path(h)) {
+    pd_set_error("the per-line packed real transform needs a power-of-two N_t in [128, 16384] (got %d); "
+                 "pd_stage_rfft_pair covers every N_t >= 8", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   switch (h->cfg.N_t / 2) {
-    case 64:   return launch_rfft<16, 4, 1, 1>(h, in, out, nlines, to_freq, st);
-    case 128:  return launch_rfft<16, 8, 1, 1>(h, in, out, nlines, to_freq, st);
-    case 256:  return launch_rfft<16, 16, 1, 1>(h, in, out, nlines, to_freq, st);
-    case 512:  return launch_rfft<16, 8, 4, 1>(h, in, out, nlines, to_freq, st);
-    case 1024: return launch_rfft<16, 16, 4, 1>(h, in, out, nlines, to_freq, st);
-    case 2048: return launch_rfft<16, 16, 8, 1>(h, in, out, nlines, to_freq, st);
-    case 4096: return launch_rfft<16, 16, 16, 1>(h, in, out, nlines, to_freq, st);
-    case 8192: return launch_rfft<16, 16, 8, 4>(h, in, out, nlines, to_freq, st);
+    case 64:   return launch_rfft<16, 4, 1, 1>(h, in, out, nlines, to_freq, st, g);
+    case 128:  return launch_rfft<16, 8, 1, 1>(h, in, out, nlines, to_freq, st, g);
+    case 256:  return launch_rfft<16, 16, 1, 1>(h, in, out, nlines, to_freq, st, g);
+    case 512:  return launch_rfft<16, 8, 4, 1>(h, in, out, nlines, to_freq, st, g);
+    case 1024: return launch_rfft<16, 16, 4, 1>(h, in, out, nlines, to_freq, st, g);
+    case 2048: return launch_rfft<16, 16, 8, 1>(h, in, out, nlines, to_freq, st, g);
+    case 4096: return launch_rfft<16, 16, 16, 1>(h, in, out, nlines, to_freq, st, g);
+    case 8192: return launch_rfft<16, 16, 8, 4>(h, in, out, nlines, to_freq, st, g);
     default: break;
   }
   pd_set_error("pd_rfft_launch: unsupported N_t %d", h->cfg.N_t);

@@ -110,7 +110,7 @@ __device__ __forceinline__ void cluster_store(uint32_t addr, cplx v) {
 }
 
 template <int R, bool INV, bool FIRST, bool LAST, bool PRE = false, bool KEEP = false, bool CLARRIVE = false,
-          bool GAM = false>
+          int GAM = 0>
 __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
                                           cplx* sm, const cplx* __restrict__ tw, int N, int Ns,
                                           int t, int T, double scale, bool live, cplx* io = nullptr,
@@ -118,7 +118,8 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
   // GAM / gam (alpha != 1 only; a template flag so that the alpha = 1 kernels carry no trace of it -- a run-time
   // test on the pointer inside the load loop cost the inverse transform 17 %): Gamma_alpha time weights fused into the transform -- the samples are scaled
   // by gam[time index] as the FIRST pass loads them (Gamma before the inverse FFT) or as the LAST pass stores them
-  // (Gamma^-1 after the forward FFT): no separate elementwise sweep.
+  // (Gamma^-1 after the forward FFT): no separate elementwise sweep.  GAM = 1: complex samples, one weight each;
+  // GAM = 2: the packed real line of pd_rfft_kernel (element i holds the real samples 2i and 2i + 1).
   constexpr int NB = 16 / R;  // butterflies per thread
   const int NR = N / R;
   const int tws = N / (Ns * R);
@@ -133,7 +134,11 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         x = io[u * R + q];
       } else {
         x = FIRST ? gsrc[j + q * NR] : sm[pad16(j + q * NR)];
-        if (GAM && FIRST) x = cscale(x, gam[j + q * NR]);
+        if (GAM == 1 && FIRST) x = cscale(x, gam[j + q * NR]);
+        if (GAM == 2 && FIRST) {
+          x.x *= gam[2 * (j + q * NR)];
+          x.y *= gam[2 * (j + q * NR) + 1];
+        }
         if (FIRST && INV) x.y = -x.y;
       }
       v[u][q] = x;
@@ -180,7 +185,11 @@ __device__ __forceinline__ void pow2_pass(const cplx* __restrict__ gsrc, cplx* _
         io[u * R + r] = x;
       } else if (LAST) {
         if (INV) x.y = -x.y;
-        if (live) gdst[base + r * Ns] = cscale(x, GAM ? scale * gam[base + r * Ns] : scale);
+        if (GAM == 2) {
+          x.x *= gam[2 * (base + r * Ns)];
+          x.y *= gam[2 * (base + r * Ns) + 1];
+        }
+        if (live) gdst[base + r * Ns] = cscale(x, GAM == 1 ? scale * gam[base + r * Ns] : scale);
       } else {
         sm[pad16(base + r * Ns)] = x;
       }

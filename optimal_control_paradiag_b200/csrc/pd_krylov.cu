@@ -819,7 +819,7 @@ extern "C" int pd_gmres(pd_handle* h, const void* b_dev, void* x_dev, double rto
 extern "C" int pd_gmres_real(pd_handle* h, const void* b_dev, void* x_dev, double rtol, double atol, int restart,
                              int max_it, int* its_out, double* hist, int* reason_out, void* stream) {
   if (h && !pd_rfft_supported(h)) {
-    pd_set_error("pd_gmres_real: needs a power-of-two N_t in [128, 16384] (got %d); use pd_gmres", h->cfg.N_t);
+    pd_set_error("pd_gmres_real: needs N_t >= 8 (got %d); use pd_gmres", h->cfg.N_t);
     return PD_ERR_UNSUPPORTED;
   }
   return gmres_impl(h, b_dev, x_dev, rtol, atol, restart, max_it, its_out, hist, reason_out, stream, 1);

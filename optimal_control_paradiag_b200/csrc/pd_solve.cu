@@ -296,7 +296,10 @@ __device__ __forceinline__ void slab_functionals(const KCoef& kc, const SolvePar
     }
   }
   sP = cmake(0, 0); sM = cmake(0, 0);
-  if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+  if (!sp.first_dirichlet) {
+    if (sp.al) rotate_in<true>(kc, w[kk], w[sp.plane + kk], sP, sM);
+    else rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+  }
 }
 
 // ------------------------------------------------ top interface system (PCR in smem)
@@ -623,7 +626,10 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
       if (!up) {
         const cplx fv = cfma(z, rvL, lv.F[0][(int64_t)rhs * K + kk]);
         cplx sP = cmake(0, 0), sM = cmake(0, 0);
-        if (!sp.first_dirichlet) rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+        if (!sp.first_dirichlet) {
+          if (sp.al) rotate_in<true>(kc, w[kk], w[sp.plane + kk], sP, sM);
+          else rotate_in<false>(kc, w[kk], w[sp.plane + kk], sP, sM);
+        }
         for (int p = 0; p < cm.G; ++p) {
           cplx* g = cm.peer_gath[p] + slot;
           g[0] = fv; g[4 * cm.kmax] = rhs ? sM : sP;
@@ -1164,7 +1170,7 @@ int pd_solve_plan(pd_handle* h) {
   // one-launch sequential interface (pd_solve_iface_thomas_kernel): factorise the level-1 system once
   if (pl->nlev >= 1 && h->iface_thomas_max > 0 && pl->rows[1] <= h->iface_thomas_max &&
       (pl->rows[1] > PD_PCR_MAX || h->slab_count > 1 || getenv("PD_ITHOMAS_MAX"))) {
-    const bool want_half = pd_rfft_supported(h) && h->cfg.alpha == 1.0;
+    const bool want_half = pd_rfft_supported(h);
     for (int half = 0; half <= (want_half ? 1 : 0); ++half) {
       SolveParams sp; Levels lv; SlabPtrs sl;
       fill_params(h, sp, lv, sl, half);
@@ -1448,7 +1454,10 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
   bool pushed = false;
   if (sp.nlev >= 1) {
     if (!passA_done) {
-      pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+      if (sp.al)
+        pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+      else
+        pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
       PD_CHECK_LAUNCH();
       h->launches++;
     }
@@ -1464,7 +1473,10 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
     // a single chunk: its first / last entries come from one forward sweep; reuse pass A with a
     // private F buffer (zout is free at this point: 4K entries >= 2K)
     lv.F[0] = pl->zout;
-    pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+    if (sp.al)
+      pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+    else
+      pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) { cudaEventRecord(ev[0], st); cudaEventRecord(ev[1], st); }
@@ -1535,7 +1547,10 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   }
   PD_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[0], st);
-  pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  if (sp.al)
+    pd_solve_passB_kernel<true, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+  else
+    pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches += 2;
   return PD_OK;

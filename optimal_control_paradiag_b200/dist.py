@@ -43,7 +43,7 @@ def slab_bounds(total, parts):
 
 class DistributedDiagFFTPC:
     def __init__(self, N_x, N_t, T=2.0, gamma=1.0, device=0, group=None, backend_factory=None,
-                 mode="alltoall", transport=None):
+                 mode="alltoall", transport=None, alpha=1.0):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -60,12 +60,15 @@ class DistributedDiagFFTPC:
             from .handle import ParaDiagHandle
 
             def backend_factory(**kw):
-                return ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, device=device, **kw)
+                return ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, alpha=alpha, device=device, **kw)
             self.device = torch.device(f"cuda:{device}")
         else:
             self.device = torch.device("cpu")
         if mode not in ("alltoall", "slab"):
             raise ValueError(f"unknown mode {mode!r}")
+        self.alpha = float(alpha)
+        if self.alpha != 1.0 and mode != "slab":
+            raise NotImplementedError("alpha != 1 (an extension) is available in slab mode only")
         self.mode = mode
         c128 = torch.complex128
         self.local_size = 2 * self.n_r * self.N_t
@@ -212,18 +215,33 @@ class DistributedDiagFFTPC:
         t = self.torch
         if self.transport == "peer":
             return self.backend.slab_apply(x_local.reshape(-1), y_local.reshape(-1))          # :491-553
+        if self.alpha != 1.0:
+            # (collective transport + the alpha extension: Gamma / Gamma^-1 as plain elementwise products here; the
+            # peer-store transport has them inside the transforms)
+            x_local = (x_local.reshape(-1, self.N_t) * self._gamma(False)).reshape(-1)
         self.backend.stage_fft(x_local.reshape(-1), self.w_time, 2 * self.n_r, True)      # :500-501
         self.backend.slab_reduce(self.w_time, self.fl_out)
         self.dist.all_gather_into_tensor(t.view_as_real(self.gathered).reshape(-1),
                                          t.view_as_real(self.fl_out).reshape(-1), group=self.group)
         self.backend.slab_finish(self.w_time, self.gathered)                               # :445-540
         self.backend.stage_fft(self.w_time, y_local.reshape(-1), 2 * self.n_r, False)     # :547-548
+        if self.alpha != 1.0:
+            y_local.reshape(-1, self.N_t).mul_(self._gamma(True))
         return y_local
+
+    def _gamma(self, inverse):
+        """Gamma_alpha time weights a^j (inverse: a^-j), a = alpha^(1/N_t), as a float64 device vector."""
+        t = self.torch
+        if getattr(self, "_gam", None) is None:
+            j = t.arange(self.N_t, dtype=t.float64, device=self.device) / self.N_t
+            lna = float(np.log(self.alpha))
+            self._gam = (t.exp(lna * j), t.exp(-lna * j))
+        return self._gam[1 if inverse else 0]
 
     def apply_real(self, x_local, y_local=None):
         """The same apply for REAL node-slab blocks (float64, (2, n_r, N_t)): what GMRES feeds the PC in this
         real problem.  Half spectrum (k <= N_t/2) in every stage: half the bytes of ``apply``, and the
-        all-gather shrinks to 6 (N_t/2 + 1) values per rank.  Slab mode, power-of-two N_t in [128, 16384]."""
+        all-gather shrinks to 6 (N_t/2 + 1) values per rank.  Slab mode, N_t >= 8."""
         t = self.torch
         if self.mode != "slab":
             raise NotImplementedError("the real-input distributed apply uses the slab decomposition")
@@ -239,12 +257,16 @@ class DistributedDiagFFTPC:
             self._w_half = t.empty(2 * self.n_r * Kp, dtype=c128, device=self.device)
             self._fl_half = t.empty(6 * Kp, dtype=c128, device=self.device)
             self._gath_half = t.empty(self.world * 6 * Kp, dtype=c128, device=self.device)
+        if self.alpha != 1.0:
+            x_local = (x_local.reshape(-1, self.N_t) * self._gamma(False)).reshape(-1)
         self.backend.stage_rfft_pair(x_local.reshape(-1), self._w_half, self.n_r, True)
         self.backend.slab_reduce_half(self._w_half, self._fl_half)
         self.dist.all_gather_into_tensor(t.view_as_real(self._gath_half).reshape(-1),
                                          t.view_as_real(self._fl_half).reshape(-1), group=self.group)
         self.backend.slab_finish_half(self._w_half, self._gath_half)
         self.backend.stage_rfft_pair(self._w_half, y_local.reshape(-1), self.n_r, False)
+        if self.alpha != 1.0:
+            y_local.reshape(-1, self.N_t).mul_(self._gamma(True))
         return y_local
 
     def apply_host(self, x_host, y_host):
@@ -457,7 +479,7 @@ class LocalSlabGroup:
     only one GPU is leased: every first half ``pd_slab_apply_begin`` is issued before any second half, so no
     kernel ever waits for one queued behind it) or on several GPUs with peer access (one per slab)."""
 
-    def __init__(self, N_x, N_t, G, T=2.0, gamma=1.0, devices=None, split_on_one_stream=False):
+    def __init__(self, N_x, N_t, G, T=2.0, gamma=1.0, devices=None, split_on_one_stream=False, alpha=1.0):
         import torch
 
         from .handle import ParaDiagHandle
@@ -465,7 +487,8 @@ class LocalSlabGroup:
         self.N_x, self.N_t, self.n, self.G = int(N_x), int(N_t), int(N_x) + 1, int(G)
         self.devices = [0] * self.G if devices is None else [int(d) for d in devices]
         self.ncount, self.noff = slab_bounds(self.n, self.G)
-        self.handles = [ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, device=self.devices[r], slab_rank=r, slab_count=G)
+        self.handles = [ParaDiagHandle(N_x, N_t, T=T, gamma=gamma, alpha=alpha, device=self.devices[r], slab_rank=r,
+                                       slab_count=G)
                         for r in range(self.G)]
         bases = [h.slab_comm_create()[1] for h in self.handles]
         for h in self.handles:

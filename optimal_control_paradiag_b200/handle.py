@@ -68,9 +68,9 @@ class ParaDiagHandle:
 
     @property
     def real_path_supported(self):
-        """True when pd_pc_apply_real exists for this handle: power-of-two N_t in [128, 16384], alpha = 1."""
-        N = self.N_t
-        return self.alpha == 1.0 and N >= 128 and N <= 16384 and (N & (N - 1)) == 0
+        """True when pd_pc_apply_real exists for this handle: every N_t >= 8 (register pipelines for the powers of
+        two in [128, 16384], the shared-memory pair kernel for the rest -- the upstream default N_t = 81 included)."""
+        return self.N_t >= 8
 
     @property
     def launch_count(self):

@@ -171,9 +171,9 @@ class DiagFFTPC(PCBase):
         self.dpc = None
         if self._want_distributed(pc, cfg):
             from .dist import DistributedDiagFFTPC
-            if self.alpha != 1.0 or self.node_order is not None:
-                raise NotImplementedError("the distributed backend supports alpha = 1 and monotone node order")
-            self.dpc = DistributedDiagFFTPC(self.N_x, self.N_t, T=self.T, gamma=self.gamma,
+            if self.node_order is not None:
+                raise NotImplementedError("the distributed backend supports the monotone node order only")
+            self.dpc = DistributedDiagFFTPC(self.N_x, self.N_t, T=self.T, gamma=self.gamma, alpha=self.alpha,
                                             device=int(cfg.get("device", 0)), group=cfg.get("group"),
                                             backend_factory=cfg.get("backend_factory"), mode="slab")
             self.handle = self.dpc.backend
@@ -242,8 +242,8 @@ class DiagFFTPC(PCBase):
                 raise NotImplementedError("node_order is only supported on the host-Vec path")
             if x.dtype == torch.float64:
                 # real vectors (what GMRES feeds the PC in this problem): half-spectrum fast path where the
-                # library has one (power-of-two N_t in [128, 16384], alpha = 1); every other size -- the
-                # upstream default N_t = 81 included -- goes through the complex apply like any other vector
+                # library has one (every N_t >= 8, the upstream default N_t = 81 included); shorter time axes go
+                # through the complex apply like any other vector
                 if self.handle.real_path_supported:
                     self.handle.pc_apply_real(x.reshape(-1), y.reshape(-1))
                 else:

@@ -50,13 +50,13 @@ def test_invalid_config_is_rejected_before_touching_cuda():
     assert b"ABI" in lib.pd_last_error()
     cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=1, N_t=8, T=2.0, gamma=1.0, alpha=1.0)
     assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_INVALID
-    # alpha outside (0, 1] is invalid; alpha != 1 (an extension) on a sharded handle is unsupported
+    # alpha outside (0, 1] is invalid; alpha != 1 (an extension) on a frequency-sharded stage handle is unsupported
     cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=8, N_t=8, T=2.0, gamma=1.0, alpha=1.5)
     assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_INVALID
     cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=8, N_t=8, T=2.0, gamma=1.0, alpha=0.0)
     assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_INVALID
     cfg = _lib.pd_config(abi_version=_lib.PD_ABI_VERSION, N_x=8, N_t=8, T=2.0, gamma=1.0, alpha=0.1,
-                         slab_rank=0, slab_count=2)
+                         k_begin=0, k_count=4)
     assert lib.pd_create(C.byref(cfg), C.byref(h)) == _lib.PD_ERR_UNSUPPORTED
     assert lib.pd_create(None, C.byref(h)) == _lib.PD_ERR_INVALID
     assert lib.pd_destroy(None) == 0

@@ -52,7 +52,8 @@ def test_peer_exchange_on_one_gpu_equals_single_gpu_apply(N_x, N_t, G):
         assert all(not to for to, _ in st) and all(ep == 5 for _, ep in st), st
 
 
-@pytest.mark.parametrize("N_x,N_t,G", [(255, 128, 3), (1024, 1024, 4), (40, 16384, 2), (4096, 256, 8)])
+@pytest.mark.parametrize("N_x,N_t,G", [(255, 128, 3), (1024, 1024, 4), (40, 16384, 2), (4096, 256, 8),
+                                        (80, 81, 2), (255, 100, 3), (64, 16, 4)])   # + the shared-memory pair kernel
 def test_peer_exchange_real_input_path_on_one_gpu(N_x, N_t, G):
     with ParaDiagHandle(N_x, N_t) as h, LocalSlabGroup(N_x, N_t, G) as grp:
         for rep in range(3):
