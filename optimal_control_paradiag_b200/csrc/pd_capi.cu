@@ -127,6 +127,16 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
   cudaDeviceProp prop;
   PD_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   h->num_sms = prop.multiProcessorCount;
+  {
+    // Programmatic dependent launch of the apply's kernels (PD_KLAUNCH in pd_common.cuh).  Measured on B200
+    // (bench.py, L2 flushed between applies): cfg1 46.8 -> 45.7 us, cfg2 80.0 -> 76.2 us, but cfg5 0.670 -> 0.784 ms
+    // and cfg3 +13 %: the streaming passes are persistent grids with a static, balanced split of the work, and
+    // CTAs that become resident while the previous kernel drains land unevenly on the SMs.  So it is on only where
+    // the grids are below one wave (vector <= 64 MiB); PD_PDL=0 / 1 forces it off / on.
+    const char* e = getenv("PD_PDL");
+    const double vec_bytes = 32.0 * (double)h->n * (double)cfg->N_t;
+    h->pdl = e ? (e[0] == '1') : (vec_bytes <= 64.0 * 1024 * 1024);
+  }
   int rc = pd_fft_plan(h);
   if (rc == PD_OK) rc = pd_solve_plan(h);
   if (rc != PD_OK) {

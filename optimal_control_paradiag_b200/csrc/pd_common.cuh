@@ -78,6 +78,41 @@ struct PdDeviceGuard {
 };
 #define PD_ON_DEVICE(h) PdDeviceGuard pd_device_guard_((h)->cfg.device)
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The kernels of one apply depend on each other in a chain, and at the small and the sharded sizes the launch
+// latency and the drain / ramp at every kernel boundary are a visible share of the apply.  Kernels launched through
+// PD_KLAUNCH carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled as soon as every
+// CTA of the preceding kernel has executed `griddepcontrol.launch_dependents` (or exited), i.e. while that kernel
+// drains.  Every such kernel starts with pd_pdl_enter(): it releases ITS dependents and then blocks in
+// `griddepcontrol.wait` until the preceding grid has completed and its writes are visible -- before its first global
+// access other than plan-time tables, so read-after-write and write-after-read across kernels stay ordered
+// (transitively along the chain: a kernel cannot complete before its own wait has returned).  Launched without the
+// attribute (PD_PDL=0, or any plain <<< >>> launch) both instructions are no-ops.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pd_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... P, typename... A>
+static inline cudaError_t pd_klaunch(int pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+// kernel names with template commas go in parentheses: PD_KLAUNCH((k<a, b>), grid, block, smem, stream, args...)
+#define PD_KLAUNCH(kernel, grid, block, smem, st, ...) \
+  (void)pd_klaunch(h->pdl, kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+#endif
+
 // ------------------------------------------------------------------ the handle
 static const int PD_MAX_FFT_PASSES = 16;
 
@@ -148,6 +183,7 @@ struct pd_handle {
   int opt_gmres_correction;  // pd_set_option "gmres_residual_correction"
   int opt_slab_no_overlap;   // pd_set_option "slab_overlap" 0: the slab apply stays on the caller's stream
   int opt_kry_real;          // pd_set_option "krylov_real_vectors"
+  int pdl;                   // 1: the apply's kernels are launched with programmatic stream serialisation (PD_KLAUNCH)
   int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;

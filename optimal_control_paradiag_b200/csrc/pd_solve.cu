@@ -51,6 +51,7 @@ template <bool AL>
 __global__ void __launch_bounds__(PD_KB, 4)
 pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
                       SolveParams sp, cplx* __restrict__ lastl) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
@@ -69,6 +70,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
 // recurrences, emits f_c and the partial rhs of its trailing separator for level lev + 1.
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.kend) return;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
@@ -117,6 +119,7 @@ pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
 // trailing separator) are overwritten by the solution in R[lev].
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_LG][PD_KB];  // per-thread column of chunk pivots
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.kend) return;
@@ -312,6 +315,7 @@ template <bool PUSH>
 __global__ void __launch_bounds__(PD_PCR_THREADS)
 pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __restrict__ w, SlabPtrs sl,
                     SlabCommDev cm) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   __shared__ cplx c_off[32], c_dmain[32], c_dlast[32], c_offb[32];
   const int n = sp.rows[lev];
@@ -495,6 +499,7 @@ template <bool PUSH, int PD_IRING>
 __global__ void __launch_bounds__(4 * PD_ITK)
 pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
                              SlabPtrs sl, SlabCommDev cm) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   __shared__ cplx xch[4 * PD_ITK][2];                                // meeting point: (last value, off * pivot)
   constexpr int NT = 4 * PD_ITK;
@@ -647,6 +652,7 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
 template <bool SLAB, bool AL>
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp, SlabPtrs sl) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
@@ -752,7 +758,10 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
 }
 
 // The same as a launch of its own, for the two-stream variant of the apply (after the join of both halves).
-__global__ void pd_slab_epoch_bump_kernel(unsigned long long* epoch) { *epoch += 1ull; }
+__global__ void pd_slab_epoch_bump_kernel(unsigned long long* epoch) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+  *epoch += 1ull;
+}
 
 // ------------------------------------------------------------ slab-mode kernels
 // Slab mode = x-slab sharding kept through the solve (no transposes): rank r owns a contiguous node
@@ -767,6 +776,7 @@ template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
                            cplx* __restrict__ out, SlabCommDev cm) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
   if (kk < sp.kend) {
@@ -830,6 +840,7 @@ __global__ void __launch_bounds__(PD_KB)
 pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveParams sp, SlabGeom sg,
                       const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm,
                       cplx* __restrict__ zsep, const cplx* __restrict__ green) {
+  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
   if (WAIT) {
     // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
     const unsigned long long ep = *cm.epoch + 1ull;
@@ -1053,10 +1064,10 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
 #define PD_IFACE_LAUNCH(RING)                                                                                       \
   do {                                                                                                              \
     if (push)                                                                                                       \
-      pd_solve_iface_thomas_kernel<true, RING><<<nblk, 4 * PD_ITK, PD_ISMEM(RING), st>>>(lv, sp, piv, push->w,      \
+      PD_KLAUNCH((pd_solve_iface_thomas_kernel<true, RING>), nblk, 4 * PD_ITK, PD_ISMEM(RING), st, lv, sp, piv, push->w,      \
                                                                                        push->sl, push->cm);         \
     else                                                                                                            \
-      pd_solve_iface_thomas_kernel<false, RING><<<nblk, 4 * PD_ITK, PD_ISMEM(RING), st>>>(lv, sp, piv, nullptr,     \
+      PD_KLAUNCH((pd_solve_iface_thomas_kernel<false, RING>), nblk, 4 * PD_ITK, PD_ISMEM(RING), st, lv, sp, piv, nullptr,     \
                                                                                         nosl, nocm);                \
   } while (0)
     if (ring == 8) PD_IFACE_LAUNCH(8);
@@ -1068,7 +1079,7 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
     return PD_OK;
   }
   for (int lev = 1; lev < top; ++lev) {
-    pd_solve_level_reduce_kernel<<<stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    PD_KLAUNCH(pd_solve_level_reduce_kernel, stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st, lv, sp, lev);
     PD_CHECK_LAUNCH();
     h->launches++;
   }
@@ -1081,19 +1092,19 @@ static int run_interface(pd_handle* h, const SolveParams& sp, const Levels& lv, 
   const size_t smem = (size_t)n * kpb * 64;
   const int nblk = (ncol + kpb - 1) / kpb;
   if (push && top == 1 && kpb % PD_FKB == 0) {
-    pd_solve_pcr_kernel<true><<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb, push->w, push->sl, push->cm);
+    PD_KLAUNCH((pd_solve_pcr_kernel<true>), nblk, PD_PCR_THREADS, smem, st, lv, sp, top, kpb, push->w, push->sl, push->cm);
     if (pushed) *pushed = true;
   } else {
     SlabPtrs nosl;
     SlabCommDev nocm;
     memset(&nosl, 0, sizeof(nosl));
     memset(&nocm, 0, sizeof(nocm));
-    pd_solve_pcr_kernel<false><<<nblk, PD_PCR_THREADS, smem, st>>>(lv, sp, top, kpb, nullptr, nosl, nocm);
+    PD_KLAUNCH((pd_solve_pcr_kernel<false>), nblk, PD_PCR_THREADS, smem, st, lv, sp, top, kpb, nullptr, nosl, nocm);
   }
   PD_CHECK_LAUNCH();
   h->launches++;
   for (int lev = top - 1; lev >= 1; --lev) {
-    pd_solve_level_back_kernel<<<stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st>>>(lv, sp, lev);
+    PD_KLAUNCH(pd_solve_level_back_kernel, stream_grid(h, ncol, sp.rows[lev + 1] + 1), PD_KB, 0, st, lv, sp, lev);
     PD_CHECK_LAUNCH();
     h->launches++;
   }
@@ -1245,9 +1256,9 @@ static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, 
   const dim3 grid0 = stream_grid(h, kend - koff, sp.rows[1] + 1, 2);
   if (sp.nlev >= 1) {
     if (sp.al)
-      pd_solve_passA_kernel<true><<<gridA, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+      PD_KLAUNCH((pd_solve_passA_kernel<true>), gridA, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, nullptr);
     else
-      pd_solve_passA_kernel<false><<<gridA, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+      PD_KLAUNCH((pd_solve_passA_kernel<false>), gridA, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, nullptr);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) cudaEventRecord(ev[0], st);
@@ -1260,9 +1271,9 @@ static int solve_range(pd_handle* h, cplx* w, SolveParams sp, const Levels& lv, 
     cudaEventRecord(ev[1], st);
   }
   if (sp.al)
-    pd_solve_passB_kernel<false, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<false, true>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   else
-    pd_solve_passB_kernel<false, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<false, false>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1289,9 +1300,9 @@ int pd_solve_passA_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st)
   sp.c0 = c0; sp.c1 = c1;
   const dim3 grid0 = stream_grid(h, sp.K, c1 - c0, 4);
   if (sp.al)
-    pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+    PD_KLAUNCH((pd_solve_passA_kernel<true>), grid0, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, nullptr);
   else
-    pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, nullptr);
+    PD_KLAUNCH((pd_solve_passA_kernel<false>), grid0, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, nullptr);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1307,9 +1318,9 @@ int pd_solve_passB_range(pd_handle* h, cplx* w, int c0, int c1, cudaStream_t st)
   sp.c0 = c0; sp.c1 = c1;
   const dim3 grid0 = stream_grid(h, sp.K, c1 - c0, 2);
   if (sp.al)
-    pd_solve_passB_kernel<false, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<false, true>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   else
-    pd_solve_passB_kernel<false, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<false, false>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1455,9 +1466,9 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
   if (sp.nlev >= 1) {
     if (!passA_done) {
       if (sp.al)
-        pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+        PD_KLAUNCH((pd_solve_passA_kernel<true>), grid0, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, sl.lastl);
       else
-        pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], lv.R[1], sp, sl.lastl);
+        PD_KLAUNCH((pd_solve_passA_kernel<false>), grid0, PD_KB, 0, st, w, lv.F[0], lv.R[1], sp, sl.lastl);
       PD_CHECK_LAUNCH();
       h->launches++;
     }
@@ -1474,9 +1485,9 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
     // private F buffer (zout is free at this point: 4K entries >= 2K)
     lv.F[0] = pl->zout;
     if (sp.al)
-      pd_solve_passA_kernel<true><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+      PD_KLAUNCH((pd_solve_passA_kernel<true>), grid0, PD_KB, 0, st, w, lv.F[0], nullptr, sp, sl.lastl);
     else
-      pd_solve_passA_kernel<false><<<grid0, PD_KB, 0, st>>>(w, lv.F[0], nullptr, sp, sl.lastl);
+      PD_KLAUNCH((pd_solve_passA_kernel<false>), grid0, PD_KB, 0, st, w, lv.F[0], nullptr, sp, sl.lastl);
     PD_CHECK_LAUNCH();
     h->launches++;
     if (ev) { cudaEventRecord(ev[0], st); cudaEventRecord(ev[1], st); }
@@ -1485,9 +1496,9 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
   if (out) {
     SlabCommDev none;
     memset(&none, 0, sizeof(none));
-    pd_slab_functionals_kernel<false><<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, out, none);
+    PD_KLAUNCH((pd_slab_functionals_kernel<false>), kblocks, PD_KB, 0, st, w, lv, sp, sl, out, none);
   } else {
-    pd_slab_functionals_kernel<true><<<kblocks, PD_KB, 0, st>>>(w, lv, sp, sl, nullptr, comm_dev_of(h));
+    PD_KLAUNCH((pd_slab_functionals_kernel<true>), kblocks, PD_KB, 0, st, w, lv, sp, sl, nullptr, comm_dev_of(h));
   }
   PD_CHECK_LAUNCH();
   h->launches++;
@@ -1496,7 +1507,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
 
 int pd_slab_epoch_bump_launch(pd_handle* h, cudaStream_t st) {
   SolvePlan* pl = plan_of(h);
-  pd_slab_epoch_bump_kernel<<<1, 1, 0, st>>>(pl->comm_epoch);
+  PD_KLAUNCH(pd_slab_epoch_bump_kernel, 1, 1, 0, st, pl->comm_epoch);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1525,7 +1536,7 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   const dim3 ggrid(kblocks, gy);
   cplx* zsep = sp.nlev >= 1 ? lv.R[1] : nullptr;
 #define PD_GLOBAL_LAUNCH(W, GT_, GPTR, GSTR, CM)                                                                   \
-  pd_slab_global_kernel<W, GT_><<<ggrid, PD_KB, 0, st>>>(GPTR, GSTR, sp, pl->sg, coef, pl->zout, CM, zsep, sl.green)
+  PD_KLAUNCH((pd_slab_global_kernel<W, GT_>), ggrid, PD_KB, 0, st, GPTR, GSTR, sp, pl->sg, coef, pl->zout, CM, zsep, sl.green)
 #define PD_GLOBAL_DISPATCH(W, GPTR, GSTR, CM)                                                                      \
   switch (pl->sg.G) {                                                                                              \
     case 2: PD_GLOBAL_LAUNCH(W, 2, GPTR, GSTR, CM); break;                                                         \
@@ -1548,9 +1559,9 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   PD_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[0], st);
   if (sp.al)
-    pd_solve_passB_kernel<true, true><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<true, true>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   else
-    pd_solve_passB_kernel<true, false><<<grid0, PD_KB, 0, st>>>(w, lv.R[1], sp, sl);
+    PD_KLAUNCH((pd_solve_passB_kernel<true, false>), grid0, PD_KB, 0, st, w, lv.R[1], sp, sl);
   PD_CHECK_LAUNCH();
   h->launches += 2;
   return PD_OK;
