@@ -262,6 +262,23 @@ int pd_mdot(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* w_d
 int pd_maxpy(pd_handle* h, const void* V_dev, int64_t ld, int nv, const void* coef_dev, double sign,
              void* w_dev, int64_t len, void* norm2_out_dev, void* stream);
 
+/* The host-side algebra of one restarted-GMRES cycle as KSPGMRES keeps it (the solver :347-359 selects): Hessenberg
+ * column update with Givens rotations, residual-norm estimate, back substitution.  Host memory only, no CUDA calls.
+ * pd_gmres / pd_gmres_real use exactly this object internally; a distributed Krylov loop (dist.py) that owns its
+ * own collectives calls it through these entry points, so there is one implementation of the recurrence.
+ *   pd_hess_create : state for cycles of up to `restart` columns.
+ *   pd_hess_start  : begin a cycle with ||r0|| = beta.
+ *   pd_hess_push   : append column j (the j-th call of the cycle): hcol = j + 2 complex numbers (re, im pairs), the
+ *                    classical Gram-Schmidt coefficients h_0..h_j followed by the SQUARED norm of the orthogonalised
+ *                    vector (real part).  *resnorm_out = |g_{j+1}|, *hnorm_out (optional) = h_{j+1,j}.
+ *   pd_hess_solve  : y = H^-1 g for the columns pushed in this cycle (y_out: that many complex numbers).       */
+typedef struct pd_hessenberg pd_hessenberg;
+int pd_hess_create(int restart, pd_hessenberg** out);
+int pd_hess_destroy(pd_hessenberg* q);
+int pd_hess_start(pd_hessenberg* q, double beta);
+int pd_hess_push(pd_hessenberg* q, const void* hcol, double* resnorm_out, double* hnorm_out);
+int pd_hess_solve(pd_hessenberg* q, void* y_out, int* ncol_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,11 @@ SYMBOLS = {
     "pd_gmres_real": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),
     "pd_mdot": (_I, [_VP, _VP, _I64, _I, _VP, _I64, _VP, _VP]),
     "pd_maxpy": (_I, [_VP, _VP, _I64, _I, _VP, _D, _VP, _I64, _VP, _VP]),
+    "pd_hess_create": (_I, [_I, C.POINTER(_VP)]),
+    "pd_hess_destroy": (_I, [_VP]),
+    "pd_hess_start": (_I, [_VP, _D]),
+    "pd_hess_push": (_I, [_VP, _VP, C.POINTER(_D), C.POINTER(_D)]),
+    "pd_hess_solve": (_I, [_VP, _VP, C.POINTER(_I)]),
 }
 
 _lib = None
@@ -112,3 +117,43 @@ def check(status, allow=()):
     if status != PD_OK and status not in allow:
         raise ParaDiagError(status, load_library().pd_last_error().decode())
     return status
+
+
+class Hessenberg:
+    """Host-side state of one restarted-GMRES cycle (``pd_hess_*`` in include/paradiag.h): the same Givens /
+    Hessenberg recurrence ``pd_gmres`` runs internally, for Krylov loops that own their collectives (dist.py)."""
+
+    def __init__(self, restart):
+        import numpy as np
+        self.np = np
+        self.lib = load_library()
+        self.restart = int(restart)
+        self._q = C.c_void_p()
+        check(self.lib.pd_hess_create(self.restart, C.byref(self._q)))
+
+    def start(self, beta):
+        check(self.lib.pd_hess_start(self._q, float(beta)))
+
+    def push(self, hcol):
+        """hcol: complex array (h_0..h_j, squared norm of the orthogonalised vector); returns (|g_{j+1}|, h_{j+1,j})."""
+        a = self.np.ascontiguousarray(hcol, dtype=self.np.complex128)
+        rn, hn = _D(), _D()
+        check(self.lib.pd_hess_push(self._q, a.ctypes.data_as(_VP), C.byref(rn), C.byref(hn)))
+        return rn.value, hn.value
+
+    def solve(self):
+        y = self.np.empty(self.restart, dtype=self.np.complex128)
+        n = _I()
+        check(self.lib.pd_hess_solve(self._q, y.ctypes.data_as(_VP), C.byref(n)))
+        return y[:n.value].copy()
+
+    def close(self):
+        if self._q:
+            self.lib.pd_hess_destroy(self._q)
+            self._q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

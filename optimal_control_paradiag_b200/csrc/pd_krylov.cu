@@ -574,6 +574,98 @@ static inline hcplx hdiv(hcplx a, hcplx b) {
   return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
 }
 
+// The small host-side part of restarted GMRES as KSPGMRES keeps it (Control_Wave_PC.py:347-359 selects KSPGMRES with
+// classical Gram-Schmidt): the Hessenberg matrix of one cycle, reduced to triangular form column by column with
+// Givens rotations, the rotated right-hand side g whose last entry is the residual-norm estimate, and the back
+// substitution at the end of the cycle.  ONE implementation serves pd_gmres / pd_gmres_real here and, through the
+// pd_hess_* entry points, the distributed Krylov loop of dist.py (which owns the collectives but not this algebra).
+struct pd_hessenberg {
+  int restart;
+  int ncol;                   // columns pushed in the current cycle
+  std::vector<hcplx> H;       // column-major, stride restart + 1; grows with the columns pushed (restart = 300
+                              // would otherwise cost a 1.4 MB zero-fill per solve)
+  std::vector<hcplx> g, cs, sn;
+  explicit pd_hessenberg(int m) : restart(m), ncol(0), g(m + 1), cs(m), sn(m) {}
+  hcplx& at(int i, int j) { return H[(size_t)j * (restart + 1) + i]; }
+  void start(double beta) {
+    for (auto& e : g) e = {0, 0};
+    g[0] = {beta, 0};
+    ncol = 0;
+  }
+  // column j = ncol: hcol[0..j] = the Gram-Schmidt coefficients, hcol[j + 1].re = SQUARED norm of the orthogonalised
+  // vector.  Returns the residual-norm estimate |g_{j+1}|; *hnorm = h_{j+1,j}.
+  double push(const hcplx* hcol, double* hnorm) {
+    const int j = ncol;
+    if (H.size() < (size_t)(j + 1) * (restart + 1)) H.resize((size_t)(j + 1) * (restart + 1));
+    for (int i = 0; i <= j; ++i) at(i, j) = hcol[i];
+    const double hn = sqrt(fmax(hcol[j + 1].re, 0.0));
+    at(j + 1, j) = {hn, 0};
+    for (int i = 0; i < j; ++i) {
+      const hcplx a_ = at(i, j), b_ = at(i + 1, j);
+      at(i, j) = hadd(hmul(hconj(cs[i]), a_), hmul(hconj(sn[i]), b_));
+      at(i + 1, j) = hsub(hmul(cs[i], b_), hmul(sn[i], a_));
+    }
+    const hcplx a_ = at(j, j), b_ = at(j + 1, j);
+    const double den = sqrt(a_.re * a_.re + a_.im * a_.im + b_.re * b_.re + b_.im * b_.im);
+    if (den == 0.0) { cs[j] = {1, 0}; sn[j] = {0, 0}; }
+    else { cs[j] = {a_.re / den, a_.im / den}; sn[j] = {b_.re / den, b_.im / den}; }
+    at(j, j) = hadd(hmul(hconj(cs[j]), a_), hmul(hconj(sn[j]), b_));
+    at(j + 1, j) = {0, 0};
+    const hcplx gj = g[j];
+    g[j + 1] = hmul({-sn[j].re, -sn[j].im}, gj);
+    g[j] = hmul(hconj(cs[j]), gj);
+    ncol = j + 1;
+    if (hnorm) *hnorm = hn;
+    return habs(g[j + 1]);
+  }
+  // y = H^-1 g for the ncol columns of this cycle (upper triangular after the rotations)
+  void solve(hcplx* y) {
+    for (int i = ncol - 1; i >= 0; --i) {
+      hcplx s = g[i];
+      for (int k = i + 1; k < ncol; ++k) s = hsub(s, hmul(at(i, k), y[k]));
+      y[i] = hdiv(s, at(i, i));
+    }
+  }
+};
+
+extern "C" int pd_hess_create(int restart, pd_hessenberg** out) {
+  if (restart < 1 || !out) {
+    pd_set_error("pd_hess_create: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  *out = new pd_hessenberg(restart);
+  return PD_OK;
+}
+extern "C" int pd_hess_destroy(pd_hessenberg* q) {
+  delete q;
+  return PD_OK;
+}
+extern "C" int pd_hess_start(pd_hessenberg* q, double beta) {
+  if (!q) {
+    pd_set_error("pd_hess_start: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  q->start(beta);
+  return PD_OK;
+}
+extern "C" int pd_hess_push(pd_hessenberg* q, const void* hcol, double* resnorm_out, double* hnorm_out) {
+  if (!q || !hcol || !resnorm_out || q->ncol >= q->restart) {
+    pd_set_error("pd_hess_push: invalid argument or cycle full");
+    return PD_ERR_INVALID;
+  }
+  *resnorm_out = q->push(reinterpret_cast<const hcplx*>(hcol), hnorm_out);
+  return PD_OK;
+}
+extern "C" int pd_hess_solve(pd_hessenberg* q, void* y_out, int* ncol_out) {
+  if (!q || !y_out) {
+    pd_set_error("pd_hess_solve: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  q->solve(reinterpret_cast<hcplx*>(y_out));
+  if (ncol_out) *ncol_out = q->ncol;
+  return PD_OK;
+}
+
 static int ensure_basis(pd_handle* h, std::vector<cplx*>& V, int need, int64_t len) {
   // basis vectors are cached on the handle as one allocation each
   while ((int)V.size() < need) {
@@ -685,11 +777,8 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
   bool converged = false, first = true;
   PD_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * (size_t)len, st));
 
-  // Hessenberg matrix, column-major with stride restart + 1; columns are appended as the iteration proceeds
-  // (restart = 300 would otherwise cost a 1.4 MB zero-fill per solve, as much as a whole 5-iteration solve of
-  // the small configurations)
-  std::vector<hcplx> H, g(restart + 1), cs(restart), sn(restart), yk(restart);
-  auto Hat = [&](int i, int j) -> hcplx& { return H[(size_t)j * (restart + 1) + i]; };
+  pd_hessenberg hess(restart);   // Hessenberg / Givens state of one cycle (shared with the distributed loop)
+  std::vector<hcplx> yk(restart);
 
   while (!converged && (its < max_it || first)) {
     if ((rc = ensure_basis(h, kc->V, 1, alloc_len))) { pd_set_error("pd_gmres: out of device memory for the Krylov basis"); return rc; }
@@ -724,8 +813,7 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
     pd_normalize_kernel<<<nb1, 256, 0, st>>>(v0, hdev, len);
     PD_CHECK_LAUNCH();
     h->launches++;
-    for (auto& e : g) e = {0, 0};
-    g[0] = {beta, 0};
+    hess.start(beta);
     int jdone = 0;
     for (int j = 0; j < restart; ++j) {
       // a basis slot for w; if memory runs out, restart early with what we have
@@ -750,29 +838,10 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
       if ((rc = maxpy_list(h, kc->V.data(), j + 1, hdev, -1.0, w, len, hdev + (j + 1), st))) return rc;
       PD_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(cplx) * (size_t)(j + 2), cudaMemcpyDeviceToHost, st));
       PD_CUDA(cudaStreamSynchronize(st));
-      if (H.size() < (size_t)(j + 1) * (restart + 1)) H.resize((size_t)(j + 1) * (restart + 1));
-      for (int i = 0; i <= j; ++i) Hat(i, j) = hhost[i];
-      const double hn = sqrt(fmax(hhost[j + 1].re, 0.0));
-      Hat(j + 1, j) = {hn, 0};
-      for (int i = 0; i < j; ++i) {
-        hcplx a_ = Hat(i, j), b_ = Hat(i + 1, j);
-        Hat(i, j) = hadd(hmul(hconj(cs[i]), a_), hmul(hconj(sn[i]), b_));
-        Hat(i + 1, j) = hsub(hmul(cs[i], b_), hmul(sn[i], a_));
-      }
-      {
-        hcplx a_ = Hat(j, j), b_ = Hat(j + 1, j);
-        double den = sqrt(a_.re * a_.re + a_.im * a_.im + b_.re * b_.re + b_.im * b_.im);
-        if (den == 0.0) { cs[j] = {1, 0}; sn[j] = {0, 0}; }
-        else { cs[j] = {a_.re / den, a_.im / den}; sn[j] = {b_.re / den, b_.im / den}; }
-        Hat(j, j) = hadd(hmul(hconj(cs[j]), a_), hmul(hconj(sn[j]), b_));
-        Hat(j + 1, j) = {0, 0};
-        hcplx gj = g[j];
-        g[j + 1] = hmul({-sn[j].re, -sn[j].im}, gj);
-        g[j] = hmul(hconj(cs[j]), gj);
-      }
+      double hn = 0.0;
+      const double rn = hess.push(hhost, &hn);
       ++its;
       jdone = j + 1;
-      const double rn = habs(g[j + 1]);
       if (hist) hist[its] = rn;
       if (rn <= target) {
         converged = true;
@@ -785,11 +854,7 @@ static int gmres_impl(pd_handle* h, const void* b_dev, void* x_dev, double rtol,
       h->launches++;
     }
     // y = H^-1 g (upper triangular), x += V y
-    for (int i = jdone - 1; i >= 0; --i) {
-      hcplx s = g[i];
-      for (int k = i + 1; k < jdone; ++k) s = hsub(s, hmul(Hat(i, k), yk[k]));
-      yk[i] = hdiv(s, Hat(i, i));
-    }
+    hess.solve(yk.data());
     if (jdone > 0) {
       for (int i = 0; i < jdone; ++i) hhost[i] = yk[i];
       PD_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(cplx) * (size_t)jdone, cudaMemcpyHostToDevice, st));

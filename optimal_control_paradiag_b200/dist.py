@@ -386,6 +386,8 @@ class DistributedDiagFFTPC:
         hist, its, reason, first, converged = [], 0, "DIVERGED_ITS", True, False
         beta0 = target = 0.0
         hbuf = t.zeros(restart + 2, dtype=c128, device=self.device)
+        from ._lib import Hessenberg
+        hess = Hessenberg(restart)
         while not converged and (its < max_it or first):
             v0 = vec(0)
             if first:
@@ -406,9 +408,7 @@ class DistributedDiagFFTPC:
                     break
             v0.mul_(1.0 / beta)
             m = restart
-            H = np.zeros((m + 1, m), dtype=complex)
-            cs, sn, g = np.zeros(m, complex), np.zeros(m, complex), np.zeros(m + 1, complex)
-            g[0] = beta
+            hess.start(beta)
             jdone = 0
             for j in range(m):
                 w = vec(j + 1)
@@ -418,24 +418,10 @@ class DistributedDiagFFTPC:
                 hbuf[: j + 1] = hd
                 maxpy_all(j + 1, hbuf, -1.0, w, hbuf[j + 1: j + 2])
                 self._allreduce(hbuf[j + 1: j + 2])
-                hh = hbuf[: j + 2].cpu().numpy()
-                H[: j + 1, j] = hh[: j + 1]
-                hn = math.sqrt(max(hh[j + 1].real, 0.0))
-                H[j + 1, j] = hn
-                for i in range(j):
-                    a_, b_ = H[i, j], H[i + 1, j]
-                    H[i, j] = np.conj(cs[i]) * a_ + np.conj(sn[i]) * b_
-                    H[i + 1, j] = cs[i] * b_ - sn[i] * a_
-                a_, b_ = H[j, j], H[j + 1, j]
-                den = math.sqrt(abs(a_) ** 2 + abs(b_) ** 2)
-                cs[j], sn[j] = (1.0, 0.0) if den == 0 else (a_ / den, b_ / den)
-                H[j, j] = np.conj(cs[j]) * a_ + np.conj(sn[j]) * b_
-                H[j + 1, j] = 0
-                g[j + 1] = -sn[j] * g[j]
-                g[j] = np.conj(cs[j]) * g[j]
+                # Hessenberg column, Givens rotations, residual estimate: the library's one implementation
+                rn, hn = hess.push(hbuf[: j + 2].cpu().numpy())
                 its += 1
                 jdone = j + 1
-                rn = abs(g[j + 1])
                 hist.append(rn)
                 if rn <= target:
                     converged, reason = True, ("CONVERGED_RTOL" if rn > atol else "CONVERGED_ATOL")
@@ -444,8 +430,7 @@ class DistributedDiagFFTPC:
                     break
                 w.mul_(1.0 / hn)
             if jdone:
-                yk = np.linalg.solve(np.triu(H[:jdone, :jdone]), g[:jdone])
-                coef = t.tensor(yk, dtype=c128, device=self.device)
+                coef = t.tensor(hess.solve(), dtype=c128, device=self.device)
                 maxpy_all(jdone, coef, 1.0, x)
             if its >= max_it:
                 break

@@ -126,3 +126,31 @@ def test_pd_config_mirrors_match_the_header_field_for_field():
     names = re.findall(r'\("(\w+)",\s*C\.c_(?:int32|double)(?:\s*\*\s*(\d+))?\)', stub)
     assert [n for n, _ in names] == [f[0] for f in fields]
     assert [int(l) if l else 0 for _, l in names] == [f[2] for f in fields]
+
+
+def test_hessenberg_state_matches_a_dense_least_squares_solve():
+    # pd_hess_* (host only): Givens-reduced Hessenberg of a GMRES cycle against numpy's least squares on the same H
+    import numpy as np
+    from optimal_control_paradiag_b200._lib import Hessenberg
+    rng = np.random.default_rng(0)
+    m, beta = 9, 2.5
+    H = np.zeros((m + 1, m), dtype=complex)
+    q = Hessenberg(m)
+    q.start(beta)
+    for j in range(m):
+        col = rng.standard_normal(j + 1) + 1j * rng.standard_normal(j + 1)
+        hn = abs(rng.standard_normal()) + 0.1
+        H[: j + 1, j], H[j + 1, j] = col, hn
+        rn, hn_out = q.push(np.concatenate([col, [hn * hn]]))
+        assert abs(hn_out - hn) < 1e-15
+        e1 = np.zeros(j + 2, dtype=complex)
+        e1[0] = beta
+        y, *_ = np.linalg.lstsq(H[: j + 2, : j + 1], e1, rcond=None)
+        assert abs(rn - np.linalg.norm(e1 - H[: j + 2, : j + 1] @ y)) < 1e-12      # residual estimate = LS residual
+    assert np.allclose(q.solve(), y, rtol=1e-11, atol=1e-13)
+    q.start(1.0)                                                                  # a new cycle reuses the state
+    rn, _ = q.push(np.array([3.0 + 0j, 16.0]))
+    assert abs(rn - 4.0 / 5.0) < 1e-15 and np.allclose(q.solve(), [3.0 / 25.0])
+    lib = pkg.load_library()
+    assert lib.pd_hess_create(0, None) == _lib.PD_ERR_INVALID
+    q.close()
