@@ -128,14 +128,17 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
   PD_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   h->num_sms = prop.multiProcessorCount;
   {
-    // Programmatic dependent launch of the apply's kernels (PD_KLAUNCH in pd_common.cuh).  Measured on B200
-    // (bench.py, L2 flushed between applies): cfg1 46.8 -> 45.7 us, cfg2 80.0 -> 76.2 us, but cfg5 0.670 -> 0.784 ms
-    // and cfg3 +13 %: the streaming passes are persistent grids with a static, balanced split of the work, and
-    // CTAs that become resident while the previous kernel drains land unevenly on the SMs.  So it is on only where
-    // the grids are below one wave (vector <= 64 MiB); PD_PDL=0 / 1 forces it off / on.
+    // Programmatic dependent launch of the apply's kernels (PD_KLAUNCH / pd_pdl_enter in pd_common.cuh).  Measured on
+    // B200 (bench.py): with the kernels also releasing their dependents at their first instruction cfg1 46.8 -> 45.7 us
+    // and cfg2 80.0 -> 76.2 us, but cfg5 0.674 -> 0.783 ms and cfg3 2.75 -> 3.10 ms (the early release in pass A /
+    // interface / pass B is what costs; in the FFT kernels it changes nothing); with the launch attribute alone
+    // cfg5 0.674 -> 0.665 ms, cfg3 unchanged.  So: attribute everywhere, early release only where the grids are
+    // below one wave (vector <= 64 MiB).  PD_PDL=0 turns the attribute off, PD_PDL_EARLY=0/1 forces the release.
     const char* e = getenv("PD_PDL");
+    const char* t = getenv("PD_PDL_EARLY");
     const double vec_bytes = 32.0 * (double)h->n * (double)cfg->N_t;
-    h->pdl = e ? (e[0] == '1') : (vec_bytes <= 64.0 * 1024 * 1024);
+    h->pdl = !(e && e[0] == '0');
+    h->pdl_early = t ? (t[0] == '1') : (vec_bytes <= 64.0 * 1024 * 1024);
   }
   int rc = pd_fft_plan(h);
   if (rc == PD_OK) rc = pd_solve_plan(h);

@@ -89,8 +89,8 @@ struct PdDeviceGuard {
 // (transitively along the chain: a kernel cannot complete before its own wait has returned).  Launched without the
 // attribute (PD_PDL=0, or any plain <<< >>> launch) both instructions are no-ops.
 #if defined(__CUDACC__)
-__device__ __forceinline__ void pd_pdl_enter() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+__device__ __forceinline__ void pd_pdl_enter(bool release_dependents_now = true) {
+  if (release_dependents_now) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <typename... P, typename... A>
@@ -184,6 +184,7 @@ struct pd_handle {
   int opt_slab_no_overlap;   // pd_set_option "slab_overlap" 0: the slab apply stays on the caller's stream
   int opt_kry_real;          // pd_set_option "krylov_real_vectors"
   int pdl;                   // 1: the apply's kernels are launched with programmatic stream serialisation (PD_KLAUNCH)
+  int pdl_early;             // 1: they also release their dependents at their first instruction (else implicitly at exit)
   int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;

@@ -19,6 +19,7 @@
 
 #include "pd_common.cuh"
 
+
 namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------ twiddle table
@@ -61,8 +62,8 @@ template <bool INV>
 __global__ void __launch_bounds__(256)
 pd_fft_generic_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int N,
                       int64_t nlines, const cplx* __restrict__ tw, PassList pl, double scale,
-                      const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+                      const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cplx* buf0 = reinterpret_cast<cplx*>(pd_smem_raw);
   cplx* buf1 = buf0 + N;
@@ -144,8 +145,8 @@ __device__ __forceinline__ cplx* generic_forward_passes(cplx* s, cplx* d, int N,
 template <bool TO_FREQ>
 __global__ void __launch_bounds__(256)
 pd_rfft_pair_generic_kernel(const void* __restrict__ in_, void* __restrict__ out_, int N, int64_t nnodes,
-                            const cplx* __restrict__ tw, PassList pl, const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+                            const cplx* __restrict__ tw, PassList pl, const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cplx* buf0 = reinterpret_cast<cplx*>(pd_smem_raw);
   cplx* buf1 = buf0 + N;
@@ -210,8 +211,8 @@ template <int R0, int R1, int R2, int R3, bool INV, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_fft_pow2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
                    const cplx* __restrict__ tw, double scale, int64_t seg_lines, int64_t seg_stride,
-                   const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+                   const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
@@ -411,8 +412,8 @@ template <bool INV, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(256, 2)
 pd_fft_16k_l2_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64_t nlines,
                      const cplx* __restrict__ tw, const cplx* __restrict__ tw_q, double scale,
-                     const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+                     const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   constexpr int N = PD_BIGN, Q = N / 4, T = Q / 16, J = Q / 4;
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   cplx* sm = reinterpret_cast<cplx*>(pd_smem_raw);
@@ -761,8 +762,8 @@ pd_fft_16k_tma_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int64
 template <int R0, int R1, int R2, int R3, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nlines,
-               const cplx* __restrict__ twN, const cplx* __restrict__ twM, const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+               const cplx* __restrict__ twN, const cplx* __restrict__ twM, const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   constexpr int G2 = GAM ? 2 : 0;
   constexpr int M = R0 * R1 * R2 * R3;  // complex length = N_t / 2
   constexpr int T = M / 16;
@@ -1012,19 +1013,19 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   if (inverse && !gam) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
   } else if (!gam) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
   } else if (inverse) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
   } else {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam);
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
   }
   PD_CHECK_LAUNCH();
   h->launches++;
@@ -1053,16 +1054,16 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
     const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
     if (inverse && !gam)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<true, true, false>), grid, 256, smem, st, in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                       scale, gam);
+                                                                       scale, gam, (int)(h->pdl && h->pdl_early));
     else if (!gam)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<false, false, false>), grid, 256, smem, st, in, out, nlines, h->twiddle,
-                                                                        h->twiddle_quarter, scale, gam);
+                                                                        h->twiddle_quarter, scale, gam, (int)(h->pdl && h->pdl_early));
     else if (inverse)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<true, true, true>), grid, 256, smem, st, in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                      scale, gam);
+                                                                      scale, gam, (int)(h->pdl && h->pdl_early));
     else
       PD_KLAUNCH((pd_fft_16k_l2_kernel<false, false, true>), grid, 256, smem, st, in, out, nlines, h->twiddle,
-                                                                       h->twiddle_quarter, scale, gam);
+                                                                       h->twiddle_quarter, scale, gam, (int)(h->pdl && h->pdl_early));
     PD_CHECK_LAUNCH();
     h->launches++;
     return PD_OK;
@@ -1094,8 +1095,8 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
 template <int R0, int R1, int R2, int R3, bool TO_FREQ, bool GAM>
 __global__ void __launch_bounds__(512)
 pd_rfft_pair_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nnodes,
-                    const cplx* __restrict__ tw, const double* __restrict__ gam) {
-  pd_pdl_enter();  // programmatic dependent launch: see pd_common.cuh
+                    const cplx* __restrict__ tw, const double* __restrict__ gam, int pdl_early) {
+  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int T = N / 16;
   constexpr int H = N / 2;
@@ -1216,7 +1217,7 @@ static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nno
   do {                                                                     \
     auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, TF, GM>;                  \
     PD_SET_SMEM_ONCE(k, smem);                                             \
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nnodes, h->twiddle, gam); \
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nnodes, h->twiddle, gam, (int)(h->pdl && h->pdl_early)); \
   } while (0)
   if (to_freq) {
     if (gam) PD_RFFT_PAIR_GO(true, true); else PD_RFFT_PAIR_GO(true, false);
@@ -1255,9 +1256,9 @@ int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes,
   const int64_t cap = (int64_t)h->num_sms * 8;
   const int64_t nblk = nnodes < cap ? nnodes : cap;
   if (to_freq)
-    PD_KLAUNCH((pd_rfft_pair_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam);
+    PD_KLAUNCH((pd_rfft_pair_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl && h->pdl_early));
   else
-    PD_KLAUNCH((pd_rfft_pair_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam);
+    PD_KLAUNCH((pd_rfft_pair_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl && h->pdl_early));
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1277,7 +1278,7 @@ static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, 
   do {                                                                                                  \
     auto k = pd_rfft_kernel<R0, R1, R2, R3, TF, GM>;                                                    \
     PD_SET_SMEM_ONCE(k, smem);                                                                          \
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, h->twiddle_half, gam);        \
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, h->twiddle_half, gam, (int)(h->pdl && h->pdl_early));        \
   } while (0)
   if (to_freq) {
     if (gam) PD_RFFT_GO(true, true); else PD_RFFT_GO(true, false);
@@ -1389,9 +1390,9 @@ int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int i
   int64_t nblk = nlines < (int64_t)h->num_sms * 8 ? nlines : (int64_t)h->num_sms * 8;
   double scale = inverse ? 1.0 / (double)N : 1.0;
   if (inverse)
-    PD_KLAUNCH((pd_fft_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam);
+    PD_KLAUNCH((pd_fft_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl && h->pdl_early));
   else
-    PD_KLAUNCH((pd_fft_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam);
+    PD_KLAUNCH((pd_fft_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl && h->pdl_early));
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
