@@ -108,6 +108,9 @@ int pd_host_unregister_all(pd_handle* h);
  * is rounding noise).  Needs N_t >= 8 (register pipelines for the powers of two in [128, 16384], a
  * shared-memory pair kernel for every other length, N_t = 81 included); PD_ERR_UNSUPPORTED otherwise. */
 int pd_pc_apply_real(pd_handle* h, const void* x_dev, void* y_dev, void* stream);
+/* pd_pc_apply_real through HOST buffers of 2 n N_t doubles (a real-scalar PETSc Vec, a numpy float64 array): H2D,
+ * real-input apply, D2H -- half the PCIe bytes of pd_pc_apply_host.  Same :493-497 / :552-553 as that one.   */
+int pd_pc_apply_real_host(pd_handle* h, const void* x_host, void* y_host);
 /* The stages of the real-input path: real lines of N_t samples <-> half spectra of N_t/2 + 1 complex
  * numbers (to_freq != 0: scipy ifft restricted to k <= N_t/2; to_freq == 0: scipy fft of the Hermitian
  * extension, real output), and the per-frequency stage on w = (2, n, Kp), in place; rows of a half

@@ -68,6 +68,7 @@ SYMBOLS = {
     "pd_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_matvec_slab": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_matvec_slab_real": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_pc_apply_real_host": (_I, [_VP, _VP, _VP]),
     "pd_pc_matvec": (_I, [_VP, _VP, _VP, _VP]),
     "pd_build_rhs": (_I, [_VP, _VP, _VP]),
     "pd_gmres": (_I, [_VP, _VP, _VP, _D, _D, _I, _I, C.POINTER(_I), C.POINTER(_D), C.POINTER(_I), _VP]),

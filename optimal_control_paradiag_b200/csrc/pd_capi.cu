@@ -817,6 +817,31 @@ extern "C" int pd_pc_apply_host(pd_handle* h, const void* x_host, void* y_host) 
   return PD_OK;
 }
 
+// The same for float64 host vectors (a real-scalar PETSc build, or numpy float64 arrays): the real-input path of
+// pd_pc_apply_real between the two copies -- half the PCIe bytes of pd_pc_apply_host, which is what bounds it.
+extern "C" int pd_pc_apply_real_host(pd_handle* h, const void* x_host, void* y_host) {
+  if (!h || !x_host || !y_host) {
+    pd_set_error("pd_pc_apply_real_host: invalid argument");
+    return PD_ERR_INVALID;
+  }
+  PD_ON_DEVICE(h);
+  const size_t bytes = sizeof(double) * 2 * (size_t)h->n * h->cfg.N_t;
+  if (!h->stage_x) {  // sized for the complex entry point, which shares it
+    PD_CUDA(cudaMalloc(&h->stage_x, 2 * bytes));
+    h->ws_bytes += 2 * bytes;
+  }
+  if (!h->own_stream) PD_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = h->own_stream;
+  hostreg_pin(h, x_host, bytes);
+  if (y_host != x_host) hostreg_pin(h, y_host, bytes);
+  PD_CUDA(cudaMemcpyAsync(h->stage_x, x_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = pd_pc_apply_real(h, h->stage_x, h->stage_x, st);
+  if (rc) return rc;
+  PD_CUDA(cudaMemcpyAsync(y_host, h->stage_x, bytes, cudaMemcpyDeviceToHost, st));
+  PD_CUDA(cudaStreamSynchronize(st));
+  return PD_OK;
+}
+
 extern "C" int pd_matvec(pd_handle* h, const void* x_dev, void* y_dev, void* stream) {
   if (!h || !x_dev || !y_dev || x_dev == y_dev) {
     pd_set_error("pd_matvec: invalid argument (x and y must be distinct device vectors)");

@@ -144,6 +144,18 @@ class ParaDiagHandle:
         check(self.lib.pd_pc_apply_host(self._h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
         return y
 
+    def pc_apply_real_host(self, x, y=None):
+        """Real-input path through host buffers (numpy float64): H2D, pd_pc_apply_real, D2H -- half the bytes."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if x.size != self.size:
+            raise ValueError(f"x: expected {self.size} entries, got {x.size}")
+        if y is None:
+            y = np.empty(self.size, dtype=np.float64)
+        if y.dtype != np.float64 or not y.flags.c_contiguous or y.size != self.size:
+            raise ValueError("y: need a contiguous float64 array of the vector size")
+        check(self.lib.pd_pc_apply_real_host(self._h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+        return y
+
     def host_unregister_all(self):
         """Drop the page-lock registrations pc_apply_host made for host buffers (pd_host_unregister_all)."""
         check(self.lib.pd_host_unregister_all(self._h))

@@ -257,7 +257,11 @@ class DiagFFTPC(PCBase):
         if xa.size != self.handle.size or ya.size != self.handle.size:
             raise ValueError(f"DiagFFTPC.apply: Vec size {xa.size} != 2*(N_x+1)*N_t = {self.handle.size}")
         if self.node_order is None:
-            if ya.dtype == np.complex128 and ya.flags.c_contiguous:
+            if (xa.dtype == np.float64 and ya.dtype == np.float64 and ya.flags.c_contiguous
+                    and getattr(self.handle, "real_path_supported", False)):
+                # real Vecs (a real-scalar PETSc build, numpy float64): half the PCIe bytes
+                self.handle.pc_apply_real_host(xa, ya)
+            elif ya.dtype == np.complex128 and ya.flags.c_contiguous:
                 self.handle.pc_apply_host(xa, ya)
             else:
                 ya[...] = self.handle.pc_apply_host(xa).astype(ya.dtype, copy=False)

@@ -393,6 +393,31 @@ def test_diagfftpc_through_petsc_protocol():
     DiagFFTPC._defaults = {}
 
 
+@pytest.mark.parametrize("N_x,N_t", [(80, 81), (64, 256), (33, 1024)])
+def test_real_host_vectors_take_the_half_spectrum_path(N_x, N_t):
+    # float64 host Vecs (a real-scalar PETSc build / numpy float64): pd_pc_apply_real_host, half the PCIe bytes
+    x = np.random.default_rng(5).standard_normal(2 * (N_x + 1) * N_t)
+    ref = DiagFFTPCFast(N_x, N_t, 2.0, 1.0).apply(x + 0j).real
+    with ParaDiagHandle(N_x, N_t) as h:
+        y = h.pc_apply_real_host(x)
+        assert y.dtype == np.float64 and rel(y, ref) < PC_TOL
+        assert np.array_equal(y, h.pc_apply_real(torch.tensor(x, device=DEV)).cpu().numpy())
+        xin = x.copy()
+        h.pc_apply_real_host(xin, xin)                               # in place
+        assert np.array_equal(xin, y)
+    DiagFFTPC.configure(N_x=N_x, N_t=N_t, T=2.0, gamma=1.0)
+    try:
+        pc = petsc_shim.PC()
+        pc.setPythonContext(DiagFFTPC())
+        pc.setUp()
+        yv = np.zeros_like(x)
+        pc.apply(x, yv)                                              # numpy float64 in, float64 out
+        assert np.array_equal(yv, y)
+        pc.destroy()
+    finally:
+        DiagFFTPC._defaults = {}
+
+
 def test_problem_class_reproduces_the_reference_run():
     from optimal_control_paradiag_b200 import Optimal_Control_Wave_Equation, default_parameters
     equ = Optimal_Control_Wave_Equation(80, 2, 81, 1)
