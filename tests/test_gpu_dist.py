@@ -57,6 +57,47 @@ def test_sharded_apply_equals_single_gpu_apply(N_x, N_t, mode):
         assert ret[r] < (1e-11 if mode == "alltoall" else 1e-10), (r, ret[r])
 
 
+def _alpha_worker(rank, world, port, N_x, N_t, alpha, transport, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from optimal_control_paradiag_b200 import ParaDiagHandle
+        from optimal_control_paradiag_b200.dist import DistributedDiagFFTPC
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=1.0, device=rank, mode="slab", alpha=alpha,
+                                   transport=transport)
+        rng = np.random.default_rng(1)
+        size = 2 * (N_x + 1) * N_t
+        xg = torch.tensor(rng.standard_normal(size) + 1j * rng.standard_normal(size), device=f"cuda:{rank}")
+        xr = torch.tensor(rng.standard_normal(size), device=f"cuda:{rank}")
+        yg = dpc.gather_to_global(dpc.apply(dpc.scatter_from_global(xg)))
+        yr = dpc.gather_to_global(dpc.apply_real(dpc.scatter_from_global(xr)).to(torch.complex128)).real
+        with ParaDiagHandle(N_x, N_t, alpha=alpha, device=rank) as h:
+            ref, refr = h.pc_apply(xg), h.pc_apply_real(xr)
+        ret[rank] = (float(torch.linalg.norm(yg - ref) / torch.linalg.norm(ref)),
+                     float(torch.linalg.norm(yr - refr) / torch.linalg.norm(refr)), dpc.transport)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("N_x,N_t", [(80, 81), (1024, 256), (40, 16384)])
+def test_alpha_extension_in_slab_mode_across_processes(N_x, N_t, transport):
+    # the alpha extension (no upstream counterpart) on x-slabs: Gamma inside the transforms (peer-store transport) or
+    # as elementwise products (collective transport), against the single-GPU alpha apply
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ret = mp.Manager().dict()
+    mp.spawn(_alpha_worker, args=(world, _free_port(), N_x, N_t, 1e-2, transport, ret), nprocs=world, join=True)
+    for r in range(world):
+        ec, er, used = ret[r]
+        assert ec < 1e-10 and er < 1e-10, (r, ec, er, used)
+        if transport == "nccl":
+            assert used == "nccl"
+
+
 def _gmres_worker(rank, world, port, N_x, N_t, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
