@@ -180,3 +180,56 @@ def test_peer_exchange_across_processes_over_nvlink(N_x, N_t):
         transport, err = ret[r]
         assert transport == "peer", ret[r]
         assert err < 1e-10, (r, err)
+
+
+@pytest.mark.parametrize("N_x,N_t", [(255, 256), (1024, 1024), (80, 81)])
+def test_single_gpu_apply_replays_from_a_cuda_graph(N_x, N_t):
+    # the apply is launch-only once its work buffers exist (no allocation, no host synchronisation), with or without
+    # the programmatic-dependent-launch attribute: capture once, replay on new data
+    with ParaDiagHandle(N_x, N_t) as h:
+        x = rand_global(h.size, seed=1)
+        y = torch.empty_like(x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            h.pc_apply(x, y)                                   # warm-up on a side stream: buffers, attributes
+        torch.cuda.current_stream().wait_stream(side)
+        ref = h.pc_apply(x)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            h.pc_apply(x, y)
+        for seed in (1, 2, 3):
+            x.copy_(rand_global(h.size, seed=seed))
+            want = h.pc_apply(x)
+            y.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(y, want), seed
+        assert torch.equal(ref, h.pc_apply(rand_global(h.size, seed=1)))
+
+
+@pytest.mark.parametrize("N_x,N_t,G,real", [(255, 128, 3, False), (1024, 1024, 4, False), (1024, 256, 4, True)])
+def test_slab_apply_with_peer_exchange_replays_from_a_cuda_graph(N_x, N_t, G, real):
+    # epochs, parities and flags of the exchange live in device memory: the whole distributed apply (all ranks of a
+    # LocalSlabGroup on this GPU) is captured once and replayed; every replay is a new epoch
+    with ParaDiagHandle(N_x, N_t) as h, LocalSlabGroup(N_x, N_t, G) as grp:
+        x = rand_global(h.size, seed=1, real=real)
+        xs = grp.scatter(x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            grp.apply_blocks(xs, real=real)                    # warm-up: epoch 1
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ys = grp.apply_blocks(xs, real=real)               # capture launches nothing: the epoch stays at 1
+        for rep, seed in enumerate((4, 5, 6)):
+            xn = rand_global(h.size, seed=seed, real=real)
+            for dst, src in zip(xs, grp.scatter(xn)):
+                dst.copy_(src)
+            g.replay()
+            torch.cuda.synchronize()
+            y = torch.cat([b.view(2, grp.ncount[r], N_t) for r, b in enumerate(ys)], dim=1).reshape(-1)
+            want = h.pc_apply_real(xn) if real else h.pc_apply(xn)
+            assert relerr(y, want) < 1e-10, (rep, relerr(y, want))
+        assert all(not to and ep == 4 for to, ep in grp.status()), grp.status()
