@@ -224,7 +224,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-#define PD_FKB 4  // frequencies per flag of the exchange (every producer covers whole groups of PD_FKB columns)
+// frequencies per flag of the exchange (every producer covers whole groups of PD_FKB columns: the sequential interface
+// kernel PD_ITK = 32 per CTA, the functionals kernel PD_KB = 128, the PCR kernel when it holds 32 per CTA).  One flag
+// per producing CTA and peer keeps the number of system-scope release stores -- each a fence -- at G per CTA.
+#define PD_FKB 32
 
 // slot [parity][rank] of EVERY rank's buffer (peer stores over NVLink; the own copy is a local store)
 __device__ __forceinline__ void slab_push(const SlabCommDev& cm, unsigned long long ep, int kk, cplx fP, cplx fM,
@@ -237,9 +240,11 @@ __device__ __forceinline__ void slab_push(const SlabCommDev& cm, unsigned long l
   }
 }
 // Publish the columns [k0, k0 + ncols) of this CTA to every rank: called by ALL threads of the CTA after their
-// slab_push calls; every thread's stores are ordered before the flags at system scope.
+// slab_push calls.  The block barrier orders every thread's (weak) data stores before the flag writers' release
+// stores, and a release at system scope is cumulative over what its thread has observed through the barrier -- the
+// "all store, barrier, one thread releases" pattern.  (A __threadfence_system() by every thread in front of the
+// barrier was measured as 19 % of the interface kernel's time in slab mode, ncu: ERRBAR.)
 __device__ __forceinline__ void slab_publish(const SlabCommDev& cm, unsigned long long ep, int k0, int ncols) {
-  __threadfence_system();
   __syncthreads();
   const int f0 = k0 / PD_FKB, nf = (ncols + PD_FKB - 1) / PD_FKB;
   for (int i = threadIdx.x; i < nf * cm.G; i += blockDim.x) {
@@ -842,15 +847,33 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
                       const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm,
                       cplx* __restrict__ zsep, const cplx* __restrict__ green) {
   pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  // The correction sweep at the end touches rows of zsep / green that depend on nothing the peers send: its first
+  // batch of rows is loaded HERE, so that the loads are in flight under the flag wait and the tiny separator solve
+  // (the sweep used to be half of this kernel's time, one exposed DRAM round trip per row).
+  constexpr int UNR = 4;
+  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
+  const int64_t K = sp.K;
+  const int P = sp.rows[1];
+  const bool sweep = P > 0 && zsep != nullptr && kk < sp.kend;
+  cplx bg0[UNR], bg1[UNR], bzP[UNR], bzM[UNR];
+  if (sweep) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int c = blockIdx.y + u * gridDim.y;
+      if (c < P) {
+        const int64_t o = ((int64_t)c * 2) * K + kk;
+        bg0[u] = green[o]; bg1[u] = green[o + K];
+        bzP[u] = zsep[o]; bzM[u] = zsep[o + K];
+      }
+    }
+  }
   if (WAIT) {
     // wait for the functionals of THIS frequency block from every rank (bounded spin, see SlabCommDev)
     const unsigned long long ep = *cm.epoch + 1ull;
     slab_wait(cm, ep, sp.koff + blockIdx.x * PD_KB, min(PD_KB, sp.kend - sp.koff - blockIdx.x * PD_KB));
     gathered = cm.peer_gath[cm.rank] + (int64_t)(ep & 1ull) * cm.G * 6 * cm.kmax;
   }
-  const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.kend) return;
-  const int64_t K = sp.K;
   const int64_t GS = gstride;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
   constexpr int GA = GT ? GT : PD_MAX_SLABS;
@@ -903,8 +926,7 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
   if (blockIdx.y == 0) {
     zout[kk] = leftP; zout[K + kk] = leftM; zout[2 * K + kk] = rightP; zout[3 * K + kk] = rightM;
   }
-  const int P = sp.rows[1];
-  if (P > 0 && zsep) {
+  if (sweep) {
     const int Llast = sp.m - P * (PD_L + 1);
     VRec v;
     v.init(kc.a, kc.sh, cmake(0, 0));
@@ -920,11 +942,28 @@ pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveP
     }
     const cplx cLP = cneg(cmul(gl, leftP)), cLM = cneg(cmul(gl, leftM));
     const cplx cRP = cneg(cmul(gr, rightP)), cRM = cneg(cmul(gr, rightM));
-    for (int c = blockIdx.y; c < P; c += gridDim.y) {
-      const int64_t o = ((int64_t)c * 2) * K + kk;
-      const cplx g0 = green[o], g1 = green[o + K];
-      zsep[o] = cfma(cLP, g0, cfma(cRP, g1, zsep[o]));
-      zsep[o + K] = cfma(cLM, g0, cfma(cRM, g1, zsep[o + K]));
+    // batches of UNR rows: all loads of a batch before its first store (the first batch is already in registers)
+    for (int cb = blockIdx.y; cb < P; cb += gridDim.y * UNR) {
+      if (cb != (int)blockIdx.y) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int c = cb + u * gridDim.y;
+          if (c < P) {
+            const int64_t o = ((int64_t)c * 2) * K + kk;
+            bg0[u] = green[o]; bg1[u] = green[o + K];
+            bzP[u] = zsep[o]; bzM[u] = zsep[o + K];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c = cb + u * gridDim.y;
+        if (c < P) {
+          const int64_t o = ((int64_t)c * 2) * K + kk;
+          zsep[o] = cfma(cLP, bg0[u], cfma(cRP, bg1[u], bzP[u]));
+          zsep[o + K] = cfma(cLM, bg0[u], cfma(cRM, bg1[u], bzM[u]));
+        }
+      }
     }
   }
 }
@@ -1532,9 +1571,10 @@ int pd_slab_finish_launch(pd_handle* h, cplx* w, const cplx* gathered, cudaStrea
   const int kblocks = (ncol + PD_KB - 1) / PD_KB;
   const cplx* coef = half_spectrum ? pl->slabcoef_h : pl->slabcoef;
   // enough CTAs in y for the correction sweep over the interior separators (rows[1] x 2 x K values)
-  int gy = sp.rows[1] / 8;
+  // (one batch of 4 rows per thread where the interface is short: all its loads are issued before the flag wait)
+  int gy = sp.rows[1] / 4;
   if (gy < 1) gy = 1;
-  if (gy > 16) gy = 16;
+  if (gy > 32) gy = 32;
   const dim3 ggrid(kblocks, gy);
   cplx* zsep = sp.nlev >= 1 ? lv.R[1] : nullptr;
 #define PD_GLOBAL_LAUNCH(W, GT_, GPTR, GSTR, CM)                                                                   \

@@ -1,31 +1,46 @@
-"""Developer probe: per-stage device time of one rank's slab-mode work (no communication)."""
-import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+#!/usr/bin/env python
+"""All G x-slab ranks of one distributed apply on ONE GPU (LocalSlabGroup): the aggregate per-rank kernel work of the
+slab mode without any link or skew effect, against the single-GPU apply of the same vector.  The difference divided by
+G is what every rank pays for being a slab (short grids, interface / separator kernels).
+Usage: python tools/slab_probe.py [N_x N_t G [reps]]"""
+import os
+import sys
+
 import torch
-from optimal_control_paradiag_b200 import ParaDiagHandle
-def timeit(fn, n=20, warm=5):
-    for _ in range(warm): fn()
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from optimal_control_paradiag_b200 import ParaDiagHandle  # noqa: E402
+from optimal_control_paradiag_b200.dist import LocalSlabGroup  # noqa: E402
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
     torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(n): fn()
-    e.record(); torch.cuda.synchronize()
-    return s.elapsed_time(e) / n * 1e3
-Nx, Nt = 16384, 4096
-for G in (2, 4, 8):
-    r = G // 2
-    h = ParaDiagHandle(Nx, Nt, slab_rank=r, slab_count=G)
-    n_r = (Nx + 1) // G + (1 if r < (Nx + 1) % G else 0)
-    x = torch.randn(2 * n_r * Nt, dtype=torch.complex128, device="cuda:0")
-    w = torch.empty_like(x); y = torch.empty_like(x)
-    out = torch.empty(6 * Nt, dtype=torch.complex128, device="cuda:0")
-    gathered = torch.randn(G * 6 * Nt, dtype=torch.complex128, device="cuda:0")
-    t1 = timeit(lambda: h.stage_fft(x, w, 2 * n_r, True))
-    t2 = timeit(lambda: h.slab_reduce(w, out))
-    t3 = timeit(lambda: h.slab_finish(w, gathered))
-    t4 = timeit(lambda: h.stage_fft(w, y, 2 * n_r, False))
-    def full():
-        h.stage_fft(x, w, 2 * n_r, True); h.slab_reduce(w, out); h.slab_finish(w, gathered); h.stage_fft(w, y, 2 * n_r, False)
-    t5 = timeit(full)
-    print(f"G={G}: ifft {t1:.0f} us, reduce {t2:.0f} us, finish {t3:.0f} us, fft {t4:.0f} us, sum {t1+t2+t3+t4:.0f}, back-to-back {t5:.0f} us (ideal 1-GPU/G = {2720/G:.0f})")
-    h.close()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    N_x, N_t, G = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (16384, 4096, 8)))
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+    real = os.environ.get("PROBE_REAL") == "1"
+    with ParaDiagHandle(N_x, N_t) as h, LocalSlabGroup(N_x, N_t, G) as grp:
+        g0 = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(h.size, dtype=torch.float64, device="cuda", generator=g0)
+        if not real:
+            x = x.to(torch.complex128)
+        y = torch.empty_like(x)
+        one = timed(lambda: (h.pc_apply_real(x, y) if real else h.pc_apply(x, y)), reps)
+        xs = grp.scatter(x)
+        agg = timed(lambda: grp.apply_blocks(xs, real=real), reps)
+        print(f"{N_x}x{N_t} G={G} real={real}: single-GPU apply {one:.4f} ms | all {G} slab ranks on one GPU {agg:.4f} ms "
+              f"| per rank {agg / G:.4f} ms (ideal {one / G:.4f}), slab overhead per rank {(agg - one) / G * 1e3:.1f} us")
+
+
+if __name__ == "__main__":
+    main()
