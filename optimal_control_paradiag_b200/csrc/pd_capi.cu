@@ -129,16 +129,19 @@ extern "C" int pd_create(const pd_config* cfg, pd_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   {
     // Programmatic dependent launch of the apply's kernels (PD_KLAUNCH / pd_pdl_enter in pd_common.cuh).  Measured on
-    // B200 (bench.py): with the kernels also releasing their dependents at their first instruction cfg1 46.8 -> 45.7 us
-    // and cfg2 80.0 -> 76.2 us, but cfg5 0.674 -> 0.783 ms and cfg3 2.75 -> 3.10 ms (the early release in pass A /
-    // interface / pass B is what costs; in the FFT kernels it changes nothing); with the launch attribute alone
-    // cfg5 0.674 -> 0.665 ms, cfg3 unchanged.  So: attribute everywhere, early release only where the grids are
-    // below one wave (vector <= 64 MiB).  PD_PDL=0 turns the attribute off, PD_PDL_EARLY=0/1 forces the release.
+    // B200: the launch attribute alone gives cfg5 0.674 -> 0.665 ms, 2048 x 4096 360 -> 350 us, cfg3 unchanged.
+    // Letting kernels ALSO release their dependents at their first instruction helps only where the grids are below
+    // one wave (cfg1 46.8 -> 45.7 us, cfg2 80.0 -> 76.2 us).  At the large sizes it is neutral in the time transforms
+    // and in pass B, and harmful in the interface kernel (cfg3 2.53 -> 2.74 ms: the next kernel's CTAs become resident
+    // beside a kernel that runs one warp per scheduler on its own latency chain) and in pass A of a short slab
+    // (0.388 -> 0.409 ms per rank at cfg3 / 8).  So: attribute everywhere; early release (a bit mask per kernel group,
+    // pd_handle::pdl_early) everywhere for vectors <= 64 MiB, nowhere above.  PD_PDL=0 turns the attribute off,
+    // PD_PDL_EARLY=<mask> forces the release mask.
     const char* e = getenv("PD_PDL");
     const char* t = getenv("PD_PDL_EARLY");
     const double vec_bytes = 32.0 * (double)h->n * (double)cfg->N_t;
     h->pdl = !(e && e[0] == '0');
-    h->pdl_early = t ? (t[0] == '1') : (vec_bytes <= 64.0 * 1024 * 1024);
+    h->pdl_early = t ? atoi(t) : (vec_bytes <= 64.0 * 1024 * 1024 ? 31 : 0);  // bit mask, see pd_common.cuh
   }
   int rc = pd_fft_plan(h);
   if (rc == PD_OK) rc = pd_solve_plan(h);

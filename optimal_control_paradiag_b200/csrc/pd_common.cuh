@@ -184,7 +184,8 @@ struct pd_handle {
   int opt_slab_no_overlap;   // pd_set_option "slab_overlap" 0: the slab apply stays on the caller's stream
   int opt_kry_real;          // pd_set_option "krylov_real_vectors"
   int pdl;                   // 1: the apply's kernels are launched with programmatic stream serialisation (PD_KLAUNCH)
-  int pdl_early;             // 1: they also release their dependents at their first instruction (else implicitly at exit)
+  int pdl_early;             // which kernels also release their dependents at their first instruction (else implicitly
+                             // at exit): 1 time transforms, 2 pass A, 4 interface / functionals, 8 pass B, 16 separators
   int opt_host_register;     // pd_set_option "host_register": page-lock host buffers of pd_pc_apply_host once
   cplx* kry_h;
   double* kry_host;

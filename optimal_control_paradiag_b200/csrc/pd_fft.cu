@@ -1013,19 +1013,19 @@ static int launch_pow2(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, 
   if (inverse && !gam) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   } else if (!gam) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, false>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   } else if (inverse) {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, true, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   } else {
     auto k = pd_fft_pow2_kernel<R0, R1, R2, R3, false, true>;
     PD_SET_SMEM_ONCE(k, smem);
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, scale, seg_lines, seg_stride, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   }
   PD_CHECK_LAUNCH();
   h->launches++;
@@ -1054,16 +1054,16 @@ static int launch_16k(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, i
     const unsigned grid = (unsigned)(nlines < (int64_t)h->num_sms * 64 ? nlines : (int64_t)h->num_sms * 64);
     if (inverse && !gam)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<true, true, false>), grid, 256, smem, st, in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                       scale, gam, (int)(h->pdl && h->pdl_early));
+                                                                       scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
     else if (!gam)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<false, false, false>), grid, 256, smem, st, in, out, nlines, h->twiddle,
-                                                                        h->twiddle_quarter, scale, gam, (int)(h->pdl && h->pdl_early));
+                                                                        h->twiddle_quarter, scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
     else if (inverse)
       PD_KLAUNCH((pd_fft_16k_l2_kernel<true, true, true>), grid, 256, smem, st, in, out, nlines, h->twiddle, h->twiddle_quarter,
-                                                                      scale, gam, (int)(h->pdl && h->pdl_early));
+                                                                      scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
     else
       PD_KLAUNCH((pd_fft_16k_l2_kernel<false, false, true>), grid, 256, smem, st, in, out, nlines, h->twiddle,
-                                                                       h->twiddle_quarter, scale, gam, (int)(h->pdl && h->pdl_early));
+                                                                       h->twiddle_quarter, scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
     PD_CHECK_LAUNCH();
     h->launches++;
     return PD_OK;
@@ -1217,7 +1217,7 @@ static int launch_rfft_pair(pd_handle* h, const void* in, void* out, int64_t nno
   do {                                                                     \
     auto k = pd_rfft_pair_kernel<R0, R1, R2, R3, TF, GM>;                  \
     PD_SET_SMEM_ONCE(k, smem);                                             \
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nnodes, h->twiddle, gam, (int)(h->pdl && h->pdl_early)); \
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nnodes, h->twiddle, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0)); \
   } while (0)
   if (to_freq) {
     if (gam) PD_RFFT_PAIR_GO(true, true); else PD_RFFT_PAIR_GO(true, false);
@@ -1256,9 +1256,9 @@ int pd_rfft_pair_launch(pd_handle* h, const void* in, void* out, int64_t nnodes,
   const int64_t cap = (int64_t)h->num_sms * 8;
   const int64_t nblk = nnodes < cap ? nnodes : cap;
   if (to_freq)
-    PD_KLAUNCH((pd_rfft_pair_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH((pd_rfft_pair_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   else
-    PD_KLAUNCH((pd_rfft_pair_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH((pd_rfft_pair_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nnodes, h->twiddle, pl, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;
@@ -1278,7 +1278,7 @@ static int launch_rfft(pd_handle* h, const void* in, void* out, int64_t nlines, 
   do {                                                                                                  \
     auto k = pd_rfft_kernel<R0, R1, R2, R3, TF, GM>;                                                    \
     PD_SET_SMEM_ONCE(k, smem);                                                                          \
-    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, h->twiddle_half, gam, (int)(h->pdl && h->pdl_early));        \
+    PD_KLAUNCH(k, (unsigned)nblk, threads, smem, st, in, out, nlines, h->twiddle, h->twiddle_half, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));        \
   } while (0)
   if (to_freq) {
     if (gam) PD_RFFT_GO(true, true); else PD_RFFT_GO(true, false);
@@ -1390,9 +1390,9 @@ int pd_fft_launch(pd_handle* h, const cplx* in, cplx* out, int64_t nlines, int i
   int64_t nblk = nlines < (int64_t)h->num_sms * 8 ? nlines : (int64_t)h->num_sms * 8;
   double scale = inverse ? 1.0 / (double)N : 1.0;
   if (inverse)
-    PD_KLAUNCH((pd_fft_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH((pd_fft_generic_kernel<true>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   else
-    PD_KLAUNCH((pd_fft_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl && h->pdl_early));
+    PD_KLAUNCH((pd_fft_generic_kernel<false>), (unsigned)nblk, 256, smem, st, in, out, N, nlines, h->twiddle, pl, scale, gam, (int)(h->pdl ? (h->pdl_early & 1) : 0));
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;

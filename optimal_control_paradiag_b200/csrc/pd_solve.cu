@@ -52,7 +52,7 @@ template <bool AL>
 __global__ void __launch_bounds__(PD_KB, 4)
 pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* __restrict__ R1,
                       SolveParams sp, cplx* __restrict__ lastl) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 2) != 0);  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
@@ -71,7 +71,7 @@ pd_solve_passA_kernel(const cplx* __restrict__ w, cplx* __restrict__ F0, cplx* _
 // recurrences, emits f_c and the partial rhs of its trailing separator for level lev + 1.
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 4) != 0);  // programmatic dependent launch: see pd_common.cuh
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.kend) return;
   const KCoef kc = make_coef(freq_of(sp, kk), sp);
@@ -120,7 +120,7 @@ pd_solve_level_reduce_kernel(Levels lv, SolveParams sp, int lev) {
 // trailing separator) are overwritten by the solution in R[lev].
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_level_back_kernel(Levels lv, SolveParams sp, int lev) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 4) != 0);  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_LG][PD_KB];  // per-thread column of chunk pivots
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   if (kk >= sp.kend) return;
@@ -321,7 +321,7 @@ template <bool PUSH>
 __global__ void __launch_bounds__(PD_PCR_THREADS)
 pd_solve_pcr_kernel(Levels lv, SolveParams sp, int lev, int kpb, const cplx* __restrict__ w, SlabPtrs sl,
                     SlabCommDev cm) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 4) != 0);  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   __shared__ cplx c_off[32], c_dmain[32], c_dlast[32], c_offb[32];
   const int n = sp.rows[lev];
@@ -505,7 +505,7 @@ template <bool PUSH, int PD_IRING>
 __global__ void __launch_bounds__(4 * PD_ITK)
 pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__ piv, const cplx* __restrict__ w,
                              SlabPtrs sl, SlabCommDev cm) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 4) != 0);  // programmatic dependent launch: see pd_common.cuh
   extern __shared__ __align__(16) unsigned char pd_smem_raw[];
   __shared__ cplx xch[4 * PD_ITK][2];                                // meeting point: (last value, off * pivot)
   constexpr int NT = 4 * PD_ITK;
@@ -658,7 +658,7 @@ pd_solve_iface_thomas_kernel(Levels lv, SolveParams sp, const cplx* __restrict__
 template <bool SLAB, bool AL>
 __global__ void __launch_bounds__(PD_KB)
 pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, SolveParams sp, SlabPtrs sl) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 8) != 0);  // programmatic dependent launch: see pd_common.cuh
   __shared__ cplx mtab[PD_L][PD_KB];
   const int tid = threadIdx.x;
   const int kk = sp.koff + blockIdx.x * PD_KB + tid;
@@ -765,7 +765,7 @@ pd_solve_passB_kernel(cplx* __restrict__ w, const cplx* __restrict__ zsep, Solve
 
 // The same as a launch of its own, for the two-stream variant of the apply (after the join of both halves).
 __global__ void pd_slab_epoch_bump_kernel(unsigned long long* epoch, int pdl_early) {
-  pd_pdl_enter(pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((pdl_early & 16) != 0);  // programmatic dependent launch: see pd_common.cuh
   *epoch += 1ull;
 }
 
@@ -782,7 +782,7 @@ template <bool PUSH>
 __global__ void __launch_bounds__(PD_KB)
 pd_slab_functionals_kernel(const cplx* __restrict__ w, Levels lv, SolveParams sp, SlabPtrs sl,
                            cplx* __restrict__ out, SlabCommDev cm) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 4) != 0);  // programmatic dependent launch: see pd_common.cuh
   const int kk = sp.koff + blockIdx.x * PD_KB + threadIdx.x;
   const unsigned long long ep = PUSH ? *cm.epoch + 1ull : 0ull;
   if (kk < sp.kend) {
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(PD_KB)
 pd_slab_global_kernel(const cplx* __restrict__ gathered, int64_t gstride, SolveParams sp, SlabGeom sg,
                       const cplx* __restrict__ coef, cplx* __restrict__ zout, SlabCommDev cm,
                       cplx* __restrict__ zsep, const cplx* __restrict__ green) {
-  pd_pdl_enter(sp.pdl_early != 0);  // programmatic dependent launch: see pd_common.cuh
+  pd_pdl_enter((sp.pdl_early & 16) != 0);  // programmatic dependent launch: see pd_common.cuh
   // The correction sweep at the end touches rows of zsep / green that depend on nothing the peers send: its first
   // batch of rows is loaded HERE, so that the loads are in flight under the flag wait and the tiny separator solve
   // (the sweep used to be half of this kernel's time, one exposed DRAM round trip per row).
@@ -1071,7 +1071,7 @@ static void fill_params(pd_handle* h, SolveParams& sp, Levels& lv, SlabPtrs& sl,
   sp.freq_perm = h->cfg.N_t == 16384 && !half_spectrum;
   sp.al = h->cfg.alpha != 1.0;
   sp.lna = log(h->cfg.alpha) / (double)h->cfg.N_t;
-  sp.pdl_early = h->pdl && h->pdl_early;
+  sp.pdl_early = h->pdl ? h->pdl_early : 0;
   for (int l = 0; l < PD_MAX_LEVELS; ++l) sp.rows[l] = pl->rows[l];
   for (int l = 0; l < PD_MAX_LEVELS; ++l) { lv.R[l] = pl->R[l]; lv.F[l] = pl->F[l]; }
   sl.lastl = pl->lastl; sl.green = half_spectrum ? pl->green_h : pl->green; sl.zout = pl->zout;
@@ -1548,7 +1548,7 @@ int pd_slab_reduce_launch(pd_handle* h, cplx* w, cplx* out, cudaStream_t st, int
 
 int pd_slab_epoch_bump_launch(pd_handle* h, cudaStream_t st) {
   SolvePlan* pl = plan_of(h);
-  PD_KLAUNCH(pd_slab_epoch_bump_kernel, 1, 1, 0, st, pl->comm_epoch, h->pdl_early);
+  PD_KLAUNCH(pd_slab_epoch_bump_kernel, 1, 1, 0, st, pl->comm_epoch, h->pdl ? h->pdl_early : 0);
   PD_CHECK_LAUNCH();
   h->launches++;
   return PD_OK;

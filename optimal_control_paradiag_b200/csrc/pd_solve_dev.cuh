@@ -30,7 +30,7 @@ struct SolveParams {
   int c0, c1;     // level-0 chunk range [c0, c1) this launch of pass A / pass B works on (all: 0, rows[1] + 1)
   int al;         // 1: alpha != 1 (extension, see make_coef<true>); 0: the upstream operator
   double lna;     // ln(alpha) / N_t
-  int pdl_early;  // 1: kernels release their programmatic-launch dependents at their first instruction (pd_common.cuh)
+  int pdl_early;  // bit mask: which kernels release their programmatic-launch dependents at once (pd_handle::pdl_early)
 };
 
 // Slab-mode extras (device pointers; all null in single-GPU mode)
