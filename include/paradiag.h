@@ -59,9 +59,10 @@ typedef struct pd_config {
                           Other values are an EXTENSION with no upstream pin (the
                           reference has no alpha): Gamma_alpha time weights around
                           the FFTs and alpha-shifted symbols in the per-frequency
-                          stage, defined in oracle/pc_alpha.py.  Single-GPU complex
-                          apply / GMRES only; sharded handles, the real-input path
-                          and pd_pc_matvec return PD_ERR_UNSUPPORTED.            */
+                          stage, defined in oracle/pc_alpha.py.  Available on the
+                          single-GPU and slab-mode applies (complex and real-input)
+                          and GMRES; frequency-sharded stage handles (k_count /
+                          n_local) and pd_pc_matvec return PD_ERR_UNSUPPORTED.    */
   int32_t device;      /* CUDA device ordinal                                    */
   /* Frequency shard solved by this handle in pd_stage_solve (multi-GPU):
    * global frequencies [k_begin, k_begin + k_count).  k_count = 0 means all.   */
