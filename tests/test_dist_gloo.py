@@ -18,9 +18,13 @@ class OracleStageBackend:
     """pd_stage_fft / pd_stage_solve semantics on CPU tensors, from the oracle's fast route."""
     launch_count = 0
 
-    def __init__(self, N_x, N_t, T, gamma, k_begin=0, k_count=0, n_local=0, slab_rank=0, slab_count=0):
+    def __init__(self, N_x, N_t, T, gamma, k_begin=0, k_count=0, n_local=0, slab_rank=0, slab_count=0, alpha=1.0):
         from oracle.pc_fast import DiagFFTPCFast
         self.pc = DiagFFTPCFast(N_x, N_t, T, gamma, workers=1)
+        self.cf = None                                   # alpha != 1 (extension): oracle/pc_alpha.py's closed form
+        if alpha != 1.0:
+            from oracle.pc_alpha import decoupled_coeffs
+            self.cf = decoupled_coeffs(N_x, N_t, T, gamma, alpha)
         self.N_t, self.n = N_t, N_x + 1
         k_count = k_count or N_t
         self.ks = slice(k_begin, k_begin + k_count)
@@ -35,12 +39,20 @@ class OracleStageBackend:
     def _rot_in(self, W, kidx=None):
         pc = self.pc
         kidx = np.arange(self.N_t) if kidx is None else kidx
+        if self.cf is not None:
+            cf = self.cf
+            rp = cf["gp"][kidx] * W[0] + cf["e"][kidx] * W[1]
+            rm = cf["gm"][kidx] * W[0] - cf["e"][kidx] * W[1]
+            return rp, np.conj(rm)
         uz = W[0] * np.conj(pc.z[kidx])
         ip = (1j * pc.sigma[kidx]) * W[1]
         return (uz + ip) / 2, np.conj((uz - ip) / 2)          # slot +, conj slot -
 
+    def _ab(self, k):
+        return (self.cf["off"][k], self.cf["diag"][k]) if self.cf is not None else (self.pc.a[k], self.pc.b[k])
+
     def _T(self, m, k):
-        a, b = self.pc.a[k], self.pc.b[k]
+        a, b = self._ab(k)
         return (np.diag(np.full(m, b)) + np.diag(np.full(m - 1, a), 1) + np.diag(np.full(m - 1, a), -1))
 
     def slab_reduce(self, w, out, kidx=None):
@@ -129,7 +141,7 @@ class OracleStageBackend:
         rP, rM = self._rot_in(W, kidx)
         m = self.body[r]
         for col, k in enumerate(kidx):
-            a, b = pc.a[k], pc.b[k]
+            a, b = self._ab(k)
             inv = [np.linalg.inv(self._T(ms, k)) for ms in self.body]
             A = np.zeros((G - 1, G - 1), complex)
             rhs = np.zeros((G - 1, 2), complex)
@@ -154,8 +166,12 @@ class OracleStageBackend:
             zM = np.zeros(self.n_r, complex)
             zP[1:1 + m], zM[1:1 + m] = out[0], np.conj(out[1])
             zP[0], zM[0] = zl[0], np.conj(zl[1])
-            W[0, :, col] = zP + zM
-            W[1, :, col] = (-1j * pc.sigma[k] * pc.z[k]) * (zP - zM)
+            if self.cf is not None:
+                W[0, :, col] = self.cf["eic"][k] * (zP + zM)
+                W[1, :, col] = 1j * (self.cf["bmd"][k] * zP + self.cf["bpd"][k] * zM)
+            else:
+                W[0, :, col] = zP + zM
+                W[1, :, col] = (-1j * pc.sigma[k] * pc.z[k]) * (zP - zM)
 
     def stage_fft(self, src, dst, nlines, inverse):
         import scipy.fft as sfft
@@ -249,6 +265,41 @@ def test_slab_mode_real_input_apply_matches_single_process_oracle(world, N_x, N_
     mp.spawn(_real_worker, args=(world, _free_port(), N_x, N_t, 0.5, ret), nprocs=world, join=True)
     for r in range(world):
         assert ret[r] < 1e-11, (r, ret[r])
+
+
+def _alpha_worker(rank, world, port, N_x, N_t, alpha, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pc_alpha import DiagFFTPCAlpha
+        factory = lambda **kw: OracleStageBackend(N_x, N_t, 2.0, 1.0, alpha=alpha, **kw)
+        dpc = DistributedDiagFFTPC(N_x, N_t, T=2.0, gamma=1.0, backend_factory=factory, mode="slab", alpha=alpha)
+        rng = np.random.default_rng(2)
+        size = 2 * (N_x + 1) * N_t
+        xg = rng.standard_normal(size) + 1j * rng.standard_normal(size)
+        ref = DiagFFTPCAlpha(N_x, N_t, 2.0, 1.0, alpha).apply(xg)
+        x_local = dpc.scatter_from_global(torch.from_numpy(xg))
+        x_keep = x_local.clone()
+        yg = dpc.gather_to_global(dpc.apply(x_local)).numpy()
+        assert torch.equal(x_local, x_keep)                                   # the input block is not scaled in place
+        xr = rng.standard_normal(size)
+        refr = DiagFFTPCAlpha(N_x, N_t, 2.0, 1.0, alpha).apply(xr + 0j).real
+        yr = dpc.gather_to_global(dpc.apply_real(dpc.scatter_from_global(torch.from_numpy(xr))).to(torch.complex128))
+        ret[rank] = (float(np.linalg.norm(yg - ref) / np.linalg.norm(ref)),
+                     float(np.linalg.norm(yr.numpy().real - refr) / np.linalg.norm(refr)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N_x,N_t,alpha", [(2, 16, 8, 0.5), (3, 22, 16, 1e-2)])
+def test_slab_mode_alpha_extension_matches_single_process_oracle(world, N_x, N_t, alpha):
+    # alpha != 1 (no upstream counterpart) through the collective transport: Gamma / Gamma^-1 as elementwise products
+    # around the slab-distributed solve, complex and real-input applies, against oracle/pc_alpha.py
+    ret = mp.Manager().dict()
+    mp.spawn(_alpha_worker, args=(world, _free_port(), N_x, N_t, alpha, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r][0] < 1e-10 and ret[r][1] < 1e-10, (r, ret[r])
 
 
 @pytest.mark.parametrize("world,N_x,N_t", [(2, 16, 6), (3, 22, 5)])
