@@ -878,7 +878,9 @@ pd_rfft_kernel(const void* __restrict__ in_, void* __restrict__ out_, int64_t nl
 static void factorize(int N, PassList& pl) {
   pl.n = 0;
   int rem = N;
-  const int pref[] = {16, 8, 4, 2, 3, 5, 7};
+  // (9 before 3: N_t = 81, the upstream default, becomes two radix-9 passes instead of four radix-3 passes -- the
+  // generic kernel's cost is its block barriers and index arithmetic per pass, not the 9-term sums)
+  const int pref[] = {16, 8, 4, 2, 9, 3, 5, 7};
   for (int f : pref)
     while (rem % f == 0 && rem > 1 && pl.n < PD_MAX_FFT_PASSES - 1) {
       pl.r[pl.n++] = f;
