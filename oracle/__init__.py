@@ -31,28 +31,30 @@ What it restates (all citations are into the read-only upstream checkout,
 * ``pc_alpha``     the alpha EXTENSION (no upstream counterpart): explicit P_alpha,
                    per-frequency block LU, decoupled closed form.
 
-PARITY UNPINNED, except for everything of the reference that runs without
-Firedrake.  The upstream repository holds no golden vectors, fixtures or recorded
-logs for PC-apply outputs or GMRES iteration counts, and none of Firedrake /
-petsc4py / MUMPS is installable in this image, so ``DiagFFTPC.apply`` and the
-Krylov solve themselves cannot be run.  Pinned against EXECUTED upstream code
-(the generators read the upstream files at generation time, run the lines
+PARITY PINNED AGAINST EXECUTED UPSTREAM CODE, with one stated substitution.  The upstream repository holds no golden
+vectors, fixtures or recorded logs, and none of Firedrake / petsc4py / MUMPS is installable in this image, so the
+script cannot run as it is.  What runs (the generators read the upstream files at generation time, execute the lines
 unmodified and store numerical outputs only):
 
-* the eigen-set-up stage :387-436 (Lambda_1, Lambda_2, the per-frequency
-  ``eig`` / ``inv`` loop): ``tests/golden/make_reference_setup_golden.py``;
-  ``eigs`` reproduces it bit for bit and every route agrees with the
-  line-by-line route driven by those arrays
+* the two CLASSES of ``Code/Control_Wave_PC.py`` -- ``Optimal_Control_Wave_Equation`` (:13-179: ``__init__``,
+  ``Build_f``, ``Build_g``, ``Build_Initial_Condition``, ``Build_L``) and ``DiagFFTPC`` (:376-558: ``initialize``,
+  ``update``, ``apply``, ``applyTranspose``) -- executed with ``fd`` bound to ``tests/golden/firedrake_standin.py``,
+  which supplies only the textbook part (P1 mass / stiffness on the uniform interval, UFL forms affine in their
+  coefficient functions, homogeneous Dirichlet rows, sparse LU instead of MUMPS, the mixed-vector layout) and nothing
+  that knows about the preconditioner: ``tests/golden/make_reference_executed_golden.py``.
+  ``tests/test_reference_executed_golden.py`` pins every route of ``DiagFFTPC.apply`` here to the executed apply
+  (2e-14 ... 1.5e-12), ``operator.AllAtOnce`` to the executed forms (right-hand side and matvec to 2e-16, the
+  1/2-weight rows and the :138 quirk included), the direct baseline, and GMRES (same counts -- 5 at the upstream
+  constants -- and residual histories to 1e-12 when ``gmres`` runs on the executed operator with the executed apply);
+  ``tests/test_gpu_reference_executed.py`` does the same for the CUDA path;
+* the eigen-set-up stage :387-436 on its own (Lambda_1, Lambda_2, the per-frequency ``eig`` / ``inv`` loop):
+  ``tests/golden/make_reference_setup_golden.py``; ``eigs`` reproduces it bit for bit
   (``tests/test_reference_setup_golden.py``);
-* the whole known-answer notebook ``Code/mat_test.ipynb`` (cells executed from
-  its JSON) and the closed forms of ``Code/pre_cond.py:32-38``:
-  ``tests/golden/make_reference_notebook_golden.py``;
-  ``tests/test_reference_notebook_golden.py`` pins ``eigs.lambdas``,
-  ``eigs.closed_form``, the FFT / circulant conventions and the numpy eig route
-  to them (``tests/test_oracle_notebook.py`` re-derives the same identities).
+* the whole known-answer notebook ``Code/mat_test.ipynb`` (cells executed from its JSON) and the closed forms of
+  ``Code/pre_cond.py:32-38``: ``tests/golden/make_reference_notebook_golden.py``,
+  ``tests/test_reference_notebook_golden.py``.
 
-Unpinned (restated from the source, checked only against itself -- three
-independent routes agreeing to ~1e-13 at small sizes): the P1 mass / stiffness
-assembly, the shifted solves with Dirichlet rows, the operator / right-hand
-side of ``Build_L`` / ``Build_f/g/IC`` and PETSc's GMRES semantics.
+Still UNPINNED (restated from documentation, checked only against itself): what the stand-in replaces -- Firedrake's
+assembly of P1 forms and its boundary-condition handling, MUMPS -- and PETSc's KSPGMRES (``gmres`` restates the
+semantics the options :347-359 select; the fixtures above run that restatement on executed operators).
 """
