@@ -136,7 +136,7 @@ class Scal:
 
 
 def Constant(v):
-    return Scal(v)
+    return Scal(v.value if isinstance(v, Scal) else v)
 
 
 class Nodal:
@@ -471,8 +471,10 @@ class MixedTrial:
 
 
 def TestFunction(space):
+    if space.kind == "CG1":
+        return Test("scalar", None)         # upstream's solve() builds (and never assembles) a few scalar check forms
     if space.kind != "MIXED":
-        raise NotImplementedError("stand-in: test functions of the mixed space only")
+        raise NotImplementedError("stand-in: test functions of the mixed or the scalar P1 space only")
     return MixedTest(space)
 
 
@@ -506,6 +508,10 @@ class Form:
         self.terms += [(-c, l, t) for c, l, t in o.terms]
         return self
     def __neg__(self): return Form([(-c, l, t) for c, l, t in self.terms])
+    def __rmul__(self, o):
+        v = _num(o)
+        return NotImplemented if v is None else Form([(v * c, l, t) for c, l, t in self.terms])
+    __mul__ = __rmul__
 
 
 class _Integrand:
@@ -513,8 +519,17 @@ class _Integrand:
         self.pairs = pairs                  # [(Lin | mixed Function, Test | MixedTest)]
 
     def __mul__(self, measure):
-        assert measure is dx
-        return Form([(1.0, l, t) for l, t in self.pairs])
+        if measure is dx:
+            return Form([(getattr(self, "scale", 1.0), l, t) for l, t in self.pairs])
+        return self.__rmul__(measure)
+
+    def __rmul__(self, o):                  # scalar * inner(...) [* dx]
+        v = _num(o)
+        if v is None:
+            return NotImplemented
+        out = _Integrand(self.pairs)
+        out.scale = getattr(self, "scale", 1.0) * v
+        return out
 
 
 class _Measure:
@@ -551,8 +566,8 @@ def assemble(form, bcs=None):
 
 class DirichletBC:
     def __init__(self, subspace, value, where):
-        assert where == "on_boundary" and isinstance(subspace, SubSpace)
-        self.field = subspace.index
+        assert where == "on_boundary"
+        self.field = subspace.index if isinstance(subspace, SubSpace) else None
 
 
 # --------------------------------------------------------------------------------------------------- assembly
@@ -646,6 +661,37 @@ class NonlinearVariationalProblem:
     def affine_system(self):
         """The residual of this script is affine in U: F(U; v) = A U - b.  (``snes_type ksponly`` solves A U = b.)"""
         return assemble_affine(self.F, self.u.space, self.u, self.bcs)
+
+
+class NonlinearVariationalSolver:
+    """``snes_type ksponly`` from the zero initial guess: one linear solve of A U = b.  ``pc_type lu`` -> sparse LU
+    (upstream: MUMPS).  ``pc_type python`` -> the class named by ``pc_python_type`` is instantiated, initialised and
+    used as left preconditioner of the Krylov loop the driver script injected as ``ksp`` (PETSc's KSPGMRES is not
+    runnable here; the driver passes its restatement together with PETSc's defaults for what the options leave open)."""
+    python_pcs = {}        # class name -> class, registered by the driver script
+    ksp = None             # callable(matvec, pc_apply, b, options) -> (x, iterations, history, reason)
+    last = None            # (iterations, history, reason) of the latest Krylov solve
+
+    def __init__(self, problem, solver_parameters=None):
+        self.problem, self.params = problem, dict(solver_parameters or {})
+
+    def solve(self):
+        pr = self.problem
+        A, b = pr.affine_system()
+        if self.params.get("pc_type") == "python":
+            cls = type(self).python_pcs[self.params["pc_python_type"].split(".")[-1]]
+            pc = cls()
+            pc.initialize(None)
+
+            def pc_apply(x):
+                xv, yv = HostVec(x), HostVec(np.zeros(b.size))
+                pc.apply(None, xv, yv)
+                return yv.array.copy()
+            x, its, hist, reason = type(self).ksp(lambda z: A @ z, pc_apply, b, self.params)
+            type(self).last = (its, hist, reason)
+        else:
+            x = spla.splu(A.tocsc()).solve(b)
+        Dat._View(pr.u).setArray(x)
 
 
 class PCBase:

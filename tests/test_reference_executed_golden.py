@@ -108,3 +108,25 @@ def test_standin_matrices_are_the_p1_matrices_of_the_oracle():
     # exactness for P1: integral of a linear function times a hat function
     x = mesh.coords
     assert np.isclose(np.ones_like(x) @ (mesh.M @ x), 0.5) and np.isclose(x @ (mesh.K @ x), 1.0)
+
+
+def test_executed_upstream_script_flow_for_the_accuracy_study():
+    # tests/golden/upstream_accuracy.json: equ.solve(...) + equ.write(...) of the upstream script executed for
+    # N = 5 ... 70 (both branches).  Non-binding numbers (write / plot.py are outside the hot path); pinned here:
+    # the solve itself -- 5 GMRES iterations at every N, pc and LU branches agreeing, and the oracle's direct
+    # solution having the norm the executed solve produced.
+    import json
+    tab = json.load(open(os.path.join(GOLDEN, "upstream_accuracy.json")))["table"]
+    assert sorted(int(k) for k in tab) == list(range(5, 75, 5))
+    for k, row in tab.items():
+        N = int(k)
+        assert row["gmres_its"] == 5 and row["gmres_reason"] == "CONVERGED_RTOL"
+        assert abs(row["pc_u_norm"] - row["lu_u_norm"]) < 1e-9 * row["lu_u_norm"]
+        if N < 25:       # write() reads nodal entry 25 (:281-282): the committed script cannot run these sizes
+            assert str(row["pc"]).startswith("IndexError") and str(row["lu"]).startswith("IndexError")
+        else:
+            assert abs(row["pc"] - row["lu"]) < 1e-8 * row["lu"]
+            assert row["lu"] > 5 * row["plot_py"]    # the committed script does not reproduce plot.py:5-18
+    for N in (10, 25, 40):
+        u = AllAtOnce(N, N, 2.0, 1.0).direct_solve().reshape(2, N + 1, N)[0]
+        assert abs(np.linalg.norm(u) - tab[str(N)]["lu_u_norm"]) < 1e-9 * tab[str(N)]["lu_u_norm"]
